@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE — CPU oracle (numpy f64 + OpenCV) for the geometry stages.  Never imported by the product.
+
+  undistort_points      sfm/geometry.py:103-118  -> cv2.undistortPoints(pts, K, dist, None, K), cast to f32.
+                        OpenCV (third party, unpinned in pyproject.toml:22; 4.13.0 here) is the reference's own
+                        arithmetic for this call, so the oracle calls it directly; `undistort_points_np` restates
+                        OpenCV's published algorithm (5 fixed-point iterations of the Brown model) for the
+                        stopping rule the CUDA kernel mirrors.
+  iterative_ls          thirdparty/triangulation.py:79-177 (vectorised over points; 4x3 LS solve per iteration;
+                        NOTE the reference re-scales A and b *cumulatively* every iteration, :157-160)
+  linear_dlt            sfm/triangulation.py:154-183 (6x6 SVD null vector, dehomogenised)
+  fundamental_magsac    matching/geometric_verification.py:89-92 -> cv2.findFundamentalMat(USAC_MAGSAC, 0.5, 0.999, 100000)
+  sampson_error / symmetric epipolar distance: used by tests to compare inlier sets geometrically.
+Pinned against the reference itself by tests/test_oracle_vs_golden.py.
+"""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+
+
+def undistort_points(pts: np.ndarray, K: np.ndarray, dist: np.ndarray) -> np.ndarray:
+    return cv2.undistortPoints(pts, K, dist, None, K)[:, 0, :].astype("float32")
+
+
+def undistort_points_np(pts: np.ndarray, K: np.ndarray, dist: np.ndarray, iters: int = 5) -> np.ndarray:
+    """OpenCV's cvUndistortPointsInternal with default criteria (5 iterations), k1,k2,p1,p2,k3 model, f64."""
+    k1, k2, p1, p2, k3 = [float(v) for v in np.asarray(dist).ravel()[:5]]
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    x0 = (pts[:, 0].astype(np.float64) - cx) / fx
+    y0 = (pts[:, 1].astype(np.float64) - cy) / fy
+    x, y = x0.copy(), y0.copy()
+    for _ in range(iters):
+        r2 = x * x + y * y
+        icdist = 1.0 / (1 + ((k3 * r2 + k2) * r2 + k1) * r2)
+        dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+        dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+        x = (x0 - dx) * icdist
+        y = (y0 - dy) * icdist
+    return np.stack([x * fx + cx, y * fy + cy], 1).astype("float32")
+
+
+def iterative_ls(u1: np.ndarray, P1: np.ndarray, u2: np.ndarray, P2: np.ndarray, tol: float = 3e-5):
+    """Returns (X [N,3] f64, status [N] int) with the reference's status codes."""
+    u1 = np.asarray(u1, dtype=np.float64)
+    u2 = np.asarray(u2, dtype=np.float64)
+    n = len(u1)
+    X = np.zeros((n, 3))
+    status = np.zeros(n, dtype=int)
+    for i in range(n):
+        rows, rhs = [], []
+        for (u, P) in ((u1[i], P1), (u2[i], P2)):
+            rows.append(u[0] * P[2, :3] - P[0, :3])
+            rows.append(u[1] * P[2, :3] - P[1, :3])
+            rhs.append(-(u[0] * P[2, 3] - P[0, 3]))
+            rhs.append(-(u[1] * P[2, 3] - P[1, 3]))
+        A, b = np.array(rows), np.array(rhs)
+        d1 = d2 = 1.0
+        for it in range(10):
+            x = np.linalg.lstsq(A, b, rcond=None)[0]
+            d1n = P1[2, :3] @ x + P1[2, 3]
+            d2n = P2[2, :3] @ x + P2[2, 3]
+            if abs(d1n - d1) <= tol and abs(d2n - d2) <= tol:
+                break
+            A[:2] /= d1n
+            b[:2] /= d1n
+            A[2:] /= d2n
+            b[2:] /= d2n
+            d1, d2 = d1n, d2n
+        X[i] = x
+        st = int(d1n > 0 and d2n > 0)          # `i < 10` in the reference is always true
+        if d1n <= 0:
+            st -= 1
+        if d2n <= 0:
+            st -= 2
+        status[i] = st
+    return X, status
+
+
+def linear_dlt(x1: np.ndarray, P1: np.ndarray, x2: np.ndarray, P2: np.ndarray) -> np.ndarray:
+    """x1,x2 [N,2] undistorted pixels -> X [N,3] f64."""
+    out = np.zeros((len(x1), 3))
+    for i in range(len(x1)):
+        M = np.zeros((6, 6))
+        M[:3, :4], M[3:, :4] = P1, P2
+        M[:3, 4] = -np.array([x1[i, 0], x1[i, 1], 1.0])
+        M[3:, 5] = -np.array([x2[i, 0], x2[i, 1], 1.0])
+        V = np.linalg.svd(M)[-1]
+        out[i] = V[-1, :3] / V[-1, 3]
+    return out
+
+
+def fundamental_magsac(m0: np.ndarray, m1: np.ndarray):
+    F, inl = cv2.findFundamentalMat(m0, m1, cv2.USAC_MAGSAC, 0.5, 0.999, 100000)
+    return F, (inl > 0).squeeze()
+
+
+def sampson_distance(F: np.ndarray, m0: np.ndarray, m1: np.ndarray) -> np.ndarray:
+    """sqrt of the Sampson error, pixels."""
+    x0 = np.concatenate([m0.astype(np.float64), np.ones((len(m0), 1))], 1)
+    x1 = np.concatenate([m1.astype(np.float64), np.ones((len(m1), 1))], 1)
+    Fx0 = x0 @ F.T
+    Ftx1 = x1 @ F
+    num = np.sum(x1 * Fx0, 1) ** 2
+    den = Fx0[:, 0] ** 2 + Fx0[:, 1] ** 2 + Ftx1[:, 0] ** 2 + Ftx1[:, 1] ** 2
+    return np.sqrt(num / den)

@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+The reference's own tests hold no golden vectors for this path, so these fixtures — outputs
+of the reference code itself on seeded inputs with the seeded weights of icepy4d_b200/weights.py — are what
+pins the oracle (tests/test_oracle_vs_golden.py) and, through it, the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from icepy4d_b200 import synthetic, weights  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _t(img):
+    return torch.tensor(img / 255.0, dtype=torch.float)[None, None]
+
+
+def golden_superpoint_superglue():
+    sp_sd, sg_sd = weights.make_superpoint_state(1), weights.make_superglue_state(2)
+    i0, i1 = synthetic.stereo_pair(240, 320, seed=1000, shift=(16, 24), channels=1)
+    sp = ref_shims.build_reference_superpoint_sg({"nms_radius": 3, "keypoint_threshold": 1e-4, "max_keypoints": 256}, sp_sd)
+    sg = ref_shims.build_reference_superglue({"weights": "outdoor", "sinkhorn_iterations": 20, "match_threshold": 0.2}, sg_sd)
+    from icepy4d.thirdparty.SuperGlue.models.superpoint import simple_nms
+    with torch.inference_mode():
+        p0, p1 = sp({"image": _t(i0)}), sp({"image": _t(i1)})
+        # the NMS'd score map itself (reference function applied to the reference's own score tensor)
+        x = _t(i0)
+        for a, b in (("conv1a", "conv1b"), ("conv2a", "conv2b"), ("conv3a", "conv3b"), ("conv4a", "conv4b")):
+            x = sp.relu(getattr(sp, b)(sp.relu(getattr(sp, a)(x))))
+            if a != "conv4a":
+                x = sp.pool(x)
+        logits = sp.convPb(sp.relu(sp.convPa(x)))
+        sc = torch.softmax(logits, 1)[:, :-1]
+        b_, _, h, w = sc.shape
+        sc = sc.permute(0, 2, 3, 1).reshape(b_, h, w, 8, 8).permute(0, 1, 3, 2, 4).reshape(b_, h * 8, w * 8)
+        nms = simple_nms(sc, 3)[0]
+        data = {"image0": _t(i0), "image1": _t(i1),
+                "keypoints0": torch.stack(p0["keypoints"]), "keypoints1": torch.stack(p1["keypoints"]),
+                "scores0": torch.stack(p0["scores"]), "scores1": torch.stack(p1["scores"]),
+                "descriptors0": torch.stack(p0["descriptors"]), "descriptors1": torch.stack(p1["descriptors"])}
+        out = sg(data)
+    np.savez_compressed(
+        os.path.join(OUT, "sp_sg_small.npz"), image0=i0, image1=i1, logits0=logits[0].numpy(),
+        nms0=nms.numpy(),
+        kpts0=p0["keypoints"][0].numpy(), kpts1=p1["keypoints"][0].numpy(),
+        scores0=p0["scores"][0].numpy(), scores1=p1["scores"][0].numpy(),
+        desc0=p0["descriptors"][0].numpy(), desc1=p1["descriptors"][0].numpy(),
+        matches0=out["matches0"][0].numpy(), matches1=out["matches1"][0].numpy(),
+        mscores0=out["matching_scores0"][0].numpy(), mscores1=out["matching_scores1"][0].numpy())
+    print("sp_sg_small: kpts", len(p0["keypoints"][0]), len(p1["keypoints"][0]), "matches", int((out["matches0"] > -1).sum()))
+
+
+def golden_lightglue():
+    sp_sd = weights.make_superpoint_state(1)
+    i0, i1 = synthetic.stereo_pair(240, 320, seed=1001, shift=(8, 16), channels=1)
+    for tag, conf_layers, prune, kw in (("plain", (), False, {}), ("adaptive", (2, 3, 4, 5, 6, 7), False, {}),
+                                        ("prune", (), True, {"depth_confidence": -1})):
+        lg_sd = weights.make_lightglue_state(3, confident_layers=conf_layers, prune_variant=prune)
+        sp = ref_shims.build_reference_superpoint_lg(sp_sd, max_num_keypoints=256)
+        lg = ref_shims.build_reference_lightglue(lg_sd, **kw)
+        with torch.inference_mode():
+            f0 = sp.extract(torch.tensor(i0 / 255.0, dtype=torch.float)[None], resize=None)
+            f1 = sp.extract(torch.tensor(i1 / 255.0, dtype=torch.float)[None], resize=None)
+            out = lg({"image0": f0, "image1": f1})
+        np.savez_compressed(
+            os.path.join(OUT, f"lg_{tag}.npz"), image0=i0, image1=i1,
+            kpts0=f0["keypoints"][0].numpy(), kpts1=f1["keypoints"][0].numpy(),
+            scores0=f0["keypoint_scores"][0].numpy(), scores1=f1["keypoint_scores"][0].numpy(),
+            desc0=f0["descriptors"][0].numpy(), desc1=f1["descriptors"][0].numpy(),
+            size0=f0["image_size"][0].numpy(), size1=f1["image_size"][0].numpy(),
+            matches0=out["matches0"][0].numpy(), matches1=out["matches1"][0].numpy(),
+            mscores0=out["matching_scores0"][0].numpy(), mscores1=out["matching_scores1"][0].numpy(),
+            matches=out["matches"][0].numpy(), scores=out["scores"][0].numpy(), stop=np.int64(out["stop"]),
+            prune0=out["prune0"][0].numpy(), prune1=out["prune1"][0].numpy(),
+            confident_layers=np.array(conf_layers, dtype=np.int64), prune_variant=np.bool_(prune),
+            depth_confidence=np.float64(kw.get("depth_confidence", 0.95)))
+        print(f"lg_{tag}: kpts", f0["keypoints"].shape[1], f1["keypoints"].shape[1], "matches",
+              len(out["matches"][0]), "stop", out["stop"],
+              "prune0 min/max", int(out["prune0"].min()), int(out["prune0"].max()))
+
+
+def golden_matchers():
+    """Whole-plugin goldens: SuperGlueMatcher.match / LightGlueMatcher.match with GRID tiling + MAGSAC."""
+    ref_shims.install_shims()
+    import icepy4d.matching.matchers as M
+    from icepy4d.matching import GeometricVerification, Quality, TileSelection
+
+    sp_sd, sg_sd, lg_sd = weights.make_superpoint_state(1), weights.make_superglue_state(2), weights.make_lightglue_state(3)
+    i0, i1 = synthetic.stereo_pair(480, 640, seed=1002, shift=(16, 8), channels=3)
+    with ref_shims.no_checkpoint_loading():
+        m = M.SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": 512,
+                                "match_threshold": 0.2, "force_cpu": True, "sinkhorn_iterations": 20})
+    m.matcher.superpoint.load_state_dict(sp_sd)
+    m.matcher.superglue.load_state_dict(sg_sd)
+    m.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.GRID, grid=[2, 2], overlap=40,
+            geometric_verification=GeometricVerification.NONE)
+    sg_all = (m.mkpts0.copy(), m.mkpts1.copy(), m.scores0.copy(), m.mconf.copy())
+    m.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.GRID, grid=[2, 2], overlap=40,
+            geometric_verification=GeometricVerification.MAGSAC)
+    sg_gv = (m.mkpts0.copy(), m.mkpts1.copy())
+    m.match(i0, i1, quality=Quality.MEDIUM, tile_selection=TileSelection.GRID, grid=[1, 1], overlap=0,
+            geometric_verification=GeometricVerification.NONE)
+    sg_med = (m.mkpts0.copy(), m.mkpts1.copy())
+
+    # LightGlueMatcher re-instantiates both nets on every call (matchers.py:1256-1258): patch the constructors
+    import icepy4d.thirdparty.LightGlue.lightglue as LGpkg
+    o_sp, o_lg = LGpkg.SuperPoint, LGpkg.LightGlue
+    LGpkg.SuperPoint = lambda **kw: ref_shims.build_reference_superpoint_lg(sp_sd, **kw)
+    LGpkg.LightGlue = lambda features="superpoint", **kw: ref_shims.build_reference_lightglue(lg_sd, **kw)
+    try:
+        lm = M.LightGlueMatcher({"features": "superpoint", "force_cpu": True})
+        lm.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.GRID, grid=[2, 2], overlap=40,
+                 max_keypoints=512, geometric_verification=GeometricVerification.NONE)
+        lg_all = (lm.mkpts0.copy(), lm.mkpts1.copy(), lm.mconf.copy())
+    finally:
+        LGpkg.SuperPoint, LGpkg.LightGlue = o_sp, o_lg
+    np.savez_compressed(os.path.join(OUT, "matchers.npz"), image0=i0, image1=i1,
+                        sg_mkpts0=sg_all[0], sg_mkpts1=sg_all[1], sg_scores0=sg_all[2], sg_mconf=sg_all[3],
+                        sg_gv_mkpts0=sg_gv[0], sg_gv_mkpts1=sg_gv[1],
+                        sg_med_mkpts0=sg_med[0], sg_med_mkpts1=sg_med[1],
+                        lg_mkpts0=lg_all[0], lg_mkpts1=lg_all[1], lg_mconf=lg_all[2])
+    print("matchers: SG", len(sg_all[0]), "SG+GV", len(sg_gv[0]), "SG medium", len(sg_med[0]), "LG", len(lg_all[0]))
+
+
+def golden_tiler_quality():
+    ref_shims.install_shims()
+    import cv2
+    from icepy4d.matching.tiling import Tiler
+
+    rows = []
+    for (h, w, grid, ov, org) in [(4000, 6000, [2, 3], 0, [0, 0]), (4000, 6000, [3, 4], 0, [0, 0]),
+                                  (4008, 6012, [3, 2], 200, [0, 0]), (1000, 1500, [1, 1], 0, [0, 0]),
+                                  (480, 640, [2, 2], 40, [0, 0]), (4000, 6000, [2, 3], 100, [50, 30]),
+                                  (2250, 3350, [2, 2], 0, [0, 0])]:
+        lims, _ = Tiler(grid=grid, overlap=ov, origin=org).compute_limits_by_grid(np.zeros((h, w), np.uint8))
+        for k in sorted(lims):
+            rows.append([h, w, grid[0], grid[1], ov, org[0], org[1], int(k), *[int(v) for v in lims[k]]])
+    img = synthetic.blurred_noise(123, 201, 5)
+    img3 = np.repeat(img[:, :, None], 3, 2)
+    np.savez_compressed(os.path.join(OUT, "tiler_quality.npz"), tiler=np.array(rows, dtype=np.int64), img=img,
+                        pyrdown=cv2.pyrDown(img3), pyrdown2=cv2.pyrDown(cv2.pyrDown(img3)), pyrup=cv2.pyrUp(img3),
+                        gray=cv2.cvtColor(img3, cv2.COLOR_RGB2GRAY))
+    print("tiler_quality: rows", len(rows))
+
+
+def golden_geometry():
+    ref_shims.install_shims()
+    from icepy4d.matching import GeometricVerification, geometric_verification
+    from icepy4d.sfm import Triangulate
+
+    sc = synthetic.two_view_scene(n=3000, seed=7)
+    cams = sc["cams"]
+    F, mask = geometric_verification(sc["pts0"], sc["pts1"], method=GeometricVerification.MAGSAC)
+    inl = sc["inlier"]
+    tri = Triangulate(cams, [sc["pts0"][inl][:600], sc["pts1"][inl][:600]])
+    X_it = tri.triangulate_two_views().copy()
+    from icepy4d.sfm.geometry import undistort_points
+    from icepy4d.thirdparty.triangulation import iterative_LS_triangulation
+    u0 = undistort_points(sc["pts0"][inl][:600], cams[0])
+    u1 = undistort_points(sc["pts1"][inl][:600], cams[1])
+    _, status = iterative_LS_triangulation(u0, cams[0].P, u1, cams[1].P)
+    X_lin = Triangulate(cams, [sc["pts0"][inl][:600], sc["pts1"][inl][:600]]).triangulate_two_views(
+        approach="linear_triangulation").copy()
+    np.savez_compressed(os.path.join(OUT, "geometry.npz"), pts0=sc["pts0"], pts1=sc["pts1"], inlier=inl, X=sc["X"],
+                        F=F, mask=mask, und0=u0, und1=u1, X_iter=X_it, status=status, X_lin=X_lin,
+                        P0=cams[0].P, P1=cams[1].P)
+    print("geometry: MAGSAC inliers", int(mask.sum()), "of", len(mask), "true inliers", int(inl.sum()),
+          "tri rel err", float(np.median(np.linalg.norm(X_it - sc["X"][inl][:600], axis=1) / np.linalg.norm(sc["X"][inl][:600], axis=1))))
+
+
+if __name__ == "__main__":
+    assert ref_shims.reference_available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    golden_tiler_quality()
+    golden_geometry()
+    golden_superpoint_superglue()
+    golden_lightglue()
+    golden_matchers()
