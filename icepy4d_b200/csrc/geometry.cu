@@ -1,0 +1,224 @@
+// Two-view geometry kernels on sm_100a, all f64, one thread per correspondence (latency/ALU bound — tens of MB
+// of traffic at most — so they are reported as points/s, not against a roofline).
+// Compiled with -fmad=false so that the f64 arithmetic rounds like the host code it replaces.
+//
+// Reference behaviour replaced (paths into /root/reference/src/icepy4d):
+//   sfm/geometry.py:103-118            undistort_points -> cv2.undistortPoints(pts, K, dist, None, K) (5 fixed-point
+//                                      iterations of the Brown model, f64 inside, f32 out)
+//   thirdparty/triangulation.py:79-177 iterative_LS_triangulation (Hartley-Sturm, <= 10 iterations, tolerance 3e-5)
+//   sfm/triangulation.py:154-183       triangulate_points_linear / triangulate_nviews (6x6 SVD null vector)
+#include "common.cuh"
+#include "../../include/icepy4d_b200.h"
+
+struct Cam9 { double K[9]; double d[5]; };
+struct Proj2 { double P1[12]; double P2[12]; };
+
+__global__ void __launch_bounds__(256) undistort_kernel(const float* __restrict__ pts, int n, Cam9 c,
+                                                        float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
+  const double ifx = 1.0 / fx, ify = 1.0 / fy;
+  const double k1 = c.d[0], k2 = c.d[1], p1 = c.d[2], p2 = c.d[3], k3 = c.d[4];
+  float2 p = reinterpret_cast<const float2*>(pts)[i];
+  const double x0 = ((double)p.x - cx) * ifx, y0 = ((double)p.y - cy) * ify;
+  double x = x0, y = y0;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    double r2 = x * x + y * y;
+    double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    if (icdist < 0) { x = x0; y = y0; break; }
+    double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    double dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  // new camera matrix P = K (rows of K; K[1] = skew, normally 0)
+  double xx = c.K[0] * x + c.K[1] * y + c.K[2];
+  double yy = c.K[3] * x + c.K[4] * y + c.K[5];
+  double ww = 1.0 / (c.K[6] * x + c.K[7] * y + c.K[8]);
+  reinterpret_cast<float2*>(out)[i] = make_float2((float)(xx * ww), (float)(yy * ww));
+}
+
+// least-squares solve of a 4x3 system by Householder QR (A and b are overwritten)
+__device__ __forceinline__ void lstsq_4x3(double A[4][3], double b[4], double x[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = k; i < 4; ++i) nrm += A[i][k] * A[i][k];
+    nrm = sqrt(nrm);
+    if (nrm == 0.0) continue;
+    double alpha = A[k][k] > 0 ? -nrm : nrm;
+    double v[4];
+#pragma unroll
+    for (int i = k; i < 4; ++i) v[i] = A[i][k];
+    v[k] -= alpha;
+    double vn = 0.0;
+#pragma unroll
+    for (int i = k; i < 4; ++i) vn += v[i] * v[i];
+    if (vn == 0.0) continue;
+    double inv = 2.0 / vn;
+#pragma unroll
+    for (int j = k; j < 3; ++j) {
+      double dot = 0.0;
+#pragma unroll
+      for (int i = k; i < 4; ++i) dot += v[i] * A[i][j];
+      dot *= inv;
+#pragma unroll
+      for (int i = k; i < 4; ++i) A[i][j] -= dot * v[i];
+    }
+    double dot = 0.0;
+#pragma unroll
+    for (int i = k; i < 4; ++i) dot += v[i] * b[i];
+    dot *= inv;
+#pragma unroll
+    for (int i = k; i < 4; ++i) b[i] -= dot * v[i];
+  }
+  x[2] = b[2] / A[2][2];
+  x[1] = (b[1] - A[1][2] * x[2]) / A[1][1];
+  x[0] = (b[0] - A[0][1] * x[1] - A[0][2] * x[2]) / A[0][0];
+}
+
+__global__ void __launch_bounds__(128) tri_iterls_kernel(const float* __restrict__ u1, const float* __restrict__ u2,
+                                                         int n, Proj2 pr, double tol, double* __restrict__ X,
+                                                         int* __restrict__ status) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double* P1 = pr.P1; const double* P2 = pr.P2;
+  float2 a = reinterpret_cast<const float2*>(u1)[idx], c = reinterpret_cast<const float2*>(u2)[idx];
+  const double ux[4] = {(double)a.x, (double)a.y, (double)c.x, (double)c.y};
+  // A0 = [u*P[2,:3] - P[row,:3]],  b0 = -(u*P[2,3] - P[row,3])        (triangulation.py:113-123)
+  double A0[4][3], b0[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double* P = r < 2 ? P1 : P2;
+    int row = r & 1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A0[r][j] = ux[r] * P[8 + j] - P[4 * row + j];
+    b0[r] = -(ux[r] * P[11] - P[4 * row + 3]);
+  }
+  double d1 = 1.0, d2 = 1.0, d1n = 1.0, d2n = 1.0;
+  double x[3] = {0, 0, 0};
+#pragma unroll 1
+  for (int it = 0; it < 10; ++it) {
+    double A[4][3], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      b[r] = b0[r];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) A[r][j] = A0[r][j];
+    }
+    lstsq_4x3(A, b, x);
+    d1n = P1[8] * x[0] + P1[9] * x[1] + P1[10] * x[2] + P1[11];
+    d2n = P2[8] * x[0] + P2[9] * x[1] + P2[10] * x[2] + P2[11];
+    if (fabs(d1n - d1) <= tol && fabs(d2n - d2) <= tol) break;
+    // the reference re-weights the *already weighted* system each iteration (triangulation.py:157-160)
+    double w1 = 1.0 / d1n, w2 = 1.0 / d2n;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { A0[0][j] *= w1; A0[1][j] *= w1; A0[2][j] *= w2; A0[3][j] *= w2; }
+    b0[0] *= w1; b0[1] *= w1; b0[2] *= w2; b0[3] *= w2;
+    d1 = d1n; d2 = d2n;
+  }
+  X[3 * (size_t)idx + 0] = x[0]; X[3 * (size_t)idx + 1] = x[1]; X[3 * (size_t)idx + 2] = x[2];
+  int st = (d1n > 0 && d2n > 0) ? 1 : 0;   // `i < 10` in the reference is always true (triangulation.py:169)
+  if (d1n <= 0) st -= 1;
+  if (d2n <= 0) st -= 2;
+  status[idx] = st;
+}
+
+// DLT: right singular vector of the smallest singular value of the 6x6 matrix [[P1, -x1, 0], [P2, 0, -x2]],
+// by one-sided (Hestenes) Jacobi directly on M — no squaring of the condition number.
+__global__ void __launch_bounds__(64) tri_dlt_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int n,
+                                                     Proj2 pr, double* __restrict__ X) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float2 a = reinterpret_cast<const float2*>(x1)[idx], c = reinterpret_cast<const float2*>(x2)[idx];
+  double A[6][6], V[6][6];  // A[col][row]
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { A[j][i] = 0.0; V[j][i] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { A[j][i] = pr.P1[4 * i + j]; A[j][3 + i] = pr.P2[4 * i + j]; }
+  A[4][0] = -(double)a.x; A[4][1] = -(double)a.y; A[4][2] = -1.0;
+  A[5][3] = -(double)c.x; A[5][4] = -(double)c.y; A[5][5] = -1.0;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < 6; ++q) {
+        double al = 0, be = 0, ga = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { al += A[p][i] * A[p][i]; be += A[q][i] * A[q][i]; ga += A[p][i] * A[q][i]; }
+        if (fabs(ga) > 1e-15 * sqrt(al * be) && ga != 0.0) {
+          rotated = true;
+          double zeta = (be - al) / (2.0 * ga);
+          double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            double ap = A[p][i], aq = A[q][i];
+            A[p][i] = cs * ap - sn * aq; A[q][i] = sn * ap + cs * aq;
+            double vp = V[p][i], vq = V[q][i];
+            V[p][i] = cs * vp - sn * vq; V[q][i] = sn * vp + cs * vq;
+          }
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  int jmin = 0; double best = INFINITY;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += A[j][i] * A[j][i];
+    if (s < best) { best = s; jmin = j; }
+  }
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 1;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j == jmin) { v0 = V[j][0]; v1 = V[j][1]; v2 = V[j][2]; v3 = V[j][3]; }
+  X[3 * (size_t)idx + 0] = v0 / v3; X[3 * (size_t)idx + 1] = v1 / v3; X[3 * (size_t)idx + 2] = v2 / v3;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_undistort_points(const float* pts, int n, const double* K_host, const double* dist_host,
+                                    int n_dist, float* out, void* stream) {
+  I4D_CHECK_ARG(pts && out && K_host && n >= 0, "null pointer");
+  I4D_CHECK_ARG(n_dist >= 0 && n_dist <= 5, "only the k1,k2,p1,p2[,k3] Brown model is supported");
+  if (n == 0) return I4D_OK;
+  Cam9 c;
+  for (int i = 0; i < 9; ++i) c.K[i] = K_host[i];
+  for (int i = 0; i < 5; ++i) c.d[i] = (dist_host && i < n_dist) ? dist_host[i] : 0.0;
+  undistort_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(pts, n, c, out);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_triangulate_iterative_ls(const float* u1, const float* u2, int n, const double* P1_host,
+                                            const double* P2_host, double tolerance, double* X, int* status,
+                                            void* stream) {
+  I4D_CHECK_ARG(u1 && u2 && X && status && P1_host && P2_host && n >= 0, "null pointer");
+  if (n == 0) return I4D_OK;
+  Proj2 pr;
+  for (int i = 0; i < 12; ++i) { pr.P1[i] = P1_host[i]; pr.P2[i] = P2_host[i]; }
+  tri_iterls_kernel<<<i4d_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(u1, u2, n, pr, tolerance, X, status);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_triangulate_dlt(const float* x1, const float* x2, int n, const double* P1_host,
+                                   const double* P2_host, double* X, void* stream) {
+  I4D_CHECK_ARG(x1 && x2 && X && P1_host && P2_host && n >= 0, "null pointer");
+  if (n == 0) return I4D_OK;
+  Proj2 pr;
+  for (int i = 0; i < 12; ++i) { pr.P1[i] = P1_host[i]; pr.P2[i] = P2_host[i]; }
+  tri_dlt_kernel<<<i4d_cdiv(n, 64), 64, 0, (cudaStream_t)stream>>>(x1, x2, n, pr, X);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}

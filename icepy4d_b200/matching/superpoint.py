@@ -1,0 +1,112 @@
+"""SuperPoint on the device: cuDNN backbone (interim) + hand-written sm_100a post-processing.
+
+Mirrors thirdparty/SuperGlue/models/superpoint.py:100-220 and thirdparty/LightGlue/lightglue/superpoint.py:88-215
+of the reference; accepts a state_dict with the reference's parameter names.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+
+_CONVS = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "convPa", "convPb",
+          "convDa", "convDb"]
+
+
+@dataclass
+class DeviceFeatures:
+    """Keypoints of one image, resident in HBM.  Only the first `n` rows are valid."""
+    keypoints: torch.Tensor      # [cap, 2] f32 (x, y)
+    scores: torch.Tensor         # [cap] f32
+    descriptors: torch.Tensor    # [cap, 256] f32, token-major (reference layout [256, n] is the transpose)
+    n_dev: torch.Tensor          # int32[1] on the device
+    n: Optional[int] = None      # host copy, filled by `sync_counts`
+    height: int = 0
+    width: int = 0
+
+
+class SuperPointB200:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", nms_radius: int = 4,
+                 keypoint_threshold: float = 0.005, max_keypoints: int = -1, remove_borders: int = 4,
+                 conv_precision: str = "tf32"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("icepy4d_b200 needs a CUDA device (there is no CPU fallback)")
+        assert conv_precision in ("f32", "tf32", "bf16")
+        self.device = torch.device(device)
+        self.nms_radius, self.thr = int(nms_radius), float(keypoint_threshold)
+        self.k = -1 if max_keypoints is None else int(max_keypoints)
+        if self.k == 0 or self.k < -1:
+            raise ValueError('"max_keypoints" must be positive or "-1"')
+        self.border = int(remove_borders)
+        self.conv_precision = conv_precision
+        wdt = torch.bfloat16 if conv_precision == "bf16" else torch.float32
+        self.w = {}
+        for name in _CONVS:
+            w = state_dict[f"{name}.weight"].to(self.device, dtype=wdt).contiguous(memory_format=torch.channels_last)
+            b = state_dict[f"{name}.bias"].to(self.device, dtype=wdt)
+            self.w[name] = (w, b)
+        self._kws = {}
+
+    # -- backbone (cuDNN through torch; channels-last so the heads come out HWC for the gather kernel) --
+    def _conv(self, x, name, pad, relu=True):
+        w, b = self.w[name]
+        y = F.conv2d(x, w, b, padding=pad)
+        return F.relu_(y) if relu else y
+
+    def backbone(self, image: torch.Tensor):
+        """image [1,1,H,W] f32 -> (logits [65,h,w] f32 contiguous, desc [h,w,256] f32 contiguous)."""
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = self.conv_precision != "f32"
+        try:
+            x = image.to(torch.bfloat16) if self.conv_precision == "bf16" else image
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = self._conv(self._conv(x, "conv1a", 1), "conv1b", 1)
+            x = F.max_pool2d(x, 2, 2)
+            x = self._conv(self._conv(x, "conv2a", 1), "conv2b", 1)
+            x = F.max_pool2d(x, 2, 2)
+            x = self._conv(self._conv(x, "conv3a", 1), "conv3b", 1)
+            x = F.max_pool2d(x, 2, 2)
+            x = self._conv(self._conv(x, "conv4a", 1), "conv4b", 1)
+            logits = self._conv(self._conv(x, "convPa", 1), "convPb", 0, relu=False)
+            desc = self._conv(self._conv(x, "convDa", 1), "convDb", 0, relu=False)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        logits = logits[0].float().contiguous()                      # [65,h,w] planar
+        desc = desc[0].float().permute(1, 2, 0).contiguous()         # [h,w,256] (no copy when channels-last)
+        return logits, desc
+
+    def postprocess(self, logits: torch.Tensor, desc_hwc: torch.Tensor, k: Optional[int] = None) -> DeviceFeatures:
+        k = self.k if k is None else int(k)
+        scores = ops.sp_score_map(logits)
+        H, W = scores.shape
+        key = (H, W)
+        if key not in self._kws:
+            self._kws[key] = ops.KeypointWorkspace(H, W, self.device)
+        kpts, ksc, n_dev, _ = ops.sp_keypoints(scores, self.nms_radius, self.thr, self.border, k, self._kws[key])
+        if k < 0:
+            # "keep all": the result size is data dependent -> one host read to trim the buffers
+            n = min(int(n_dev.item()), kpts.shape[0])
+            kpts, ksc = kpts[:n].contiguous(), ksc[:n].contiguous()
+            return DeviceFeatures(kpts, ksc, ops.sp_sample_descriptors(desc_hwc, kpts, None, n), n_dev, n)
+        desc = ops.sp_sample_descriptors(desc_hwc, kpts, n_dev)
+        return DeviceFeatures(kpts, ksc, desc, n_dev)
+
+    def detect(self, image: torch.Tensor, k: Optional[int] = None) -> DeviceFeatures:
+        """image [1,1,H,W] f32 in [0,1] on the device."""
+        logits, desc = self.backbone(image)
+        f = self.postprocess(logits, desc, k)
+        f.height, f.width = int(image.shape[-2]), int(image.shape[-1])
+        return f
+
+
+def sync_counts(*feats: DeviceFeatures) -> None:
+    """One device->host read for the keypoint counts of several images."""
+    if not feats:
+        return
+    counts = torch.cat([f.n_dev for f in feats]).cpu().tolist()
+    for f, c in zip(feats, counts):
+        f.n = min(int(c), f.keypoints.shape[0])

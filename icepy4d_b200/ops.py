@@ -1,0 +1,244 @@
+"""Thin torch-tensor wrappers over the C ABI (validation + output allocation; all compute is in the .so).
+
+Every function takes CUDA tensors, launches on torch's current stream and returns CUDA tensors.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32, name="tensor"):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _st():
+    return N.current_stream()
+
+
+# ---------------------------------------------------------------- SuperPoint post-processing
+def sp_score_map(logits: torch.Tensor) -> torch.Tensor:
+    """logits [65,h,w] -> scores [8h,8w]."""
+    _chk(logits, name="logits")
+    c, h, w = logits.shape
+    assert c == 65
+    out = torch.empty((8 * h, 8 * w), device=logits.device, dtype=torch.float32)
+    N.call("i4d_sp_score_map", logits, h, w, out, _st())
+    return out
+
+
+class KeypointWorkspace:
+    """Reusable device buffers for candidate compaction + top-k of one score map size."""
+
+    def __init__(self, H: int, W: int, device, cand_cap: Optional[int] = None):
+        self.H, self.W = H, W
+        self.cand_cap = int(cand_cap or max(65536, (H * W) // 4))
+        self.keys = torch.empty(self.cand_cap, device=device, dtype=torch.int64)
+        self.spill = torch.empty(self.cand_cap, device=device, dtype=torch.int64)
+        self.count = torch.zeros(1, device=device, dtype=torch.int32)
+
+
+def sp_keypoints(scores: torch.Tensor, nms_radius: int, thr: float, border: int, k: int,
+                 ws: Optional[KeypointWorkspace] = None, want_nms: bool = False, out_cap: Optional[int] = None):
+    """scores [H,W] -> (kpts [cap,2] f32 (x,y), kscores [cap], n_dev int32[1], nms map or None).
+    Only the first n rows are valid; n stays on the device (no sync here)."""
+    _chk(scores, name="scores")
+    H, W = scores.shape
+    ws = ws or KeypointWorkspace(H, W, scores.device)
+    nms = torch.empty_like(scores) if want_nms else None
+    N.call("i4d_sp_nms_candidates", scores, H, W, int(nms_radius), float(thr), int(border), ws.keys, ws.cand_cap,
+           ws.count, nms, _st())
+    cap = int(out_cap if out_cap is not None else (k if k >= 0 else ws.cand_cap))
+    kpts = torch.empty((cap, 2), device=scores.device, dtype=torch.float32)
+    ksc = torch.empty((cap,), device=scores.device, dtype=torch.float32)
+    n_dev = torch.zeros(1, device=scores.device, dtype=torch.int32)
+    N.call("i4d_sp_select_topk", ws.keys, ws.count, ws.cand_cap, int(k), W, kpts, ksc, cap, n_dev, ws.spill, _st())
+    return kpts, ksc, n_dev, nms
+
+
+def sp_sample_descriptors(desc_hwc: torch.Tensor, kpts: torch.Tensor, n_dev: Optional[torch.Tensor] = None,
+                          n_max: Optional[int] = None) -> torch.Tensor:
+    """desc_hwc [h,w,256], kpts [n,2] -> [n,256] unit-norm rows."""
+    _chk(desc_hwc, name="desc_hwc")
+    _chk(kpts, name="kpts")
+    h, w, c = desc_hwc.shape
+    assert c == 256
+    n_max = int(kpts.shape[0] if n_max is None else n_max)
+    out = torch.zeros((n_max, 256), device=kpts.device, dtype=torch.float32)
+    N.call("i4d_sp_sample_descriptors", desc_hwc, h, w, kpts, n_dev, n_max, out, _st())
+    return out
+
+
+# ---------------------------------------------------------------- dense f32
+def gemm_f32(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False) -> torch.Tensor:
+    """out[M,N] = alpha * A[M,K] @ W[N,K]^T + bias (+relu) (+residual).  A/W/out/residual may be column slices
+    of wider row-major buffers (stride(1) == 1)."""
+    for t, nm in ((A, "A"), (W, "W")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1:
+            raise ValueError(f"{nm} must be a CUDA f32 matrix with unit column stride")
+    M, K = A.shape
+    Nn, K2 = W.shape
+    assert K == K2
+    if out is None:
+        out = torch.empty((M, Nn), device=A.device, dtype=torch.float32)
+    assert out.shape == (M, Nn) and out.stride(1) == 1
+    ldr = 0
+    if residual is not None:
+        assert residual.shape == (M, Nn) and residual.stride(1) == 1
+        ldr = residual.stride(0)
+    N.call("i4d_gemm_f32", A, A.stride(0) if M > 1 else max(K, A.stride(0)), W, W.stride(0) if Nn > 1 else max(K, W.stride(0)),
+           bias, residual, ldr, out, out.stride(0) if M > 1 else max(Nn, out.stride(0)), M, Nn, K, float(alpha), int(relu), _st())
+    return out
+
+
+def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int = 4,
+                  scale: float = 0.125) -> torch.Tensor:
+    """q [Nq, heads*64], k/v [Nk, heads*64] (may be column slices), out [Nq, heads*64]."""
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1
+    N.call("i4d_attention_f32", q, q.stride(0), k, k.stride(0), v, v.stride(0), out, out.stride(0), q.shape[0], k.shape[0],
+           heads, float(scale), _st())
+    return out
+
+
+def layernorm_gelu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   eps: float = 1e-5) -> torch.Tensor:
+    assert x.is_cuda and x.stride(1) == 1
+    out = x if out is None else out
+    N.call("i4d_layernorm_gelu", x, x.stride(0), gamma, beta, out, out.stride(0), x.shape[0], x.shape[1], float(eps), _st())
+    return out
+
+
+def lg_posenc(kpts: torch.Tensor, width: float, height: float, Wr: torch.Tensor) -> torch.Tensor:
+    _chk(kpts, name="kpts")
+    cs = torch.empty((kpts.shape[0], 64), device=kpts.device, dtype=torch.float32)
+    N.call("i4d_lg_posenc", kpts, kpts.shape[0], float(width), float(height), _chk(Wr, name="Wr"), cs, _st())
+    return cs
+
+
+def lg_rotary_(x: torch.Tensor, cs: torch.Tensor, heads: int = 4) -> torch.Tensor:
+    assert x.is_cuda and x.stride(1) == 1
+    N.call("i4d_lg_rotary", x, x.stride(0), x.shape[0], heads, cs, _st())
+    return x
+
+
+def sg_kenc_input(kpts: torch.Tensor, scores: torch.Tensor, width: float, height: float) -> torch.Tensor:
+    out = torch.empty((kpts.shape[0], 3), device=kpts.device, dtype=torch.float32)
+    N.call("i4d_sg_kenc_input", _chk(kpts), _chk(scores), kpts.shape[0], float(width), float(height), out, _st())
+    return out
+
+
+# ---------------------------------------------------------------- assignment
+class AssignWorkspace:
+    def __init__(self, M: int, N_: int, device):
+        self.M, self.N = M, N_
+        nbytes = N.lib().i4d_assignment_workspace_bytes(M, N_)
+        self.buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        self.nbytes = nbytes
+
+
+def _ws(ws, M, N_, device):
+    if ws is None or ws.M < M or ws.N < N_ or ws.nbytes < N.lib().i4d_assignment_workspace_bytes(M, N_):
+        ws = AssignWorkspace(M, N_, device)
+    return ws
+
+
+def row_lse(S: torch.Tensor, scale: float = 1.0, coloff: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(S)
+    out = torch.empty(S.shape[0], device=S.device, dtype=torch.float32)
+    N.call("i4d_row_lse", S, S.shape[0], S.shape[1], float(scale), coloff, out, _st())
+    return out
+
+
+def col_lse(S: torch.Tensor, scale: float = 1.0, rowoff: Optional[torch.Tensor] = None, ws=None) -> torch.Tensor:
+    _chk(S)
+    ws = _ws(ws, S.shape[0], S.shape[1], S.device)
+    out = torch.empty(S.shape[1], device=S.device, dtype=torch.float32)
+    N.call("i4d_col_lse", S, S.shape[0], S.shape[1], float(scale), rowoff, out, ws.buf, ws.nbytes, _st())
+    return out
+
+
+def sinkhorn(scores: torch.Tensor, bin_score: float, iters: int, ws=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    _chk(scores)
+    M, N_ = scores.shape
+    ws = _ws(ws, M, N_, scores.device)
+    u = torch.empty(M + 1, device=scores.device, dtype=torch.float32)
+    v = torch.empty(N_ + 1, device=scores.device, dtype=torch.float32)
+    N.call("i4d_sinkhorn", scores, M, N_, float(bin_score), int(iters), u, v, ws.buf, ws.nbytes, _st())
+    return u, v
+
+
+def sg_assign(scores: torch.Tensor, bin_score: float, iters: int, thr: float, ws=None):
+    """-> matches0 [M] i32, matches1 [N] i32, mscores0 [M], mscores1 [N]"""
+    _chk(scores)
+    M, N_ = scores.shape
+    ws = _ws(ws, M, N_, scores.device)
+    dev = scores.device
+    m0 = torch.empty(M, device=dev, dtype=torch.int32)
+    m1 = torch.empty(N_, device=dev, dtype=torch.int32)
+    s0 = torch.empty(M, device=dev, dtype=torch.float32)
+    s1 = torch.empty(N_, device=dev, dtype=torch.float32)
+    u = torch.empty(M + 1, device=dev, dtype=torch.float32)
+    v = torch.empty(N_ + 1, device=dev, dtype=torch.float32)
+    N.call("i4d_sg_assign", scores, M, N_, float(bin_score), int(iters), float(thr), m0, m1, s0, s1, u, v, ws.buf,
+           ws.nbytes, _st())
+    return m0, m1, s0, s1
+
+
+def lg_assign(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor, thr: float, ws=None):
+    _chk(sim)
+    M, N_ = sim.shape
+    ws = _ws(ws, M, N_, sim.device)
+    dev = sim.device
+    m0 = torch.empty(M, device=dev, dtype=torch.int32)
+    m1 = torch.empty(N_, device=dev, dtype=torch.int32)
+    s0 = torch.empty(M, device=dev, dtype=torch.float32)
+    s1 = torch.empty(N_, device=dev, dtype=torch.float32)
+    N.call("i4d_lg_assign", sim, M, N_, _chk(z0.reshape(-1)), _chk(z1.reshape(-1)), float(thr), m0, m1, s0, s1, ws.buf,
+           ws.nbytes, _st())
+    return m0, m1, s0, s1
+
+
+# ---------------------------------------------------------------- geometry
+def undistort_points(pts: torch.Tensor, K: np.ndarray, dist: np.ndarray) -> torch.Tensor:
+    _chk(pts, name="pts")
+    Kh = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    dh = np.ascontiguousarray(np.asarray(dist, dtype=np.float64).reshape(-1))
+    if dh.size > 5 and np.any(dh[5:] != 0):
+        raise ValueError("only the 5-parameter Brown model (k1,k2,p1,p2,k3) is supported")
+    dh = np.ascontiguousarray(dh[:5])
+    out = torch.empty_like(pts)
+    N.call("i4d_undistort_points", pts, pts.shape[0], Kh, dh, int(dh.size), out, _st())
+    return out
+
+
+def triangulate_iterative_ls(u1: torch.Tensor, u2: torch.Tensor, P1: np.ndarray, P2: np.ndarray, tol: float = 3e-5):
+    _chk(u1), _chk(u2)
+    n = u1.shape[0]
+    X = torch.empty((n, 3), device=u1.device, dtype=torch.float64)
+    st = torch.empty((n,), device=u1.device, dtype=torch.int32)
+    P1h = np.ascontiguousarray(np.asarray(P1, dtype=np.float64).reshape(12))
+    P2h = np.ascontiguousarray(np.asarray(P2, dtype=np.float64).reshape(12))
+    N.call("i4d_triangulate_iterative_ls", u1, u2, n, P1h, P2h, float(tol), X, st, _st())
+    return X, st
+
+
+def triangulate_dlt(x1: torch.Tensor, x2: torch.Tensor, P1: np.ndarray, P2: np.ndarray) -> torch.Tensor:
+    _chk(x1), _chk(x2)
+    n = x1.shape[0]
+    X = torch.empty((n, 3), device=x1.device, dtype=torch.float64)
+    P1h = np.ascontiguousarray(np.asarray(P1, dtype=np.float64).reshape(12))
+    P2h = np.ascontiguousarray(np.asarray(P2, dtype=np.float64).reshape(12))
+    N.call("i4d_triangulate_dlt", x1, x2, n, P1h, P2h, X, _st())
+    return X

@@ -1,0 +1,111 @@
+/* icepy4d_b200 — C ABI of the B200-native (sm_100a) hot path of ICEpy4D's per-epoch stereo
+ * match -> verify -> triangulate pipeline.
+ *
+ * The reference (franioli/icepy4d) is pure Python: there is no FFI for this path today.  Each
+ * entry point below replaces a block of torch / OpenCV / numpy calls at the cited reference location
+ * (paths relative to /root/reference/src/icepy4d).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises unless stated;
+ *   - no allocation inside: scratch comes in through `workspace` (+ its size query);
+ *   - return value: 0 = ok, <0 = error (I4D_ERR_*), message via i4d_last_error(); never throws.
+ *   - matrices are row-major with explicit leading dimensions (in elements) where given.
+ */
+#ifndef ICEPY4D_B200_H
+#define ICEPY4D_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I4D_VERSION 100 /* 0.1.0 */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int i4d_version(void);
+const char* i4d_last_error(void);
+/* SM count of the current device (0 if no device) — grids are sized from it. */
+int i4d_device_sm_count(void);
+
+/* ---- SuperPoint post-processing ----------------------------------------------------------------------- */
+/* thirdparty/SuperGlue/models/superpoint.py:169-172 — softmax over 65 channels, drop dustbin, 8x8 pixel shuffle.
+ * logits [65,h,w] f32 -> scores [8h,8w] f32. */
+int i4d_sp_score_map(const float* logits, int h, int w, float* scores, void* stream);
+/* superpoint.py:48-64 (simple_nms, 3 passes, radius <= 4) + :176-190 threshold `> thr` and border removal
+ * (LightGlue/lightglue/superpoint.py:176-186 gives the same set).  Candidates are appended (unordered) as 64-bit
+ * keys (score bits << 32 | ~linear index) to cand_keys[cand_cap]; *cand_count (device) receives the total found
+ * (may exceed cand_cap: caller checks).  nms_out (nullable) receives the dense NMS'd score map [H,W]. */
+int i4d_sp_nms_candidates(const float* scores, int H, int W, int nms_radius, float thr, int border,
+                          unsigned long long* cand_keys, int cand_cap, int* cand_count, float* nms_out,
+                          void* stream);
+/* superpoint.py:75-79,193-203 — keep the k best (k < 0: keep all), emit (x, y) as f32 and scores.  Order: score
+ * descending (ties: lower linear index first) when k applies, row-major otherwise, like topk / nonzero.
+ * kpts [out_cap,2], scores [out_cap], *n_out (device) = number written.  spill: scratch of cand_cap keys.
+ * Synchronises the stream only when k < 0 or k > 16384. */
+int i4d_sp_select_topk(const unsigned long long* cand_keys, const int* cand_count, int cand_cap, int k, int W,
+                       float* kpts, float* scores, int out_cap, int* n_out, unsigned long long* spill, void* stream);
+/* superpoint.py:82-97,208 — dense L2 normalisation, bilinear grid_sample(align_corners=True), L2 normalisation.
+ * desc_hwc [h,w,256] f32 (channels-last), kpts [n,2]; n = min(*n_dev, n_max) if n_dev != NULL else n_max.
+ * out [n,256] (token-major; the reference's [256,n] is its transpose). */
+int i4d_sp_sample_descriptors(const float* desc_hwc, int h, int w, const float* kpts, const int* n_dev, int n_max,
+                              float* out, void* stream);
+
+/* ---- dense f32 building blocks ------------------------------------------------------------------------ */
+/* C = alpha * A[M,K] * W[N,K]^T + bias[N] (+ReLU) (+R[M,N]).  Replaces Conv1d(k=1)/Linear (+ folded BatchNorm,
+ * + residual): superglue.py:51-61,119-128,147-148,276-280; lightglue.py:133-216,253-287. bias, R nullable. */
+int i4d_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias, const float* R, int ldr,
+                 float* C, int ldc, int M, int N, int K, float alpha, int relu, void* stream);
+/* softmax(scale * Q K^T) V per head, head_dim 64, head h = columns [64h, 64h+64) — superglue.py:87-93 (with the
+ * head permutation folded into the weights), lightglue.py:108-130. Never materialises the Nq x Nk matrix. */
+int i4d_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, int ldo,
+                      int Nq, int Nk, int heads, float scale, void* stream);
+/* LayerNorm(C) + GELU(erf) row-wise — lightglue.py:144-149 (ffn[1], ffn[2]). */
+int i4d_layernorm_gelu(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int rows,
+                       int C, float eps, void* stream);
+/* lightglue.py:23-35,60-74 — normalise keypoints by the image size and evaluate the learnable Fourier encoding.
+ * Wr [32,2]; cs [n,64] = (cos[32] | sin[32]) per keypoint. */
+int i4d_lg_posenc(const float* kpts, int n, float width, float height, const float* Wr, float* cs, void* stream);
+/* lightglue.py:49-57 — apply the cached rotary embedding in place to `heads` heads of 64 columns. */
+int i4d_lg_rotary(float* X, int ldx, int n, int heads, const float* cs, void* stream);
+/* superglue.py:64-71,82-84 — keypoint-encoder input rows (x_norm, y_norm, score), out [n,3]. */
+int i4d_sg_kenc_input(const float* kpts, const float* scores, int n, float width, float height, float* out,
+                      void* stream);
+
+/* ---- assignment --------------------------------------------------------------------------------------- */
+size_t i4d_assignment_workspace_bytes(int M, int N);
+/* out_i = LSE_j(scale * S_ij + coloff_j) / out_j = LSE_i(scale * S_ij + rowoff_i); offsets nullable. */
+int i4d_row_lse(const float* S, int M, int N, float scale, const float* coloff, float* out, void* stream);
+int i4d_col_lse(const float* S, int M, int N, float scale, const float* rowoff, float* out, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* superglue.py:152-186 — log-domain Sinkhorn potentials u[M+1], v[N+1] of the dustbin-augmented problem. */
+int i4d_sinkhorn(const float* scores, int M, int N, float bin_score, int iters, float* u, float* v, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* superglue.py:152-186 + :288-298 — Sinkhorn, then mutual nearest neighbours with threshold.
+ * matches0 [M] / matches1 [N] int32 (-1 = unmatched), mscores0/1 f32; u [M+1], v [N+1] scratch/outputs. */
+int i4d_sg_assign(const float* scores, int M, int N, float bin_score, int iters, float match_threshold,
+                  int* matches0, int* matches1, float* mscores0, float* mscores1, float* u, float* v,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* lightglue.py:253-266 + :290-306 — sigmoid/log double softmax + mutual NN with threshold, from sim [M,N] and
+ * matchability logits z0 [M], z1 [N].  The (M+1)x(N+1) log-assignment matrix is never written. */
+int i4d_lg_assign(const float* sim, int M, int N, const float* z0, const float* z1, float filter_threshold,
+                  int* matches0, int* matches1, float* mscores0, float* mscores1, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- two-view geometry -------------------------------------------------------------------------------- */
+/* sfm/geometry.py:103-118 — cv2.undistortPoints(pts, K, dist, None, K) cast to f32.  K_host [9] row-major,
+ * dist_host [n_dist <= 5] = k1,k2,p1,p2[,k3] (host pointers, copied by value). */
+int i4d_undistort_points(const float* pts, int n, const double* K_host, const double* dist_host, int n_dist,
+                         float* out, void* stream);
+/* thirdparty/triangulation.py:79-177 — iterative re-weighted LS triangulation (f64).  P*_host [12] row-major.
+ * X [n,3] f64, status [n] int32 with the reference's codes (1, 0, -1, -2, -3). */
+int i4d_triangulate_iterative_ls(const float* u1, const float* u2, int n, const double* P1_host,
+                                 const double* P2_host, double tolerance, double* X, int* status, void* stream);
+/* sfm/triangulation.py:154-183 — DLT via the null vector of the 6x6 system, dehomogenised. X [n,3] f64. */
+int i4d_triangulate_dlt(const float* x1, const float* x2, int n, const double* P1_host, const double* P2_host,
+                        double* X, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
