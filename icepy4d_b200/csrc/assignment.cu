@@ -226,7 +226,7 @@ static int col_splits_for(int M, int N) {
 // workspace layout (floats): pm[256*N] ps[256*N] pi[256*N] | val0[M] idx0[M] idx1[N] val1[N] rowoff[M+1] coloff[N+1] rl[M] cl[N]
 extern "C" __attribute__((visibility("default"))) size_t i4d_assignment_workspace_bytes(int M, int N) {
   if (M <= 0 || N <= 0) return 0;
-  return ((size_t)256 * N * 3 + 4 * (size_t)(M + 1) + 4 * (size_t)(N + 1) + 64) * sizeof(float);
+  return ((size_t)256 * N * 3 + 4 * (size_t)(M + 8) + 4 * (size_t)(N + 8) + 64) * sizeof(float);
 }
 
 struct AssignWs {
@@ -236,8 +236,9 @@ struct AssignWs {
     float* f = reinterpret_cast<float*>(w);
     pm = f; ps = f + (size_t)256 * N; pi = reinterpret_cast<int*>(f + (size_t)512 * N);
     float* q = f + (size_t)768 * N;
-    val0 = q; q += M + 1; idx0 = reinterpret_cast<int*>(q); q += M + 1; rowoff = q; q += M + 1; rl = q; q += M + 1;
-    idx1 = reinterpret_cast<int*>(q); q += N + 1; val1 = q; q += N + 1; coloff = q; q += N + 1; cl = q;
+    const size_t ms = ((size_t)M + 1 + 3) & ~(size_t)3, ns = ((size_t)N + 1 + 3) & ~(size_t)3;  // keep 16 B alignment (float4 loads)
+    val0 = q; q += ms; idx0 = reinterpret_cast<int*>(q); q += ms; rowoff = q; q += ms; rl = q; q += ms;
+    idx1 = reinterpret_cast<int*>(q); q += ns; val1 = q; q += ns; coloff = q; q += ns; cl = q;
   }
 };
 

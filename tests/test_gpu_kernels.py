@@ -35,16 +35,22 @@ def test_score_map(ops, golden_dir):
 
 def test_nms_teacher_forced_identical_keypoints(ops, golden_dir):
     g = np.load(os.path.join(golden_dir, "sp_sg_small.npz"))
-    scores = sp_oracle.score_map(torch.from_numpy(g["logits0"]))          # oracle's own f32 score map
+    scores = sp_oracle.score_map(torch.from_numpy(g["logits0"]))          # oracle's own f32 score map (this host)
+    ref_nms = sp_oracle.simple_nms(scores, 3)
+    rk, rs = sp_oracle.keypoints_sg(ref_nms, 1e-4, 4, 256)
     kp, sc, n, nms = ops.sp_keypoints(scores.cuda(), 3, 1e-4, 4, 256, want_nms=True)
-    assert np.array_equal(nms.cpu().numpy(), g["nms0"])                    # whole NMS map bit-identical
+    assert torch.equal(nms.cpu(), ref_nms)                                 # whole NMS map bit-identical
     n = int(n.item())
-    assert n == len(g["kpts0"])
-    assert _set(kp[:n].cpu().numpy()) == _set(g["kpts0"])                  # identical keypoint indices
-    ref = {(float(x), float(y)): float(s) for (x, y), s in zip(g["kpts0"], g["scores0"])}
+    assert n == len(rk)
+    assert _set(kp[:n].cpu().numpy()) == _set(rk.numpy())                  # identical keypoint indices
+    ref = {(float(x), float(y)): float(s) for (x, y), s in zip(rk.numpy(), rs.numpy())}
     for (x, y), s in zip(kp[:n].cpu().numpy(), sc[:n].cpu().numpy()):
         assert ref[(float(x), float(y))] == float(s)
     assert np.all(np.diff(sc[:n].cpu().numpy()) <= 0)                      # score-descending like torch.topk
+    # against the reference's own output (generated on another host: CPU softmax may differ in the last ulp,
+    # which can only swap near-tied candidates at the top-k boundary)
+    a, b = _set(kp[:n].cpu().numpy()), _set(g["kpts0"])
+    assert len(a & b) / len(a | b) >= 0.99
 
 
 @pytest.mark.parametrize("H,W,r", [(64, 64, 1), (200, 333, 2), (129, 257, 3), (300, 190, 4), (8, 8, 4), (70, 500, 0)])
