@@ -243,3 +243,31 @@ def triangulate_dlt(x1: torch.Tensor, x2: torch.Tensor, P1: np.ndarray, P2: np.n
     P2h = np.ascontiguousarray(np.asarray(P2, dtype=np.float64).reshape(12))
     N.call("i4d_triangulate_dlt", x1, x2, n, P1h, P2h, X, _st())
     return X
+
+
+def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.5, confidence: float = 0.999,
+                       max_iters: int = 100000, seed: int = 0, sigma_max: float = 1.0, polish_iters: int = 20,
+                       ws: Optional[torch.Tensor] = None):
+    """x0, x1 [n,2] f32 -> (F [9] f64 device, mask [n] u8 device, n_inliers int32[1] device)."""
+    _chk(x0, name="x0"), _chk(x1, name="x1")
+    n = x0.shape[0]
+    dev = x0.device
+    nbytes = N.lib().i4d_fundamental_workspace_bytes()
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    F = torch.zeros(9, device=dev, dtype=torch.float64)
+    mask = torch.zeros(n, device=dev, dtype=torch.uint8)
+    n_inl = torch.zeros(1, device=dev, dtype=torch.int32)
+    N.call("i4d_fundamental_ransac", x0, x1, n, float(threshold), float(confidence), int(max_iters), int(seed) & 0xFFFFFFFF,
+           float(sigma_max), int(polish_iters), F, mask, n_inl, ws, ws.numel(), _st())
+    return F, mask, n_inl
+
+
+def tile_to_gray_f32(image_u8: torch.Tensor, x0: int, y0: int, tw: int, th: int, mode: int) -> torch.Tensor:
+    """image [H,W,C] or [H,W] u8 on the device -> [1,1,th,tw] f32 network input."""
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()
+    H, W = image_u8.shape[:2]
+    C = 1 if image_u8.dim() == 2 else image_u8.shape[2]
+    out = torch.empty((1, 1, th, tw), device=image_u8.device, dtype=torch.float32)
+    N.call("i4d_tile_to_gray_f32", image_u8, H, W, C, int(x0), int(y0), int(tw), int(th), int(mode), out, _st())
+    return out

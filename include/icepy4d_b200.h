@@ -105,6 +105,26 @@ int i4d_triangulate_iterative_ls(const float* u1, const float* u2, int n, const 
 int i4d_triangulate_dlt(const float* x1, const float* x2, int n, const double* P1_host, const double* P2_host,
                         double* X, void* stream);
 
+/* matching/geometric_verification.py:43-102 and sfm/two_view_geometry.py:127-197 — robust fundamental matrix.
+ * Batched-hypothesis RANSAC (8-point samples drawn from `seed`, consensus with a truncated quadratic of cut-off
+ * 3.64*sigma_max on the Sampson error) + sigma-consensus IRLS polish (`polish_iters` weighted 8-point solves),
+ * then inliers = sqrt(Sampson error) < threshold (OpenCV USAC's rule).  x0, x1 [n,2] f32 raw pixel coordinates.
+ * Outputs (device): F_out [9] f64 row-major (scaled so F[8] = 1 when possible), mask [n] u8, *n_inliers. */
+size_t i4d_fundamental_workspace_bytes(void);
+int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double threshold, double confidence,
+                           int max_iters, unsigned int seed, double sigma_max, int polish_iters, double* F_out,
+                           unsigned char* mask, int* n_inliers, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ---- tiler front end ---------------------------------------------------------------------------------- */
+/* matching/tiling.py:123-135 (extract_patch) fused with the grey conversion and the /255 tensor conversion:
+ *   mode 0 (SuperGlueMatcher, matchers.py:911-917,263-274): cv2.cvtColor(RGB2GRAY) fixed point on u8, then /255.
+ *   mode 1 (LightGlueMatcher, matchers.py:1212-1220 + LightGlue/lightglue/utils.py:35-36): /255. per channel, then
+ *          0.299 r + 0.587 g + 0.114 b in f32.
+ * image [H,W,C] u8 (C = 1 or 3) on the device; tile = rows [y0, y0+th), cols [x0, x0+tw); out [th,tw] f32. */
+int i4d_tile_to_gray_f32(const unsigned char* image, int H, int W, int C, int x0, int y0, int tw, int th, int mode,
+                         float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
