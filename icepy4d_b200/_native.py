@@ -103,3 +103,34 @@ def current_stream() -> int:
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- kernel-launch accounting (the claim reported by bench.py as `gpu_launches`) ----------------------------
+LAUNCHES = 0
+_PER_CALL = {"i4d_sp_score_map": 1, "i4d_sp_nms_candidates": 1, "i4d_sp_select_topk": 1, "i4d_sp_sample_descriptors": 1,
+             "i4d_gemm_f32": 1, "i4d_attention_f32": 1, "i4d_layernorm_gelu": 1, "i4d_lg_posenc": 1, "i4d_lg_rotary": 1,
+             "i4d_sg_kenc_input": 1, "i4d_row_lse": 1, "i4d_col_lse": 2, "i4d_lg_assign": 10, "i4d_undistort_points": 1,
+             "i4d_triangulate_iterative_ls": 1, "i4d_triangulate_dlt": 1, "i4d_tile_to_gray_f32": 1}
+
+
+def _count(name: str, args) -> int:
+    if name in _PER_CALL:
+        return _PER_CALL[name]
+    if name == "i4d_sinkhorn":
+        return 5 * int(args[4])
+    if name == "i4d_sg_assign":
+        return 5 * int(args[4]) + 5
+    if name == "i4d_fundamental_ransac":
+        rounds = min(24, -(-int(args[5]) // 4096))
+        return 1 + 5 * rounds + 1 + 2 * int(args[8]) + 1
+    return 1
+
+
+_raw_call = call
+
+
+def call(name: str, *args):  # noqa: F811
+    global LAUNCHES
+    rc = _raw_call(name, *args)
+    LAUNCHES += _count(name, args)
+    return rc

@@ -173,7 +173,20 @@ class ImageMatcherBase(ImageMatcherABC):
 
         image0_, image1_ = self._resize_images(quality, image0, image1)
         dev0, dev1 = self._upload(image0_), self._upload(image1_)
+        mk0, mk1, s0, s1, conf, d0, d1, F = self.match_device(dev0, dev1, quality, tile_selection, **config)
+        self._F = F.cpu().numpy().reshape(3, 3) if F is not None else None
+        self._store_device_results(mk0, mk1, s0, s1, conf, d0, d1)
+        if self._save_dir is not None:
+            self.save_mkpts_as_txt(self._save_dir)
+        return True
 
+    def match_device(self, dev0: torch.Tensor, dev1: torch.Tensor, quality: Quality = Quality.HIGH,
+                     tile_selection: TileSelection = TileSelection.NONE, **config):
+        """Device-resident core of `match()`: u8 images already in HBM (already resized for `quality`) ->
+        (mkpts0, mkpts1, scores0, scores1, mconf, desc0 [S,256], desc1 [S,256], F [9] f64 or None), all on the device."""
+        gv_method = config.get("geometric_verification", GeometricVerification.PYDEGENSAC)
+        threshold = config.get("threshold", 1)
+        confidence = config.get("confidence", 0.9999)
         if tile_selection == TileSelection.NONE:
             logger.info("Matching full images...")
             res = self._match_tensors(dev0, dev1, (0, 0, dev0.shape[1], dev0.shape[0]), (0, 0, dev1.shape[1], dev1.shape[0]), **config)
@@ -189,19 +202,14 @@ class ImageMatcherBase(ImageMatcherABC):
             mk0, mk1 = mk0 * scale, mk1 * scale
         logger.info("Matching done!")
 
-        self._F = None
+        F = None
         if gv_method is not GeometricVerification.NONE:
             logger.info("Performing geometric verification...")
             F, mask = self._verify(mk0, mk1, gv_method, threshold, confidence)
-            if F is not None:
-                self._F = F.cpu().numpy().reshape(3, 3)
             idx = torch.nonzero(mask).squeeze(1)
             mk0, mk1, s0, s1, conf, d0, d1 = (t.index_select(0, idx) for t in (mk0, mk1, s0, s1, conf, d0, d1))
             logger.info("Geometric verification done.")
-        self._store_device_results(mk0, mk1, s0, s1, conf, d0, d1)
-        if self._save_dir is not None:
-            self.save_mkpts_as_txt(self._save_dir)
-        return True
+        return mk0, mk1, s0, s1, conf, d0, d1, F
 
     def _full_image_mconf(self, s0, conf):
         return s0.clone()          # SuperGlue: mconf = features0.scores[valid] (matchers.py:937-938)
