@@ -1,0 +1,167 @@
+"""Tensor-core (tcgen05 / TMEM / TMA) path: bf16-operand GEMM + flash attention wrappers and the SuperGlue / LightGlue
+layer schedules built on them.  f32 master copy of the residual stream, bf16 activations between kernels, f32
+accumulation everywhere (TMEM)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _st():
+    return N.current_stream()
+
+
+def gemm_tc(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            out32: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False):
+    """out = alpha * A @ W^T + bias (+relu) (+residual f32); A [M,K], W [N,K] bf16 (column slices allowed)."""
+    assert A.dtype == BF16 and W.dtype == BF16 and A.is_cuda and W.is_cuda and A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    Nn = W.shape[0]
+    assert W.shape[1] == K
+    assert out32 is not None or out16 is not None
+    ld = lambda t, n: t.stride(0) if t.shape[0] > 1 else max(n, t.stride(0))
+    N.call("i4d_gemm_bf16_tc", A, ld(A, K), W, ld(W, K), bias, residual, 0 if residual is None else ld(residual, Nn),
+           out32, 0 if out32 is None else ld(out32, Nn), out16, 0 if out16 is None else ld(out16, Nn), M, Nn, K, float(alpha),
+           int(relu), _st())
+    return out32 if out32 is not None else out16
+
+
+def attention_tc(X: torch.Tensor, problems: Sequence[Tuple[int, int, int, int]], out: torch.Tensor, q_col: int, k_col: int,
+                 v_col: int, heads: int = 4, scale: float = 0.125):
+    """X [rows, ld] bf16 holding Q/K/V column blocks; problems = [(q_row0, nq, k_row0, nk), ...]; out [rows, >=64*heads] bf16."""
+    assert X.dtype == BF16 and out.dtype == BF16 and X.is_contiguous() and out.stride(1) == 1
+    pr = np.ascontiguousarray(np.asarray(problems, dtype=np.int32).reshape(-1))
+    N.call("i4d_attention_bf16_tc", X, X.shape[0], X.shape[1], int(q_col), int(k_col), int(v_col), int(heads), pr, len(problems),
+           float(scale), out, out.stride(0), _st())
+    return out
+
+
+def to_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == torch.float32 and out.dtype == BF16 and x.stride(1) == 1 and out.stride(1) == 1
+    N.call("i4d_f32_to_bf16", x, x.stride(0), out, out.stride(0), x.shape[0], x.shape[1], _st())
+    return out
+
+
+N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1})
+
+
+class SuperGlueTensorCore:
+    """GNN (18 layers) + final projection + score matrix of SuperGlue on the tensor-core path (superglue.py:131-149,276-280)."""
+
+    def __init__(self, w, device):
+        self.dev = torch.device(device)
+        h = lambda t: t.to(BF16).contiguous()
+        self.layers = [{"wqkv": h(L["wqkv"]), "bqkv": L["bqkv"], "wm": h(L["wm"]), "bm": L["bm"], "w1": h(L["w1"]), "b1": L["b1"],
+                        "w2": h(L["w2"]), "b2": L["b2"]} for L in w.layers]
+        self.wf, self.bf = h(w.wf), w.bf
+        self._buf = {}
+
+    def _buffers(self, nt):
+        if self._buf.get("nt") != nt:
+            d = self.dev
+            self._buf = {"nt": nt, "x32": torch.empty((nt, 256), device=d), "xm": torch.empty((nt, 512), device=d, dtype=BF16),
+                         "qkv": torch.empty((nt, 768), device=d, dtype=BF16), "att": torch.empty((nt, 256), device=d, dtype=BF16),
+                         "hid": torch.empty((nt, 512), device=d, dtype=BF16), "md": torch.empty((nt, 256), device=d, dtype=BF16)}
+        return self._buf
+
+    def gnn_and_scores(self, d0: torch.Tensor, d1: torch.Tensor, collect=None) -> torch.Tensor:
+        n0, n1 = d0.shape[0], d1.shape[0]
+        nt = n0 + n1
+        b = self._buffers(nt)
+        x32, xm, qkv, att, hid, md = b["x32"], b["xm"], b["qkv"], b["att"], b["hid"], b["md"]
+        x32[:n0] = d0
+        x32[n0:] = d1
+        to_bf16(x32, xm[:, :256])
+        self_p = [(0, n0, 0, n0), (n0, n1, n0, n1)]
+        cross_p = [(0, n0, n0, n1), (n0, n1, 0, n0)]
+        for l, L in enumerate(self.layers):
+            gemm_tc(xm[:, :256], L["wqkv"], L["bqkv"], out16=qkv)
+            attention_tc(qkv, cross_p if l % 2 == 1 else self_p, att, 0, 256, 512)
+            gemm_tc(att, L["wm"], L["bm"], out16=xm[:, 256:])
+            gemm_tc(xm, L["w1"], L["b1"], out16=hid, relu=True)
+            gemm_tc(hid, L["w2"], L["b2"], residual=x32, out32=x32, out16=xm[:, :256])
+            if collect is not None:
+                collect.append((x32[:n0].clone(), x32[n0:].clone()))
+        gemm_tc(xm[:, :256], self.wf, self.bf, out16=md)
+        scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
+        gemm_tc(md[:n0], md[n0:], out32=scores, alpha=1.0 / 16.0)
+        return scores
+
+
+class LightGlueTensorCore:
+    """Self / cross / FFN blocks and the similarity matrix of LightGlue on the tensor-core path (lightglue.py:133-216,268-284)."""
+
+    def __init__(self, w, device):
+        self.dev = torch.device(device)
+        h = lambda t: t.to(BF16).contiguous()
+        self.h = {}
+        for L in w.layers:
+            for k in ("wqkv", "wo", "wqkv_x", "wo_x", "w1_s", "w2_s", "w1_x", "w2_x"):
+                self.h[id(L[k])] = h(L[k])
+        for A in w.assign:
+            self.h[id(A["wf"])] = h(A["wf"])
+
+    def _w(self, t):
+        return self.h[id(t)]
+
+    def _x16(self, xm: torch.Tensor) -> torch.Tensor:
+        """bf16 shadow [n,512] of the f32 [x | message] buffer, refreshed for the x half."""
+        x16 = torch.empty(xm.shape, device=xm.device, dtype=BF16)
+        to_bf16(xm[:, :256], x16[:, :256])
+        return x16
+
+    def ffn(self, xm, L, tag, x16=None):
+        x16 = self._x16(xm) if x16 is None else x16
+        n = xm.shape[0]
+        hid = torch.empty((n, 512), device=xm.device, dtype=torch.float32)
+        gemm_tc(x16, self._w(L[f"w1_{tag}"]), L[f"b1_{tag}"], out32=hid)
+        ops.layernorm_gelu(hid, L[f"g_{tag}"], L[f"be_{tag}"])
+        h16 = torch.empty((n, 512), device=xm.device, dtype=BF16)
+        to_bf16(hid, h16)
+        x = xm[:, :256]
+        gemm_tc(h16, self._w(L[f"w2_{tag}"]), L[f"b2_{tag}"], residual=x, out32=x)
+
+    def self_block(self, xm, cs, L):
+        n = xm.shape[0]
+        x16 = self._x16(xm)
+        qkv = torch.empty((n, 768), device=xm.device, dtype=torch.float32)
+        gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv)
+        ops.lg_rotary_(qkv[:, :256], cs)
+        ops.lg_rotary_(qkv[:, 256:512], cs)
+        q16 = torch.empty((n, 768), device=xm.device, dtype=BF16)
+        to_bf16(qkv, q16)
+        att = torch.empty((n, 256), device=xm.device, dtype=BF16)
+        attention_tc(q16, [(0, n, 0, n)], att, 0, 256, 512)
+        gemm_tc(att, self._w(L["wo"]), L["bo"], out16=x16[:, 256:])
+        self.ffn(xm, L, "s", x16)
+
+    def cross_block(self, xm0, xm1, L):
+        m, n = xm0.shape[0], xm1.shape[0]
+        x16 = torch.empty((m + n, 512), device=xm0.device, dtype=BF16)
+        to_bf16(xm0[:, :256], x16[:m, :256])
+        to_bf16(xm1[:, :256], x16[m:, :256])
+        p = torch.empty((m + n, 512), device=xm0.device, dtype=BF16)        # [qk | v] for both images
+        gemm_tc(x16[:, :256], self._w(L["wqkv_x"]), L["bqkv_x"], out16=p)
+        att = torch.empty((m + n, 256), device=xm0.device, dtype=BF16)
+        attention_tc(p, [(0, m, m, n), (m, n, 0, m)], att, 0, 0, 256)      # q and k share the `qk` projection
+        gemm_tc(att, self._w(L["wo_x"]), L["bo_x"], out16=x16[:, 256:])
+        self.ffn(xm0, L, "x", x16[:m])
+        self.ffn(xm1, L, "x", x16[m:])
+
+    def similarity(self, x0, x1, A):
+        m, n = x0.shape[0], x1.shape[0]
+        x16 = torch.empty((m + n, 256), device=x0.device, dtype=BF16)
+        to_bf16(x0, x16[:m])
+        to_bf16(x1, x16[m:])
+        md = torch.empty((m + n, 256), device=x0.device, dtype=BF16)
+        gemm_tc(x16, self._w(A["wf"]), A["bf"], out16=md)
+        sim = torch.empty((m, n), device=x0.device, dtype=torch.float32)
+        gemm_tc(md[:m], md[m:], out32=sim)
+        return sim

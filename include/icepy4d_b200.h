@@ -72,6 +72,22 @@ int i4d_lg_rotary(float* X, int ldx, int n, int heads, const float* cs, void* st
 int i4d_sg_kenc_input(const float* kpts, const float* scores, int n, float width, float height, float* out,
                       void* stream);
 
+/* ---- dense tensor-core building blocks (tcgen05 + TMEM + TMA, bf16 operands, f32 accumulation) ---------- */
+/* Same contraction as i4d_gemm_f32 with A [M,K] and W [N,K] in bf16 (K % 64 == 0, 16-byte aligned bases/pitches).
+ * Outputs: C32 (f32, nullable) and/or C16 (bf16, nullable) written by one fused epilogue
+ * (alpha, bias, ReLU, f32 residual R). */
+int i4d_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr,
+                     float* C32, int ldc32, void* C16, int ldc16, int M, int N, int K, float alpha, int relu,
+                     void* stream);
+/* Flash attention, head_dim 64, on one bf16 buffer X [rows, ld] holding Q, K and V as column blocks
+ * (q_col/k_col/v_col + 64*head).  problems_host: n_problems x {q_row0, nq, k_row0, nk} (host ints, 1..4 problems run in
+ * one launch: both images of a self/cross layer).  O [rows, ldo] bf16, row-indexed like Q.
+ * Replaces superglue.py:87-93 and lightglue.py:108-130 on the throughput path. */
+int i4d_attention_bf16_tc(const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads,
+                          const int* problems_host, int n_problems, float scale, void* O, int ldo, void* stream);
+/* row-major f32 -> bf16 with leading dimensions (cols % 4 == 0). */
+int i4d_f32_to_bf16(const float* X, int ldx, void* Y, int ldy, int rows, int cols, void* stream);
+
 /* ---- assignment --------------------------------------------------------------------------------------- */
 size_t i4d_assignment_workspace_bytes(int M, int N);
 /* out_i = LSE_j(scale * S_ij + coloff_j) / out_j = LSE_i(scale * S_ij + rowoff_i); offsets nullable. */

@@ -1,0 +1,104 @@
+"""GPU tests of the tensor-core path (tcgen05 GEMM + flash attention) against f64 references computed from the same
+bf16-rounded operands, and of the bf16 SuperGlue / LightGlue pipelines against the reference's golden matches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from icepy4d_b200 import weights  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def tc():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from icepy4d_b200 import ops_tc
+    return ops_tc
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 256), (1000, 768, 256), (257, 512, 512), (100, 1000, 128), (5, 8, 64)])
+def test_gemm_tc(tc, M, N, K):
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).bfloat16()
+    W = torch.randn(N, K, generator=gen).bfloat16()
+    b, R = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
+    ref = torch.relu(0.25 * (A.double() @ W.double().t()) + b.double()) + R.double()
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc(A.cuda(), W.cuda(), b.cuda(), residual=R.cuda(), out32=o32, out16=o16, alpha=0.25, relu=True)
+    assert torch.allclose(o32.cpu().double(), ref, atol=2e-4 * K ** 0.5, rtol=1e-5)      # f32 accumulation of exact bf16 products
+    assert torch.allclose(o16.cpu().double(), ref, atol=0.05, rtol=1e-2)                 # bf16 rounding of the output
+    # column-slice operands / outputs (leading dimensions)
+    big = torch.zeros(M, K + 64, dtype=torch.bfloat16)
+    big[:, :K] = A
+    out = torch.zeros(M, N + 16, device="cuda")
+    tc.gemm_tc(big.cuda()[:, :K], W.cuda(), None, out32=out[:, :N])
+    assert torch.allclose(out[:, :N].cpu().double(), A.double() @ W.double().t(), atol=2e-4 * K ** 0.5, rtol=1e-5)
+    assert float(out[:, N:].abs().max()) == 0.0
+
+
+def _attn_ref(q, k, v, scale=0.125):
+    qh, kh, vh = (t.double().view(t.shape[0], 4, 64).permute(1, 0, 2) for t in (q, k, v))
+    return (torch.softmax(qh @ kh.transpose(1, 2) * scale, -1) @ vh).permute(1, 0, 2).reshape(q.shape[0], 256)
+
+
+@pytest.mark.parametrize("n0,n1", [(128, 128), (300, 200), (1000, 777), (64, 1), (513, 1025)])
+def test_attention_tc_self_and_cross(tc, n0, n1):
+    gen = torch.Generator().manual_seed(n0 * 3 + n1)
+    nt = n0 + n1
+    X = (torch.randn(nt, 768, generator=gen) * 1.5).bfloat16()
+    q, k, v = X[:, :256], X[:, 256:512], X[:, 512:]
+    Xd = X.cuda()
+    out = torch.zeros(nt, 256, device="cuda", dtype=torch.bfloat16)
+    tc.attention_tc(Xd, [(0, n0, 0, n0), (n0, n1, n0, n1)], out, 0, 256, 512)
+    ref = torch.cat([_attn_ref(q[:n0], k[:n0], v[:n0]), _attn_ref(q[n0:], k[n0:], v[n0:])])
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 0.03, err                                       # P rounded to bf16 (2^-9 rel.) + bf16 output
+    out.zero_()
+    tc.attention_tc(Xd, [(0, n0, n0, n1), (n0, n1, 0, n0)], out, 0, 256, 512)
+    ref = torch.cat([_attn_ref(q[:n0], k[n0:], v[n0:]), _attn_ref(q[n0:], k[:n0], v[:n0])])
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 0.03, err
+
+
+def test_attention_tc_peaked_softmax(tc):
+    """Large logits (one dominant key per query) exercise the running-max rescaling across key blocks."""
+    gen = torch.Generator().manual_seed(9)
+    n = 700
+    X = torch.randn(n, 768, generator=gen)
+    X[:, :256] *= 6.0
+    X = X.bfloat16()
+    out = torch.zeros(n, 256, device="cuda", dtype=torch.bfloat16)
+    tc.attention_tc(X.cuda(), [(0, n, 0, n)], out, 0, 256, 512)
+    ref = _attn_ref(X[:, :256], X[:, 256:512], X[:, 512:])
+    assert (out.cpu().double() - ref).abs().max().item() < 0.05
+
+
+def test_superglue_bf16_matches_reference(golden_dir):
+    from icepy4d_b200.matching.superglue import SuperGlueB200
+    g = np.load(os.path.join(golden_dir, "sp_sg_small.npz"))
+    sg = SuperGlueB200(weights.make_superglue_state(2), sinkhorn_iterations=20, match_threshold=0.2, precision="bf16")
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    m0, m1, s0, s1 = sg.match(c("kpts0"), c("scores0"), c("desc0").t().contiguous(), g["image0"].shape,
+                              c("kpts1"), c("scores1"), c("desc1").t().contiguous(), g["image1"].shape)
+    a = {(i, int(j)) for i, j in enumerate(m0.cpu().numpy()) if j >= 0}
+    b = {(i, int(j)) for i, j in enumerate(g["matches0"]) if j >= 0}
+    iou = len(a & b) / max(1, len(a | b))
+    print("SuperGlue bf16 tensor-core match IoU vs reference:", iou, len(a), len(b))
+    assert iou >= 0.99, iou                                      # north-star gate
+
+
+def test_lightglue_bf16_matches_reference(golden_dir):
+    from icepy4d_b200.matching.lightglue import LightGlueB200
+    g = np.load(os.path.join(golden_dir, "lg_plain.npz"))
+    lg = LightGlueB200(weights.make_lightglue_state(3), precision="bf16", depth_confidence=-1, width_confidence=-1)
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    out = lg.match(c("kpts0"), c("desc0"), tuple(g["size0"]), c("kpts1"), c("desc1"), tuple(g["size1"]))
+    a = {(i, int(j)) for i, j in enumerate(out["matches0"].cpu().numpy()) if j >= 0}
+    b = {(i, int(j)) for i, j in enumerate(g["matches0"]) if j >= 0}
+    iou = len(a & b) / max(1, len(a | b))
+    print("LightGlue bf16 tensor-core match IoU vs reference:", iou, len(a), len(b))
+    assert iou >= 0.99, iou
