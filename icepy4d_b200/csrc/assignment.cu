@@ -288,8 +288,13 @@ extern "C" __attribute__((visibility("default"))) int i4d_col_lse(const float* S
 }
 
 // ---- Sinkhorn potentials ------------------------------------------------------------------------------
+static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
+                                 cudaStream_t st);
+static int g_sinkhorn_mode = 0;   // 0 = fused when the shape allows, 1 = always the two-pass kernels (tests / comparison)
+
 static void sinkhorn_iterations(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
                                 cudaStream_t st) {
+  if (g_sinkhorn_mode == 0 && sinkhorn_fused_launch(S, M, N, alpha, iters, u, v, w, st) == 0) return;
   const float norm = -logf((float)M + (float)N);
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
   cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
@@ -388,5 +393,285 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
                                                    matches0, mscores0);
   mutual_kernel1<<<i4d_cdiv(N, 256), 256, 0, st>>>(w.idx0, w.idx1, matches0, mscores0, N, matches1, mscores1);
   I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+// ====================================================================================================================
+// Fused persistent Sinkhorn (N <= 8192, N % 4 == 0): ONE read of the score matrix per iteration instead of two.
+//
+// One CTA per SM (cooperative launch), each owning a contiguous band of rows.  Rows are streamed HBM -> shared memory
+// with cp.async.bulk (1-D TMA) through a 3-stage mbarrier ring of 2 rows (<= 64 KB) per stage.  For every stage:
+//   phase A  row log-sum-exp of (S_ij + v_j) from shared memory (8 warps per row, warp-shuffle merge)  -> u_i
+//   phase B  the SAME shared-memory rows, now with the fresh u_i added, update per-thread running (max, sum) of the
+//            columns this thread owns (16 columns in registers for the whole band)
+// After the band: column partials -> workspace, grid barrier, all CTAs combine the partials into v_j (+ the dustbin
+// terms), grid barrier, next iteration.  Everything is kept in the log2 domain (one FFMA + one MUFU.EX2 per element and
+// pass).  HBM traffic per iteration = M*N*4 bytes (the algorithmic count of SURVEY.md §8d is 2*M*N*4).
+// ====================================================================================================================
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define SK_THREADS 512
+#define SK_ROWS 2                 // rows per stage
+#define SK_STAGES 3
+#define SK_MAXN 8192
+#define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
+
+struct L2Acc {   // running (max, sum) in the log2 domain, one exp per update
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add(float x) {
+    float d = x - m;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(d)));
+    s = (d > 0.f) ? fmaf(s, e, 1.f) : (s + e);
+    m = fmaxf(m, x);
+  }
+  __device__ __forceinline__ void merge(float om, float os) {
+    float nm = fmaxf(m, om);
+    if (nm == -INFINITY) return;
+    s = s * exp2f(m - nm) + os * exp2f(om - nm);
+    m = nm;
+  }
+  __device__ __forceinline__ float lse_ln() const { return (m + log2f(s)) * LN2; }
+};
+
+__device__ __forceinline__ void sk_mbar_init(uint64_t* b, uint32_t c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(c) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
+  uint32_t ok = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void sk_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, float alpha,
+                                                                       int iters, float* u, float* v, float* pm, float* ps,
+                                                                       int rows_per_cta) {
+  extern __shared__ __align__(128) unsigned char sk_smem[];
+  float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
+  float* v_s = stage_buf + (size_t)SK_STAGES * SK_ROWS * N;                     // [N] this iteration's v, pre-scaled by log2(e)
+  __shared__ __align__(8) uint64_t full[SK_STAGES];
+  __shared__ float part_m[SK_ROWS][8], part_s[SK_ROWS][8], u_s[SK_ROWS];
+  __shared__ float red_m[16], red_s[16];
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int row0 = min(M, cta * rows_per_cta), row1 = min(M, row0 + rows_per_cta);
+  const int nstage_total = (row1 - row0 + SK_ROWS - 1) / SK_ROWS;              // stages per iteration for this CTA
+  const float norm = -logf((float)M + (float)N);
+  const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
+  const uint32_t row_bytes = (uint32_t)N * 4u;
+  const int n4 = N >> 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < SK_STAGES; ++s) sk_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int st_idx, int buf) {       // thread 0 only: load stage `st_idx` of this CTA's band into buffer `buf`
+    const int r = row0 + st_idx * SK_ROWS;
+    const int nr = min(SK_ROWS, row1 - r);
+    sk_mbar_expect(&full[buf], nr * row_bytes);
+    for (int k = 0; k < nr; ++k)
+      sk_bulk_load(stage_buf + ((size_t)buf * SK_ROWS + k) * N, S + (size_t)(r + k) * N, row_bytes, &full[buf]);
+  };
+  // the band is re-streamed every iteration: stage sequence number q = it * nstage_total + st, kept SK_STAGES ahead
+  const uint32_t total_seq = (uint32_t)iters * (uint32_t)nstage_total;
+  uint32_t issued = 0, consumed = 0;
+  if (tid == 0)
+    while (issued < total_seq && issued < SK_STAGES) { issue(issued % nstage_total, issued % SK_STAGES); ++issued; }
+
+  // phase-A mapping: 8 warps per row, each warp a segment of N/8 columns
+  const int a_row = warp >> 3, a_seg = warp & 7;
+  const int seg4 = (n4 + 7) / 8;                 // float4 groups per segment
+  const int a_g0 = a_seg * seg4, a_g1 = min(n4, a_g0 + seg4);
+
+  for (int it = 0; it < iters; ++it) {
+    const float extra_row = (alpha + __ldcg(v + N)) * LOG2E;          // dustbin column term of every row LSE (old v)
+    L2Acc col[SK_GROUPS][4];
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) col[g][c].init();
+
+    for (int j = tid; j < N; j += SK_THREADS) v_s[j] = __ldcg(v + j) * LOG2E;
+    __syncthreads();
+    // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA; overlaps with its band work)
+    if (cta == G - 1) {
+      L2Acc a; a.init();
+      for (int j = tid; j <= N; j += SK_THREADS) a.add((alpha + __ldcg(v + j)) * LOG2E);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+      if (lane == 0) { red_m[warp] = a.m; red_s[warp] = a.s; }
+      __syncthreads();
+      if (tid == 0) {
+        L2Acc t; t.init();
+        for (int w = 0; w < SK_THREADS / 32; ++w) t.merge(red_m[w], red_s[w]);
+        u[M] = log_mu_last - t.lse_ln();
+      }
+      __syncthreads();
+    }
+
+    for (int st = 0; st < nstage_total; ++st) {
+      const int buf = consumed % SK_STAGES;
+      const uint32_t ph = (consumed / SK_STAGES) & 1;
+      sk_mbar_wait(&full[buf], ph);
+      const int r_base = row0 + st * SK_ROWS;
+      const int nr = min(SK_ROWS, row1 - r_base);
+      const float* sb = stage_buf + (size_t)buf * SK_ROWS * N;
+      // ---- phase A: row LSE with the old v ----
+      if (a_row < nr) {
+        L2Acc a, a1, a2, a3; a.init(); a1.init(); a2.init(); a3.init();     // 4 independent chains per lane (ILP)
+        const float4* rp = reinterpret_cast<const float4*>(sb + (size_t)a_row * N);
+        const float4* vp = reinterpret_cast<const float4*>(v_s);
+        for (int g = a_g0 + lane; g < a_g1; g += 32) {
+          float4 x = rp[g];
+          float4 o = vp[g];
+          a.add(fmaf(x.x, LOG2E, o.x)); a1.add(fmaf(x.y, LOG2E, o.y)); a2.add(fmaf(x.z, LOG2E, o.z)); a3.add(fmaf(x.w, LOG2E, o.w));
+        }
+        a.merge(a1.m, a1.s); a2.merge(a3.m, a3.s); a.merge(a2.m, a2.s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        if (lane == 0) { part_m[a_row][a_seg] = a.m; part_s[a_row][a_seg] = a.s; }
+      }
+      __syncthreads();
+      if (warp < nr) {
+        L2Acc a; a.init();
+        if (lane < 8) { a.m = part_m[warp][lane]; a.s = part_s[warp][lane]; }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        if (lane == 0) {
+          a.add(extra_row);
+          const float ui = norm - a.lse_ln();
+          u_s[warp] = ui;
+          u[r_base + warp] = ui;
+        }
+      }
+      __syncthreads();
+      // ---- phase B: column running (max, sum) with the fresh u ----
+      for (int k = 0; k < nr; ++k) {
+        const float ul = u_s[k] * LOG2E;
+        const float4* rp = reinterpret_cast<const float4*>(sb + (size_t)k * N);
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          const int gi = g * SK_THREADS + tid;
+          if (gi < n4) {
+            float4 x = rp[gi];
+            col[g][0].add(fmaf(x.x, LOG2E, ul)); col[g][1].add(fmaf(x.y, LOG2E, ul));
+            col[g][2].add(fmaf(x.z, LOG2E, ul)); col[g][3].add(fmaf(x.w, LOG2E, ul));
+          }
+        }
+      }
+      __syncthreads();                                       // everyone is done with this buffer
+      ++consumed;
+      if (tid == 0 && issued < total_seq) {   // refill the buffer just released (wraps into the next iteration: S never changes)
+        issue(issued % nstage_total, issued % SK_STAGES);
+        ++issued;
+      }
+    }
+    // ---- column partials of this CTA ----
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g) {
+      const int gi = g * SK_THREADS + tid;
+      if (gi < n4) {
+        float4 m4 = make_float4(col[g][0].m, col[g][1].m, col[g][2].m, col[g][3].m);
+        float4 s4 = make_float4(col[g][0].s, col[g][1].s, col[g][2].s, col[g][3].s);
+        reinterpret_cast<float4*>(pm + (size_t)cta * N)[gi] = m4;
+        reinterpret_cast<float4*>(ps + (size_t)cta * N)[gi] = s4;
+      }
+    }
+    grid.sync();
+    // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
+    {
+      const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
+      // (v_s is dead until the next iteration: reuse it for the 16 -> 1 merge)
+      float (*cmb_m)[32] = reinterpret_cast<float (*)[32]>(v_s);
+      float (*cmb_s)[32] = reinterpret_cast<float (*)[32]>(v_s + (SK_THREADS / 32) * 32);
+      // 32 columns per CTA round; warp w merges the partials of CTAs c = w, w+16, ... (coalesced), then 16 -> 1 via smem
+      for (int tile = cta; tile * 32 < N; tile += G) {
+        const int j = tile * 32 + lane;
+        L2Acc a; a.init();
+        if (j < N)
+          for (int c = warp; c < G; c += SK_THREADS / 32) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
+        cmb_m[warp][lane] = a.m; cmb_s[warp][lane] = a.s;
+        __syncthreads();
+        if (warp == 0 && j < N) {
+          for (int w2 = 1; w2 < SK_THREADS / 32; ++w2) a.merge(cmb_m[w2][lane], cmb_s[w2][lane]);
+          a.add(extra_col);
+          v[j] = norm - a.lse_ln();
+        }
+        __syncthreads();
+      }
+      if (cta == G - 1) {
+        L2Acc a; a.init();
+        for (int i = tid; i <= M; i += SK_THREADS) a.add((alpha + __ldcg(u + i)) * LOG2E);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        if (lane == 0) { red_m[warp] = a.m; red_s[warp] = a.s; }
+        __syncthreads();
+        if (tid == 0) {
+          L2Acc t; t.init();
+          for (int w = 0; w < SK_THREADS / 32; ++w) t.merge(red_m[w], red_s[w]);
+          v[N] = log_nu_last - t.lse_ln();
+        }
+      }
+    }
+    grid.sync();
+  }
+}
+
+static bool sinkhorn_fused_ok(int M, int N) { return N % 4 == 0 && N <= SK_MAXN && N >= 64 && M >= 1; }
+
+// returns 0 when the fused kernel ran, 1 when the shape is unsupported (caller falls back to the two-pass kernels)
+static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
+                                 cudaStream_t st) {
+  if (!sinkhorn_fused_ok(M, N) || iters <= 0) return 1;
+  static int coop = -1, sms = 0;
+  if (coop < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!coop || sms <= 0 || sms > 256) return 1;
+  const size_t smem = ((size_t)SK_STAGES * SK_ROWS * N + (size_t)(N > 1024 ? N : 1024)) * sizeof(float);   // stages + v (>= merge scratch)
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (SK_STAGES * SK_ROWS + 1) * SK_MAXN * (int)sizeof(float)) != cudaSuccess) { cudaGetLastError(); return 1; }
+    attr_set = true;
+  }
+  int G = sms;
+  int rpc = (M + G - 1) / G;
+  rpc = (rpc + SK_ROWS - 1) / SK_ROWS * SK_ROWS;
+  G = (M + rpc - 1) / rpc;                      // CTAs that actually own rows (<= sms <= 256 partial slots)
+  cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
+  cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);
+  float* pm = w.pm; float* ps = w.ps;
+  void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps, (void*)&rpc};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+  return 0;
+}
+
+// test / comparison hook: 0 = fused Sinkhorn when possible (default), 1 = always the two-pass kernels
+extern "C" __attribute__((visibility("default"))) int i4d_set_sinkhorn_mode(int mode) {
+  I4D_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+  g_sinkhorn_mode = mode;
   return I4D_OK;
 }

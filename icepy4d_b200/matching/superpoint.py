@@ -35,7 +35,7 @@ class SuperPointB200:
                  conv_precision: str = "tf32"):
         if not torch.cuda.is_available():
             raise RuntimeError("icepy4d_b200 needs a CUDA device (there is no CPU fallback)")
-        assert conv_precision in ("f32", "tf32", "bf16")
+        assert conv_precision in ("f32", "tf32", "f16", "bf16")
         self.device = torch.device(device)
         self.nms_radius, self.thr = int(nms_radius), float(keypoint_threshold)
         self.k = -1 if max_keypoints is None else int(max_keypoints)
@@ -43,9 +43,13 @@ class SuperPointB200:
             raise ValueError('"max_keypoints" must be positive or "-1"')
         self.border = int(remove_borders)
         self.conv_precision = conv_precision
-        wdt = torch.bfloat16 if conv_precision == "bf16" else torch.float32
+        # "f16": fp16 operands / f32 accumulation — the same 10-bit operand mantissa as TF32 (the precision torch's cuDNN
+        # convolutions use by default on the reference's CUDA path); the two 1x1 head convolutions stay f32/TF32 so that
+        # logits and raw descriptors are produced in f32.
+        self.act_dtype = {"bf16": torch.bfloat16, "f16": torch.float16}.get(conv_precision, torch.float32)
         self.w = {}
         for name in _CONVS:
+            wdt = torch.float32 if name in ("convPb", "convDb") else self.act_dtype
             w = state_dict[f"{name}.weight"].to(self.device, dtype=wdt).contiguous(memory_format=torch.channels_last)
             b = state_dict[f"{name}.bias"].to(self.device, dtype=wdt)
             self.w[name] = (w, b)
@@ -54,6 +58,9 @@ class SuperPointB200:
     # -- backbone (cuDNN through torch; channels-last so the heads come out HWC for the gather kernel) --
     def _conv(self, x, name, pad, relu=True):
         w, b = self.w[name]
+        if relu and self.conv_precision != "f32":
+            # cuDNN's fused conv+bias+ReLU epilogue: removes one full read+write of the activation per layer
+            return torch.cudnn_convolution_relu(x, w, b, (1, 1), (pad, pad), (1, 1), 1)
         y = F.conv2d(x, w, b, padding=pad)
         return F.relu_(y) if relu else y
 
@@ -62,8 +69,7 @@ class SuperPointB200:
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = self.conv_precision != "f32"
         try:
-            x = image.to(torch.bfloat16) if self.conv_precision == "bf16" else image
-            x = x.contiguous(memory_format=torch.channels_last)
+            x = image.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
             x = self._conv(self._conv(x, "conv1a", 1), "conv1b", 1)
             x = F.max_pool2d(x, 2, 2)
             x = self._conv(self._conv(x, "conv2a", 1), "conv2b", 1)
@@ -71,12 +77,12 @@ class SuperPointB200:
             x = self._conv(self._conv(x, "conv3a", 1), "conv3b", 1)
             x = F.max_pool2d(x, 2, 2)
             x = self._conv(self._conv(x, "conv4a", 1), "conv4b", 1)
-            logits = self._conv(self._conv(x, "convPa", 1), "convPb", 0, relu=False)
-            desc = self._conv(self._conv(x, "convDa", 1), "convDb", 0, relu=False)
+            logits = self._conv(self._conv(x, "convPa", 1).float(), "convPb", 0, relu=False)
+            desc = self._conv(self._conv(x, "convDa", 1).float(), "convDb", 0, relu=False)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        logits = logits[0].float().contiguous()                      # [65,h,w] planar
-        desc = desc[0].float().permute(1, 2, 0).contiguous()         # [h,w,256] (no copy when channels-last)
+        logits = logits[0].contiguous()                              # [65,h,w] planar
+        desc = desc[0].permute(1, 2, 0).contiguous()                 # [h,w,256] (no copy when channels-last)
         return logits, desc
 
     def postprocess(self, logits: torch.Tensor, desc_hwc: torch.Tensor, k: Optional[int] = None) -> DeviceFeatures:

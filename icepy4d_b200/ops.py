@@ -170,6 +170,11 @@ def col_lse(S: torch.Tensor, scale: float = 1.0, rowoff: Optional[torch.Tensor] 
     return out
 
 
+def set_sinkhorn_mode(mode: int) -> None:
+    """0 = fused persistent Sinkhorn when the shape allows (default), 1 = two-pass row/column kernels."""
+    N.call("i4d_set_sinkhorn_mode", int(mode))
+
+
 def sinkhorn(scores: torch.Tensor, bin_score: float, iters: int, ws=None) -> Tuple[torch.Tensor, torch.Tensor]:
     _chk(scores)
     M, N_ = scores.shape

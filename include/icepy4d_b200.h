@@ -97,6 +97,9 @@ int i4d_col_lse(const float* S, int M, int N, float scale, const float* rowoff, 
 /* superglue.py:152-186 — log-domain Sinkhorn potentials u[M+1], v[N+1] of the dustbin-augmented problem. */
 int i4d_sinkhorn(const float* scores, int M, int N, float bin_score, int iters, float* u, float* v, void* workspace,
                  size_t workspace_bytes, void* stream);
+/* Sinkhorn implementation switch (tests / comparisons): 0 = fused persistent kernel (one HBM read of the score matrix
+ * per iteration; used when N % 4 == 0 and 64 <= N <= 8192), 1 = always the two-pass row/column kernels. */
+int i4d_set_sinkhorn_mode(int mode);
 /* superglue.py:152-186 + :288-298 — Sinkhorn, then mutual nearest neighbours with threshold.
  * matches0 [M] / matches1 [N] int32 (-1 = unmatched), mscores0/1 f32; u [M+1], v [N+1] scratch/outputs. */
 int i4d_sg_assign(const float* scores, int M, int N, float bin_score, int iters, float match_threshold,
