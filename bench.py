@@ -278,7 +278,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--conv-precision", dest="conv_precision", default="tf32", choices=["f32", "tf32", "bf16"])
+    ap.add_argument("--conv-precision", dest="conv_precision", default="tf32", choices=["f32", "tf32", "f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -401,29 +401,43 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
 //
 // One CTA per SM (cooperative launch), each owning a contiguous band of rows.  Rows are streamed HBM -> shared memory
 // with cp.async.bulk (1-D TMA) through a 3-stage mbarrier ring of 2 rows (<= 64 KB) per stage.  For every stage:
-//   phase A  row log-sum-exp of (S_ij + v_j) from shared memory (8 warps per row, warp-shuffle merge)  -> u_i
-//   phase B  the SAME shared-memory rows, now with the fresh u_i added, update per-thread running (max, sum) of the
-//            columns this thread owns (16 columns in registers for the whole band)
-// After the band: column partials -> workspace, grid barrier, all CTAs combine the partials into v_j (+ the dustbin
-// terms), grid barrier, next iteration.  Everything is kept in the log2 domain (one FFMA + one MUFU.EX2 per element and
-// pass).  HBM traffic per iteration = M*N*4 bytes (the algorithmic count of SURVEY.md §8d is 2*M*N*4).
+//   phase A  row log-sum-exp of (S_ij + v_j) from shared memory (8 warps per row, warp-shuffle reduction)  -> u_i
+//   phase B  the SAME shared-memory rows, now with the fresh u_i added, update the per-thread accumulators of the
+//            16 columns this thread owns (registers, for the whole band)
+// Phase A of stage st+1 shares a barrier interval with phase B of stage st (software pipeline).  After the band: column
+// partials -> workspace, grid barrier, all CTAs combine the partials into v_j (+ the dustbin terms), grid barrier.
+//
+// Two arithmetic modes, same result up to f32 rounding:
+//   exact : running (max, sum) per accumulator — used for the first two iterations (and always if the fast mode trips);
+//   fast  : a-priori stabilisers instead of running maxima.  After a column update sum_i exp(S_ij + u_i + v_j) = nu_j, so
+//           S_ij + v_j <= log nu_j - u_i: m_i = log(nu_max) - u_i(previous) bounds every term of row i from above; likewise
+//           m_j = log(mu_max) - v_j(previous) for the columns.  One FFMA + FADD + MUFU.EX2 + FADD per element and pass, no
+//           dependent max chain.  A sum that underflows to 0 (potential jump > ~80 nats between two iterations) or is not
+//           finite raises a flag: the whole solve restarts in exact mode, on the device, without host involvement.
+// Everything is kept in the log2 domain.  HBM traffic per iteration = M*N*4 bytes (algorithmic count of SURVEY.md §8d: 2*M*N*4).
 // ====================================================================================================================
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define SK_THREADS 512
+#define SK_THREADS 1024
 #define SK_ROWS 2                 // rows per stage
 #define SK_STAGES 3
 #define SK_MAXN 8192
 #define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
+#define SK_EXACT_ITERS 2
+
+__device__ __forceinline__ float sk_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct L2Acc {   // running (max, sum) in the log2 domain, one exp per update
   float m, s;
   __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
   __device__ __forceinline__ void add(float x) {
     float d = x - m;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(d)));
+    float e = sk_ex2(-fabsf(d));
     s = (d > 0.f) ? fmaf(s, e, 1.f) : (s + e);
     m = fmaxf(m, x);
   }
@@ -433,6 +447,7 @@ struct L2Acc {   // running (max, sum) in the log2 domain, one exp per update
     s = s * exp2f(m - nm) + os * exp2f(om - nm);
     m = nm;
   }
+  __device__ __forceinline__ float lse_log2() const { return m + log2f(s); }
   __device__ __forceinline__ float lse_ln() const { return (m + log2f(s)) * LN2; }
 };
 
@@ -458,15 +473,155 @@ __device__ __forceinline__ void sk_bulk_load(void* dst, const void* src, uint32_
                : "memory");
 }
 
+
+struct SkCtx {
+  const float* S; float* stage_buf; uint64_t* full; float (*part_m)[SK_ROWS][SK_THREADS / 32]; float (*part_s)[SK_ROWS][SK_THREADS / 32];
+  float* u; const float* v; float* pm; float* ps; int* flag;
+  int M, N, n4, row0, row1, nstage_total, cta;
+  float norm, c_mu, c_nu, extra_row;
+  uint32_t row_bytes;
+};
+
+// One stage (SK_ROWS rows) of the band: elements of my columns -> registers, row-pass partials, ONE block barrier, then
+// every warp finishes the row reduction itself and runs the column pass from registers.  FAST = a-priori stabilisers,
+// FULL = all SK_ROWS rows and all SK_GROUPS column groups are present (straight-line code without predicates).
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consumed, uint32_t& issued, uint32_t total_seq,
+                                         const float (&vl)[SK_GROUPS][4], L2Acc (&col)[SK_GROUPS][4]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = c.N, n4 = c.n4;
+  const uint32_t seq = consumed;
+  const int buf = seq % SK_STAGES;
+  const int r_base = c.row0 + st * SK_ROWS;
+  const int nr = FULL ? SK_ROWS : min(SK_ROWS, c.row1 - r_base);
+  const float* sb = c.stage_buf + (size_t)buf * SK_ROWS * N;
+  float mrow[SK_ROWS];
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FAST && (FULL || k < nr)) ? (c.c_nu - __ldcg(c.u + r_base + k) * LOG2E) : 0.f;   // previous u
+  sk_mbar_wait(&c.full[buf], (seq / SK_STAGES) & 1);
+  float x[SK_ROWS][SK_GROUPS][4];
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k)
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g) {
+      const int gi = g * SK_THREADS + tid;
+      float4 t = (FULL || (k < nr && gi < n4)) ? reinterpret_cast<const float4*>(sb + (size_t)k * N)[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[k][g][0] = t.x * LOG2E; x[k][g][1] = t.y * LOG2E; x[k][g][2] = t.z * LOG2E; x[k][g][3] = t.w * LOG2E;
+    }
+  // ---- row pass partials (old v) ----
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k) {
+    if (FULL || k < nr) {
+      if (FAST) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          if (FULL || g * SK_THREADS + tid < n4) {
+            s0 += sk_ex2(x[k][g][0] + (vl[g][0] - mrow[k])) + sk_ex2(x[k][g][1] + (vl[g][1] - mrow[k]));
+            s1 += sk_ex2(x[k][g][2] + (vl[g][2] - mrow[k])) + sk_ex2(x[k][g][3] + (vl[g][3] - mrow[k]));
+          }
+        }
+        float sm = warp_sum(s0 + s1);
+        if (lane == 0) c.part_s[st & 1][k][warp] = sm;
+      } else {
+        L2Acc a, a1; a.init(); a1.init();
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          if (FULL || g * SK_THREADS + tid < n4) {
+            a.add(x[k][g][0] + vl[g][0]); a1.add(x[k][g][1] + vl[g][1]); a.add(x[k][g][2] + vl[g][2]); a1.add(x[k][g][3] + vl[g][3]);
+          }
+        }
+        a.merge(a1.m, a1.s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        if (lane == 0) { c.part_m[st & 1][k][warp] = a.m; c.part_s[st & 1][k][warp] = a.s; }
+      }
+    }
+  }
+  __syncthreads();              // partials published; every thread has its elements in registers -> the buffer is free
+  ++consumed;
+  if (tid == 0 && issued < total_seq) {   // refill the buffer just released (wraps into the next iteration: S never changes)
+    const int st_idx = issued % c.nstage_total, nbuf = issued % SK_STAGES;
+    const int r = c.row0 + st_idx * SK_ROWS;
+    const int nrr = min(SK_ROWS, c.row1 - r);
+    sk_mbar_expect(&c.full[nbuf], nrr * c.row_bytes);
+    for (int k = 0; k < nrr; ++k)
+      sk_bulk_load(c.stage_buf + ((size_t)nbuf * SK_ROWS + k) * N, c.S + (size_t)(r + k) * N, c.row_bytes, &c.full[nbuf]);
+    ++issued;
+  }
+  // ---- every warp finishes the row reduction itself (no second barrier), then the column pass from registers ----
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k) {
+    if (FULL || k < nr) {
+      float ui;
+      if (FAST) {
+        float sm = warp_sum(c.part_s[st & 1][k][lane]) + sk_ex2(c.extra_row - mrow[k]);
+        if (!(sm > 0.f && sm < INFINITY) && tid == 0) atomicExch(c.flag, 1);
+        ui = c.norm - (mrow[k] + log2f(sm)) * LN2;
+      } else {
+        L2Acc a;
+        a.m = c.part_m[st & 1][k][lane]; a.s = c.part_s[st & 1][k][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        a.add(c.extra_row);
+        ui = c.norm - a.lse_ln();
+      }
+      if (tid == 0) c.u[r_base + k] = ui;
+      const float ul = ui * LOG2E;
+#pragma unroll
+      for (int g = 0; g < SK_GROUPS; ++g) {
+        if (FULL || g * SK_THREADS + tid < n4) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (FAST) col[g][cc].s += sk_ex2(x[k][g][cc] + (ul - col[g][cc].m));
+            else col[g][cc].add(x[k][g][cc] + ul);
+          }
+        }
+      }
+    }
+  }
+}
+
+// One iteration's pass over this CTA's band (row pass + column pass), templated on the arithmetic mode so that no
+// per-element branch survives in the inner loops.
+template <bool FAST>
+__device__ __forceinline__ void sk_band(const SkCtx& c, uint32_t& consumed, uint32_t& issued, uint32_t total_seq) {
+  const int tid = threadIdx.x;
+  const int N = c.N, n4 = c.n4;
+  float vl[SK_GROUPS][4];                                          // old v of my columns, log2 domain
+  L2Acc col[SK_GROUPS][4];                                         // exact: (max, sum); fast: (stabiliser m_j, sum)
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    const int gi = g * SK_THREADS + tid;
+    float4 t = (gi < n4) ? __ldcg(reinterpret_cast<const float4*>(c.v) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    vl[g][0] = t.x * LOG2E; vl[g][1] = t.y * LOG2E; vl[g][2] = t.z * LOG2E; vl[g][3] = t.w * LOG2E;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) { col[g][cc].init(); if (FAST) col[g][cc].m = c.c_mu - vl[g][cc]; }
+  }
+  const bool full_cols = n4 == SK_GROUPS * SK_THREADS;
+  for (int st = 0; st < c.nstage_total; ++st) {
+    if (full_cols && c.row0 + (st + 1) * SK_ROWS <= c.row1) sk_stage<FAST, true>(c, st, consumed, issued, total_seq, vl, col);
+    else sk_stage<FAST, false>(c, st, consumed, issued, total_seq, vl, col);
+  }
+  // ---- column partials of this CTA ----
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    const int gi = g * SK_THREADS + tid;
+    if (gi < n4) {
+      if (!FAST) reinterpret_cast<float4*>(c.pm + (size_t)c.cta * N)[gi] = make_float4(col[g][0].m, col[g][1].m, col[g][2].m, col[g][3].m);
+      reinterpret_cast<float4*>(c.ps + (size_t)c.cta * N)[gi] = make_float4(col[g][0].s, col[g][1].s, col[g][2].s, col[g][3].s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, float alpha,
                                                                        int iters, float* u, float* v, float* pm, float* ps,
-                                                                       int rows_per_cta) {
+                                                                       int* flag, int rows_per_cta, int allow_fast) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
-  float* v_s = stage_buf + (size_t)SK_STAGES * SK_ROWS * N;                     // [N] this iteration's v, pre-scaled by log2(e)
   __shared__ __align__(8) uint64_t full[SK_STAGES];
-  __shared__ float part_m[SK_ROWS][8], part_s[SK_ROWS][8], u_s[SK_ROWS];
-  __shared__ float red_m[16], red_s[16];
+  __shared__ float part_m[2][SK_ROWS][SK_THREADS / 32], part_s[2][SK_ROWS][SK_THREADS / 32];
+  __shared__ float red_m[SK_THREADS / 32], red_s[SK_THREADS / 32];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -474,6 +629,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   const int nstage_total = (row1 - row0 + SK_ROWS - 1) / SK_ROWS;              // stages per iteration for this CTA
   const float norm = -logf((float)M + (float)N);
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
+  const float c_mu = fmaxf(norm, log_mu_last) * LOG2E, c_nu = fmaxf(norm, log_nu_last) * LOG2E;   // log2 of the largest marginals
   const uint32_t row_bytes = (uint32_t)N * 4u;
   const int n4 = N >> 2;
 
@@ -490,28 +646,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     for (int k = 0; k < nr; ++k)
       sk_bulk_load(stage_buf + ((size_t)buf * SK_ROWS + k) * N, S + (size_t)(r + k) * N, row_bytes, &full[buf]);
   };
-  // the band is re-streamed every iteration: stage sequence number q = it * nstage_total + st, kept SK_STAGES ahead
-  const uint32_t total_seq = (uint32_t)iters * (uint32_t)nstage_total;
+  // the band is re-streamed every iteration (S never changes): stages are numbered consecutively across iterations
+  uint32_t total_seq = (uint32_t)iters * (uint32_t)nstage_total;
   uint32_t issued = 0, consumed = 0;
   if (tid == 0)
     while (issued < total_seq && issued < SK_STAGES) { issue(issued % nstage_total, issued % SK_STAGES); ++issued; }
+  bool fast_ok = allow_fast != 0;
 
-  // phase-A mapping: 8 warps per row, each warp a segment of N/8 columns
-  const int a_row = warp >> 3, a_seg = warp & 7;
-  const int seg4 = (n4 + 7) / 8;                 // float4 groups per segment
-  const int a_g0 = a_seg * seg4, a_g1 = min(n4, a_g0 + seg4);
+  SkCtx ctx;
+  ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
+  ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
+  ctx.nstage_total = nstage_total; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = row_bytes;
 
   for (int it = 0; it < iters; ++it) {
-    const float extra_row = (alpha + __ldcg(v + N)) * LOG2E;          // dustbin column term of every row LSE (old v)
-    L2Acc col[SK_GROUPS][4];
-#pragma unroll
-    for (int g = 0; g < SK_GROUPS; ++g)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) col[g][c].init();
-
-    for (int j = tid; j < N; j += SK_THREADS) v_s[j] = __ldcg(v + j) * LOG2E;
-    __syncthreads();
-    // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA; overlaps with its band work)
+    const bool fast = fast_ok && it >= SK_EXACT_ITERS;
+    ctx.extra_row = (alpha + __ldcg(v + N)) * LOG2E;                  // dustbin column term of every row LSE (old v)
+    // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA; small)
     if (cta == G - 1) {
       L2Acc a; a.init();
       for (int j = tid; j <= N; j += SK_THREADS) a.add((alpha + __ldcg(v + j)) * LOG2E);
@@ -526,96 +676,47 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
       __syncthreads();
     }
-
-    for (int st = 0; st < nstage_total; ++st) {
-      const int buf = consumed % SK_STAGES;
-      const uint32_t ph = (consumed / SK_STAGES) & 1;
-      sk_mbar_wait(&full[buf], ph);
-      const int r_base = row0 + st * SK_ROWS;
-      const int nr = min(SK_ROWS, row1 - r_base);
-      const float* sb = stage_buf + (size_t)buf * SK_ROWS * N;
-      // ---- phase A: row LSE with the old v ----
-      if (a_row < nr) {
-        L2Acc a, a1, a2, a3; a.init(); a1.init(); a2.init(); a3.init();     // 4 independent chains per lane (ILP)
-        const float4* rp = reinterpret_cast<const float4*>(sb + (size_t)a_row * N);
-        const float4* vp = reinterpret_cast<const float4*>(v_s);
-        for (int g = a_g0 + lane; g < a_g1; g += 32) {
-          float4 x = rp[g];
-          float4 o = vp[g];
-          a.add(fmaf(x.x, LOG2E, o.x)); a1.add(fmaf(x.y, LOG2E, o.y)); a2.add(fmaf(x.z, LOG2E, o.z)); a3.add(fmaf(x.w, LOG2E, o.w));
-        }
-        a.merge(a1.m, a1.s); a2.merge(a3.m, a3.s); a.merge(a2.m, a2.s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-        if (lane == 0) { part_m[a_row][a_seg] = a.m; part_s[a_row][a_seg] = a.s; }
-      }
-      __syncthreads();
-      if (warp < nr) {
-        L2Acc a; a.init();
-        if (lane < 8) { a.m = part_m[warp][lane]; a.s = part_s[warp][lane]; }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-        if (lane == 0) {
-          a.add(extra_row);
-          const float ui = norm - a.lse_ln();
-          u_s[warp] = ui;
-          u[r_base + warp] = ui;
-        }
-      }
-      __syncthreads();
-      // ---- phase B: column running (max, sum) with the fresh u ----
-      for (int k = 0; k < nr; ++k) {
-        const float ul = u_s[k] * LOG2E;
-        const float4* rp = reinterpret_cast<const float4*>(sb + (size_t)k * N);
-#pragma unroll
-        for (int g = 0; g < SK_GROUPS; ++g) {
-          const int gi = g * SK_THREADS + tid;
-          if (gi < n4) {
-            float4 x = rp[gi];
-            col[g][0].add(fmaf(x.x, LOG2E, ul)); col[g][1].add(fmaf(x.y, LOG2E, ul));
-            col[g][2].add(fmaf(x.z, LOG2E, ul)); col[g][3].add(fmaf(x.w, LOG2E, ul));
-          }
-        }
-      }
-      __syncthreads();                                       // everyone is done with this buffer
-      ++consumed;
-      if (tid == 0 && issued < total_seq) {   // refill the buffer just released (wraps into the next iteration: S never changes)
-        issue(issued % nstage_total, issued % SK_STAGES);
-        ++issued;
-      }
-    }
-    // ---- column partials of this CTA ----
-#pragma unroll
-    for (int g = 0; g < SK_GROUPS; ++g) {
-      const int gi = g * SK_THREADS + tid;
-      if (gi < n4) {
-        float4 m4 = make_float4(col[g][0].m, col[g][1].m, col[g][2].m, col[g][3].m);
-        float4 s4 = make_float4(col[g][0].s, col[g][1].s, col[g][2].s, col[g][3].s);
-        reinterpret_cast<float4*>(pm + (size_t)cta * N)[gi] = m4;
-        reinterpret_cast<float4*>(ps + (size_t)cta * N)[gi] = s4;
-      }
-    }
+    // Each thread owns the same SK_GROUPS float4 column groups in BOTH passes: a stage's elements are read from shared memory
+    // once into registers, used for the row pass (old v, in registers for the whole iteration) and — after the block-wide row
+    // reduction gives u — again for the column pass.
+    if (fast) sk_band<true>(ctx, consumed, issued, total_seq);
+    else sk_band<false>(ctx, consumed, issued, total_seq);
     grid.sync();
     // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
     {
       const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
-      // (v_s is dead until the next iteration: reuse it for the 16 -> 1 merge)
-      float (*cmb_m)[32] = reinterpret_cast<float (*)[32]>(v_s);
-      float (*cmb_s)[32] = reinterpret_cast<float (*)[32]>(v_s + (SK_THREADS / 32) * 32);
-      // 32 columns per CTA round; warp w merges the partials of CTAs c = w, w+16, ... (coalesced), then 16 -> 1 via smem
-      for (int tile = cta; tile * 32 < N; tile += G) {
-        const int j = tile * 32 + lane;
-        L2Acc a; a.init();
-        if (j < N)
-          for (int c = warp; c < G; c += SK_THREADS / 32) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
-        cmb_m[warp][lane] = a.m; cmb_s[warp][lane] = a.s;
-        __syncthreads();
-        if (warp == 0 && j < N) {
-          for (int w2 = 1; w2 < SK_THREADS / 32; ++w2) a.merge(cmb_m[w2][lane], cmb_s[w2][lane]);
-          a.add(extra_col);
-          v[j] = norm - a.lse_ln();
+      // one warp per 8-column tile: lane = 8 * sub + col; each lane reduces the partials of CTAs c = sub, sub + 4, ...
+      // (32-byte coalesced loads), then a 2-step shuffle over `sub`.  No shared memory, no block barrier.
+      const int sub = lane >> 3, cl = lane & 7;
+      for (int tile = cta * (SK_THREADS / 32) + warp; tile * 8 < N; tile += G * (SK_THREADS / 32)) {
+        const int j = tile * 8 + cl;
+        if (fast) {
+          float sm = 0.f;
+          if (j < N) {
+#pragma unroll 4
+            for (int c = sub; c < G; c += 4) sm += __ldcg(ps + (size_t)c * N + j);
+          }
+          sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+          sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+          if (sub == 0 && j < N) {
+            const float mj = c_mu - __ldcg(v + j) * LOG2E;            // the stabiliser used above (old v)
+            sm += sk_ex2(extra_col - mj);
+            if (!(sm > 0.f && sm < INFINITY)) atomicExch(flag, 1);
+            v[j] = norm - (mj + log2f(sm)) * LN2;
+          }
+        } else {
+          L2Acc a; a.init();
+          if (j < N) {
+#pragma unroll 2
+            for (int c = sub; c < G; c += 4) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
+          }
+          a.merge(__shfl_xor_sync(0xffffffffu, a.m, 8), __shfl_xor_sync(0xffffffffu, a.s, 8));
+          a.merge(__shfl_xor_sync(0xffffffffu, a.m, 16), __shfl_xor_sync(0xffffffffu, a.s, 16));
+          if (sub == 0 && j < N) {
+            a.add(extra_col);
+            v[j] = norm - a.lse_ln();
+          }
         }
-        __syncthreads();
       }
       if (cta == G - 1) {
         L2Acc a; a.init();
@@ -632,10 +733,22 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
     }
     grid.sync();
+    if (fast_ok && __ldcg(flag) != 0) {
+      // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode
+      fast_ok = false;
+      for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
+      for (int i = cta * SK_THREADS + tid; i <= M; i += G * SK_THREADS) u[i] = 0.f;
+      total_seq = consumed + (uint32_t)iters * (uint32_t)nstage_total;
+      if (tid == 0)
+        while (issued < total_seq && issued - consumed < SK_STAGES) { issue(issued % nstage_total, issued % SK_STAGES); ++issued; }
+      it = -1;
+      grid.sync();
+    }
   }
 }
 
 static bool sinkhorn_fused_ok(int M, int N) { return N % 4 == 0 && N <= SK_MAXN && N >= 64 && M >= 1; }
+static int g_sinkhorn_fast = 1;   // 1 = a-priori stabilisers after the first two iterations, 0 = running maxima throughout
 
 // returns 0 when the fused kernel ran, 1 when the shape is unsupported (caller falls back to the two-pass kernels)
 static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
@@ -649,11 +762,11 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (!coop || sms <= 0 || sms > 256) return 1;
-  const size_t smem = ((size_t)SK_STAGES * SK_ROWS * N + (size_t)(N > 1024 ? N : 1024)) * sizeof(float);   // stages + v (>= merge scratch)
+  const size_t smem = (size_t)SK_STAGES * SK_ROWS * N * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (SK_STAGES * SK_ROWS + 1) * SK_MAXN * (int)sizeof(float)) != cudaSuccess) { cudaGetLastError(); return 1; }
+                             SK_STAGES * SK_ROWS * SK_MAXN * (int)sizeof(float)) != cudaSuccess) { cudaGetLastError(); return 1; }
     attr_set = true;
   }
   int G = sms;
@@ -663,7 +776,11 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
   cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);
   float* pm = w.pm; float* ps = w.ps;
-  void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps, (void*)&rpc};
+  int* flag = w.pi;
+  cudaMemsetAsync(flag, 0, sizeof(int), st);
+  int allow_fast = g_sinkhorn_fast;
+  void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
+                  (void*)&flag, (void*)&rpc, (void*)&allow_fast};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;
@@ -671,7 +788,8 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
 
 // test / comparison hook: 0 = fused Sinkhorn when possible (default), 1 = always the two-pass kernels
 extern "C" __attribute__((visibility("default"))) int i4d_set_sinkhorn_mode(int mode) {
-  I4D_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
-  g_sinkhorn_mode = mode;
+  I4D_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (fused, fast stabilisers), 1 (two-pass kernels) or 2 (fused, running maxima)");
+  g_sinkhorn_mode = mode == 1 ? 1 : 0;
+  g_sinkhorn_fast = mode == 0 ? 1 : 0;
   return I4D_OK;
 }

@@ -1,0 +1,19 @@
+"""Small driver for ncu captures of the dominant kernels at cfg2 sizes (one launch each after warm-up)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from icepy4d_b200 import ops, ops_tc
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+N = 8192
+if which in ("sinkhorn", "all"):
+    S = torch.randn(N, N, device="cuda") * 3
+    ws = ops.AssignWorkspace(N, N, S.device)
+    for _ in range(2):
+        ops.sinkhorn(S, 1.0, 6, ws)
+    torch.cuda.synchronize()
+if which in ("attn", "all"):
+    qkv = torch.randn(2 * N, 768, device="cuda").bfloat16()
+    att = torch.empty(2 * N, 256, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        ops_tc.attention_tc(qkv, [(0, N, 0, N), (N, N, N, N)], att, 0, 256, 512)
+    torch.cuda.synchronize()

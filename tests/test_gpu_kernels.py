@@ -166,10 +166,10 @@ def test_row_col_lse(ops, M, N):
     assert torch.allclose(c, torch.logsumexp(S + ro[:, None], 0), atol=1e-4)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,N,iters", [(5, 7, 3), (200, 256, 20), (513, 300, 100), (1, 64, 4), (2500, 4096, 30), (700, 8192, 5)])
 def test_sinkhorn_and_sg_assign(ops, M, N, iters, mode):
-    """mode 0: fused persistent kernel (single HBM read per iteration) where the shape allows; mode 1: two-pass kernels."""
+    """mode 0: fused persistent kernel, a-priori stabilisers after 2 iterations; mode 1: two-pass kernels; mode 2: fused, running maxima."""
     ops.set_sinkhorn_mode(mode)
     try:
         _sinkhorn_case(ops, M, N, iters)
