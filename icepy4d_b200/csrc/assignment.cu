@@ -425,6 +425,7 @@ namespace cg = cooperative_groups;
 #define SK_MAXN 8192
 #define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
 #define SK_EXACT_ITERS 2
+#define SK_MAX_BAND 1024            // rows per CTA the previous-u staging buffer can hold
 
 __device__ __forceinline__ float sk_ex2(float x) {
   float y;
@@ -479,6 +480,7 @@ struct SkCtx {
   float* u; const float* v; float* pm; float* ps; int* flag;
   int M, N, n4, row0, row1, nstage_total, cta;
   float norm, c_mu, c_nu, extra_row;
+  const float* uold_s;   // previous-iteration u of this CTA's band, pre-scaled by log2(e) (shared memory)
   uint32_t row_bytes;
 };
 
@@ -497,7 +499,7 @@ __device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consu
   const float* sb = c.stage_buf + (size_t)buf * SK_ROWS * N;
   float mrow[SK_ROWS];
 #pragma unroll
-  for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FAST && (FULL || k < nr)) ? (c.c_nu - __ldcg(c.u + r_base + k) * LOG2E) : 0.f;   // previous u
+  for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FAST && (FULL || k < nr)) ? (c.c_nu - c.uold_s[st * SK_ROWS + k]) : 0.f;   // previous u
   sk_mbar_wait(&c.full[buf], (seq / SK_STAGES) & 1);
   float x[SK_ROWS][SK_GROUPS][4];
 #pragma unroll
@@ -557,7 +559,7 @@ __device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consu
       if (FAST) {
         float sm = warp_sum(c.part_s[st & 1][k][lane]) + sk_ex2(c.extra_row - mrow[k]);
         if (!(sm > 0.f && sm < INFINITY) && tid == 0) atomicExch(c.flag, 1);
-        ui = c.norm - (mrow[k] + log2f(sm)) * LN2;
+        ui = c.norm - (mrow[k] + __log2f(sm)) * LN2;
       } else {
         L2Acc a;
         a.m = c.part_m[st & 1][k][lane]; a.s = c.part_s[st & 1][k][lane];
@@ -622,6 +624,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   __shared__ __align__(8) uint64_t full[SK_STAGES];
   __shared__ float part_m[2][SK_ROWS][SK_THREADS / 32], part_s[2][SK_ROWS][SK_THREADS / 32];
   __shared__ float red_m[SK_THREADS / 32], red_s[SK_THREADS / 32];
+  __shared__ float uold_s[SK_MAX_BAND];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -656,6 +659,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   SkCtx ctx;
   ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
   ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
+  ctx.uold_s = uold_s;
   ctx.nstage_total = nstage_total; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = row_bytes;
 
   for (int it = 0; it < iters; ++it) {
@@ -679,6 +683,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     // Each thread owns the same SK_GROUPS float4 column groups in BOTH passes: a stage's elements are read from shared memory
     // once into registers, used for the row pass (old v, in registers for the whole iteration) and — after the block-wide row
     // reduction gives u — again for the column pass.
+    for (int i = tid; i < row1 - row0; i += SK_THREADS) uold_s[i] = __ldcg(u + row0 + i) * LOG2E;
+    __syncthreads();
     if (fast) sk_band<true>(ctx, consumed, issued, total_seq);
     else sk_band<false>(ctx, consumed, issued, total_seq);
     grid.sync();
@@ -772,6 +778,7 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   int G = sms;
   int rpc = (M + G - 1) / G;
   rpc = (rpc + SK_ROWS - 1) / SK_ROWS * SK_ROWS;
+  if (rpc > SK_MAX_BAND) return 1;
   G = (M + rpc - 1) / rpc;                      // CTAs that actually own rows (<= sms <= 256 partial slots)
   cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
   cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);

@@ -9,7 +9,7 @@ if which in ("sinkhorn", "all"):
     S = torch.randn(N, N, device="cuda") * 3
     ws = ops.AssignWorkspace(N, N, S.device)
     for _ in range(2):
-        ops.sinkhorn(S, 1.0, 6, ws)
+        ops.sinkhorn(S, 1.0, 20, ws)
     torch.cuda.synchronize()
 if which in ("attn", "all"):
     qkv = torch.randn(2 * N, 768, device="cuda").bfloat16()
