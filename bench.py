@@ -147,35 +147,36 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def _dominant_kernel_roofline(precision: str, peaks):
-    """Times the Sinkhorn streaming passes (row LSE + column LSE over the 8192x8192 f32 score matrix, the kernels the
-    100-iteration optimal transport spends its time in) with CUDA events on the launch stream.
-    Algorithmic bytes per launch pair: 2 * M * N * 4 (one read of the matrix per pass)."""
+    """Times the fused persistent Sinkhorn kernel (the HBM-bound kernel the 100-iteration optimal transport lives in: 600
+    iterations over 8192x8192 f32 score matrices per epoch) with CUDA events on the launch stream.
+    Algorithmic bytes per iteration = 2 * M * N * 4 (one read of the matrix per LSE pass, two passes per
+    iteration).  The kernel fuses both passes over one staged read, so its measured DRAM traffic (ncu, profiles/) is
+    M * N * 4 per iteration and `frac` can exceed 1 against the copy-bandwidth peak."""
     from icepy4d_b200 import ops
 
     M = N = KP
-    S = torch.randn(M, N, device="cuda")
+    S = torch.randn(M, N, device="cuda") * 3
     ws = ops.AssignWorkspace(M, N, S.device)
-    v = torch.zeros(N, device="cuda")
-    u = torch.zeros(M, device="cuda")
-    out = {}
-    for name, fn in (("row", lambda: ops.row_lse(S, 1.0, v)), ("col", lambda: ops.col_lse(S, 1.0, u, ws))):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        out[name] = e0.elapsed_time(e1) / reps
-    bytes_pair = 2.0 * M * N * 4
-    gbs = bytes_pair / ((out["row"] + out["col"]) * 1e-3) / 1e9
+    iters = SINKHORN_ITERS
+    for _ in range(3):
+        ops.sinkhorn(S, 1.0, iters, ws)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        ops.sinkhorn(S, 1.0, iters, ws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_launch = e0.elapsed_time(e1) / reps
+    bytes_launch = 2.0 * M * N * 4 * iters
+    gbs = bytes_launch / (ms_launch * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": None, "kernel": "row_reduce_kernel<0> + col_partial_kernel<0> (Sinkhorn LSE passes, 8192x8192 f32)",
-            "ms_row": out["row"], "ms_col": out["col"], "peak_source": peaks["source"],
-            "algorithmic_bytes_per_launch_pair": bytes_pair}
+            "traffic": float(M) * N * 4 * iters + 2.0 * 147 * N * 4 * iters,
+            "kernel": "sinkhorn_fused_kernel (100 iterations, 8192x8192 f32, one launch)", "ms_per_launch": ms_launch,
+            "us_per_iteration": ms_launch * 1e3 / iters, "peak_source": peaks["source"],
+            "algorithmic_bytes_per_launch": bytes_launch,
+            "note": "traffic = one HBM read of the matrix per iteration (ncu dram__bytes_read 269 MB/iter, profiles/) + column partials"}
 
 
 def run_ours(args):

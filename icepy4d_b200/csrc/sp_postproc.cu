@@ -49,20 +49,19 @@ __global__ void __launch_bounds__(128) sp_score_map_kernel(const float* __restri
 //    scores within 5r (5 chained (2r+1)^2 max-pools), so one HBM read of the tile(+halo) suffices.
 // ---------------------------------------------------------------------------------------------------
 #define NMS_T 64
-#define NMS_THREADS 256
+#define NMS_THREADS 1024
+#define NMS_WARPS (NMS_THREADS / 32)
 
-struct NmsSmem {
-  float* S0; float* T1; float* X; unsigned char* M; unsigned char* P;
-};
+// 2-D sweep of the D x D staging tile: warp w takes rows w, w + 32, ...; lanes stride the row (no integer division)
+#define NMS_FOR_TILE(y, x, D) for (int y = (int)(threadIdx.x >> 5); y < (D); y += NMS_WARPS) for (int x = (int)(threadIdx.x & 31); x < (D); x += 32)
 
 template <typename F>
 __device__ __forceinline__ void nms_rowmax(const F& src, float* __restrict__ dst, int D, int r) {
-  for (int i = threadIdx.x; i < D * D; i += NMS_THREADS) {
-    int y = i / D, x = i - y * D;
+  NMS_FOR_TILE(y, x, D) {
     int x0 = max(x - r, 0), x1 = min(x + r, D - 1);
     float m = -INFINITY;
     for (int xx = x0; xx <= x1; ++xx) m = fmaxf(m, src(y * D + xx));
-    dst[i] = m;
+    dst[y * D + x] = m;
   }
 }
 __device__ __forceinline__ float nms_colmax(const float* __restrict__ t, int D, int r, int y, int x) {
@@ -87,48 +86,37 @@ __global__ void __launch_bounds__(NMS_THREADS) sp_nms_kernel(const float* __rest
   __shared__ int s_n, s_base;
 
   const int ty0 = blockIdx.y * NMS_T - halo, tx0 = blockIdx.x * NMS_T - halo;
-  auto inimg = [&](int i) {
-    int y = i / D, x = i - y * D;
+  auto inimg = [&](int y, int x) {
     int gy = ty0 + y, gx = tx0 + x;
     return gy >= 0 && gy < H && gx >= 0 && gx < W;
   };
-  for (int i = threadIdx.x; i < D * D; i += NMS_THREADS) {
-    int y = i / D, x = i - y * D;
-    int gy = ty0 + y, gx = tx0 + x;
-    S0[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(scores + (size_t)gy * W + gx) : -INFINITY;
-  }
+  NMS_FOR_TILE(y, x, D) S0[y * D + x] = inimg(y, x) ? __ldg(scores + (size_t)(ty0 + y) * W + (tx0 + x)) : -INFINITY;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   nms_rowmax([&](int j) { return S0[j]; }, T1, D, r);
   __syncthreads();
-  for (int i = threadIdx.x; i < D * D; i += NMS_THREADS) {
-    int y = i / D, x = i - y * D;
-    M[i] = (inimg(i) && S0[i] == nms_colmax(T1, D, r, y, x)) ? 1 : 0;
-  }
+  NMS_FOR_TILE(y, x, D) M[y * D + x] = (inimg(y, x) && S0[y * D + x] == nms_colmax(T1, D, r, y, x)) ? 1 : 0;
   __syncthreads();
   for (int it = 0; it < 2; ++it) {
     nms_rowmax([&](int j) { return M[j] ? 1.f : 0.f; }, T1, D, r);
     __syncthreads();
-    for (int i = threadIdx.x; i < D * D; i += NMS_THREADS) {
-      int y = i / D, x = i - y * D;
+    NMS_FOR_TILE(y, x, D) {
       bool supp = nms_colmax(T1, D, r, y, x) > 0.f;
-      P[i] = supp ? 1 : 0;
-      X[i] = inimg(i) ? (supp ? 0.f : S0[i]) : -INFINITY;
+      P[y * D + x] = supp ? 1 : 0;
+      X[y * D + x] = inimg(y, x) ? (supp ? 0.f : S0[y * D + x]) : -INFINITY;
     }
     __syncthreads();
     nms_rowmax([&](int j) { return X[j]; }, T1, D, r);
     __syncthreads();
-    for (int i = threadIdx.x; i < D * D; i += NMS_THREADS) {
-      int y = i / D, x = i - y * D;
-      bool nm = inimg(i) && (X[i] == nms_colmax(T1, D, r, y, x));
-      if (nm && !P[i]) M[i] = 1;
+    NMS_FOR_TILE(y, x, D) {
+      bool nm = inimg(y, x) && (X[y * D + x] == nms_colmax(T1, D, r, y, x));
+      if (nm && !P[y * D + x]) M[y * D + x] = 1;
     }
     __syncthreads();
   }
   // threshold + border + block-aggregated compaction (X is free now: reuse it as the per-CTA key list)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(X);
-  for (int i = threadIdx.x; i < NMS_T * NMS_T; i += NMS_THREADS) {
-    int y = i / NMS_T, x = i - y * NMS_T;
+  NMS_FOR_TILE(y, x, NMS_T) {
     int gy = blockIdx.y * NMS_T + y, gx = blockIdx.x * NMS_T + x;
     if (gy >= H || gx >= W) continue;
     int si = (y + halo) * D + (x + halo);
@@ -264,6 +252,163 @@ __global__ void __launch_bounds__(SEL_THREADS) sp_topk_kernel(const unsigned lon
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 3b. multi-CTA top-k for 1 <= k <= 16384 (the production path: k = 2048..16384 of ~10^5 candidates).
+//     Radix select on the 32 score bits in three grid-wide histogram passes (11 + 11 + 10 bits), one compaction pass
+//     (score > T straight to the output list, score == T to a tie list), and a single-CTA finish (ties by lowest
+//     index, bitonic sort in shared memory, emit).  Same result and order as sp_topk_kernel.
+// ---------------------------------------------------------------------------------------------------
+#define TK_BINS 2048
+struct TopkState {
+  unsigned int hist[3][TK_BINS];
+  unsigned long long prefix;      // selected high bits of the 64-bit key so far
+  int remaining;                  // how many keys are still needed inside the current prefix bucket
+  int n, m, keep_all;
+  int n_gt, n_tie;
+};
+__device__ __forceinline__ int tk_shift(int pass) { return pass == 0 ? 53 : (pass == 1 ? 42 : 32); }
+__device__ __forceinline__ unsigned int tk_digit(unsigned long long key, int pass) {
+  return pass == 2 ? (unsigned int)(key >> 32) & 1023u : (unsigned int)(key >> tk_shift(pass)) & 2047u;
+}
+
+__global__ void topk_init_kernel(const int* __restrict__ cand_count, int cand_cap, int k, int out_cap, TopkState* st,
+                                 int* __restrict__ n_out) {
+  for (int i = threadIdx.x; i < 3 * TK_BINS; i += blockDim.x) (&st->hist[0][0])[i] = 0u;
+  if (threadIdx.x == 0) {
+    int n = min(*cand_count, cand_cap);
+    int keep_all = n <= k;
+    int m = keep_all ? n : k;
+    if (m > out_cap) m = out_cap;
+    st->n = n; st->m = m; st->keep_all = keep_all; st->prefix = 0ull; st->remaining = k; st->n_gt = 0; st->n_tie = 0;
+    *n_out = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) topk_hist_kernel(const unsigned long long* __restrict__ cand, TopkState* st, int pass) {
+  __shared__ unsigned int h[TK_BINS];
+  if (st->keep_all) return;
+  for (int i = threadIdx.x; i < TK_BINS; i += blockDim.x) h[i] = 0u;
+  __syncthreads();
+  const int n = st->n;
+  const unsigned long long prefix = st->prefix;
+  const int hs = pass == 0 ? 64 : tk_shift(pass - 1);          // bits above this are fixed by the prefix
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long key = cand[i];
+    bool match = (hs >= 64) || ((key >> hs) == (prefix >> hs));
+    if (match) atomicAdd(&h[tk_digit(key, pass)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TK_BINS; i += blockDim.x)
+    if (h[i]) atomicAdd(&st->hist[pass][i], h[i]);
+}
+
+__global__ void __launch_bounds__(1024) topk_scan_kernel(TopkState* st, int pass) {
+  // find the highest bin b with (count of keys in bins > b) < remaining <= (count in bins >= b)
+  __shared__ unsigned int part[1024];
+  if (st->keep_all) return;
+  const int t = threadIdx.x;
+  // two bins per thread, processed from the top: thread t owns bins 2047-2t and 2046-2t
+  unsigned int c0 = st->hist[pass][TK_BINS - 1 - 2 * t], c1 = st->hist[pass][TK_BINS - 2 - 2 * t];
+  part[t] = c0 + c1;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {                  // inclusive scan from the top
+    unsigned int v = (t >= off) ? part[t - off] : 0u;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  const unsigned int rem = (unsigned int)st->remaining;
+  const unsigned int above = part[t] - (c0 + c1);              // keys in bins above my pair
+  if (above < rem && rem <= part[t]) {
+    int b; unsigned int gt;
+    if (above + c0 >= rem) { b = TK_BINS - 1 - 2 * t; gt = above; }
+    else { b = TK_BINS - 2 - 2 * t; gt = above + c0; }
+    st->prefix |= (unsigned long long)b << tk_shift(pass);
+    st->remaining = (int)(rem - gt);
+  }
+}
+
+__global__ void __launch_bounds__(256) topk_compact_kernel(const unsigned long long* __restrict__ cand, TopkState* st,
+                                                           unsigned long long* __restrict__ sel, unsigned long long* __restrict__ ties) {
+  if (st->keep_all) return;
+  const int n = st->n;
+  const unsigned int T = (unsigned int)(st->prefix >> 32);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long key = cand[i];
+    unsigned int sc = (unsigned int)(key >> 32);
+    if (sc > T) sel[atomicAdd(&st->n_gt, 1)] = key;
+    else if (sc == T) ties[atomicAdd(&st->n_tie, 1)] = key;
+  }
+}
+
+// block-wide: k-th largest 64-bit key of a[0..n) (1 <= k <= n), 8 passes of 8 bits
+__device__ unsigned long long block_radix_kth(const unsigned long long* __restrict__ a, int n, int k, unsigned int* hist,
+                                              unsigned long long* s_prefix, int* s_remaining) {
+  if (threadIdx.x == 0) { *s_prefix = 0ull; *s_remaining = k; }
+  __syncthreads();
+  for (int pass = 7; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int shift = pass * 8;
+    const unsigned long long pmask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+    const unsigned long long prefix = *s_prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned long long key = a[i];
+      if ((key & pmask) == prefix) atomicAdd(&hist[(unsigned int)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int rem = *s_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if ((int)hist[b] >= rem) break;
+        rem -= (int)hist[b];
+      }
+      *s_remaining = rem;
+      *s_prefix = prefix | ((unsigned long long)b << shift);
+    }
+    __syncthreads();
+  }
+  return *s_prefix;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) topk_finish_kernel(const unsigned long long* __restrict__ cand, TopkState* st, int W,
+                                                                  const unsigned long long* __restrict__ sel,
+                                                                  const unsigned long long* __restrict__ ties,
+                                                                  float* __restrict__ kpts, float* __restrict__ sc) {
+  extern __shared__ __align__(16) unsigned long long skeys[];  // SEL_MAX_SMEM_KEYS
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_cnt;
+  const int m = st->m, keep_all = st->keep_all;
+  int p2 = 1;
+  while (p2 < m) p2 <<= 1;
+  for (int i = threadIdx.x; i < p2; i += blockDim.x) skeys[i] = 0ull;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if (keep_all) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { unsigned long long key = cand[i]; skeys[i] = (key << 32) | (key >> 32); }
+  } else {
+    const int n_gt = min(st->n_gt, m), n_tie = st->n_tie, need = min(st->remaining, m - n_gt);
+    for (int i = threadIdx.x; i < n_gt; i += blockDim.x) skeys[i] = sel[i];
+    if (need > 0 && n_tie > 0) {
+      // the `need` ties with the largest keys = the lowest linear indices
+      unsigned long long kth = (need >= n_tie) ? 0ull : block_radix_kth(ties, n_tie, need, hist, &s_prefix, &s_remaining);
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_tie; i += blockDim.x) {
+        unsigned long long key = ties[i];
+        if (key >= kth) {
+          int slot = atomicAdd(&s_cnt, 1);
+          if (slot < need) skeys[n_gt + slot] = key;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  bitonic_sort_desc_smem(skeys, p2);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) emit_keypoint(skeys[i], keep_all ? 1 : 0, W, kpts + 2 * i, sc + i);
+}
+
 __global__ void bitonic_global_step(unsigned long long* a, int n_pow2, int k, int j) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pow2) return;
@@ -376,6 +521,32 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_select_topk(const u
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SEL_MAX_SMEM_KEYS * 8));
     attr_set = true;
+  }
+  if (k >= 1 && k <= SEL_MAX_SMEM_KEYS) {
+    // multi-CTA radix select; scratch: `spill` holds [TopkState | selected keys (k) | ties (rest)]
+    static bool attr2 = false;
+    if (!attr2) {
+      I4D_CUDA_CALL(cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_MAX_SMEM_KEYS * 8));
+      attr2 = true;
+    }
+    const size_t st_words = (sizeof(TopkState) + 7) / 8;
+    // spill layout (2 * cand_cap + 4096 keys, see the header): [TopkState (< 4096 words) | selected keys (k <= 16384 <= cand_cap) | ties (cand_cap)]
+    static_assert(sizeof(TopkState) <= 4096 * 8, "TopkState must fit the reserved head of the spill buffer");
+    I4D_CHECK_ARG(cand_cap >= SEL_MAX_SMEM_KEYS, "cand_cap must be at least 16384");
+    TopkState* tks = reinterpret_cast<TopkState*>(spill);
+    unsigned long long* sel = spill + 4096;
+    unsigned long long* ties = sel + cand_cap;
+    (void)st_words;
+    const int G = 2 * i4d_num_sms();
+    topk_init_kernel<<<1, 1024, 0, st>>>(cand_count, cand_cap, k, out_cap, tks, n_out);
+    for (int pass = 0; pass < 3; ++pass) {
+      topk_hist_kernel<<<G, 256, 0, st>>>(cand_keys, tks, pass);
+      topk_scan_kernel<<<1, 1024, 0, st>>>(tks, pass);
+    }
+    topk_compact_kernel<<<G, 256, 0, st>>>(cand_keys, tks, sel, ties);
+    topk_finish_kernel<<<1, SEL_THREADS, SEL_MAX_SMEM_KEYS * 8, st>>>(cand_keys, tks, W, sel, ties, kpts, scores);
+    I4D_CUDA_LAUNCH_CHECK();
+    return I4D_OK;
   }
   sp_topk_kernel<<<1, SEL_THREADS, SEL_MAX_SMEM_KEYS * 8, st>>>(cand_keys, cand_count, cand_cap, k, W, kpts, scores,
                                                                 out_cap, n_out, spill);

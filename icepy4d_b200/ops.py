@@ -45,7 +45,7 @@ class KeypointWorkspace:
         cap = int(cand_cap or max(65536, (H * W) // 4))
         self.cand_cap = 1 << (cap - 1).bit_length()   # power of two: the large-result sort pads to one
         self.keys = torch.empty(self.cand_cap, device=device, dtype=torch.int64)
-        self.spill = torch.empty(self.cand_cap, device=device, dtype=torch.int64)
+        self.spill = torch.empty(2 * self.cand_cap + 4096, device=device, dtype=torch.int64)
         self.count = torch.zeros(1, device=device, dtype=torch.int32)
 
 

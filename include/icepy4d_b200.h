@@ -41,7 +41,8 @@ int i4d_sp_nms_candidates(const float* scores, int H, int W, int nms_radius, flo
                           void* stream);
 /* superpoint.py:75-79,193-203 — keep the k best (k < 0: keep all), emit (x, y) as f32 and scores.  Order: score
  * descending (ties: lower linear index first) when k applies, row-major otherwise, like topk / nonzero.
- * kpts [out_cap,2], scores [out_cap], *n_out (device) = number written.  spill: scratch of cand_cap keys.
+ * kpts [out_cap,2], scores [out_cap], *n_out (device) = number written.  spill: scratch of 2*cand_cap + 4096 keys
+ * (cand_cap >= 16384).
  * Synchronises the stream only when k < 0 or k > 16384. */
 int i4d_sp_select_topk(const unsigned long long* cand_keys, const int* cand_count, int cand_cap, int k, int W,
                        float* kpts, float* scores, int out_cap, int* n_out, unsigned long long* spill, void* stream);

@@ -53,6 +53,11 @@ ms = timeit(lambda: ops.sp_score_map(logits)); res["sp_score_map"] = (ms, f"{(65
 scores = ops.sp_score_map(logits)
 kws = ops.KeypointWorkspace(scores.shape[0], scores.shape[1], scores.device)
 ms = timeit(lambda: ops.sp_keypoints(scores, 3, 1e-4, 4, 8192, kws)); res["sp nms+topk 1992^2"] = (ms, "")
+from icepy4d_b200 import _native as NN
+st = NN.current_stream()
+ms = timeit(lambda: NN.call("i4d_sp_nms_candidates", scores, scores.shape[0], scores.shape[1], 3, 1e-4, 4, kws.keys, kws.cand_cap, kws.count, None, st)); res["  nms only"] = (ms, "")
+_k = torch.empty((8192, 2), device="cuda"); _s = torch.empty(8192, device="cuda"); _n = torch.zeros(1, device="cuda", dtype=torch.int32)
+ms = timeit(lambda: NN.call("i4d_sp_select_topk", kws.keys, kws.count, kws.cand_cap, 8192, scores.shape[1], _k, _s, 8192, _n, kws.spill, st)); res["  topk only"] = (ms, "")
 kp, ks, n, _ = ops.sp_keypoints(scores, 3, 1e-4, 4, 8192, kws)
 print("candidates", int(kws.count.item()), "kept", int(n.item()))
 ms = timeit(lambda: ops.sp_sample_descriptors(desc, kp, n)); res["sp_sample_descriptors 8192"] = (ms, f"{8192*5*1024/ms/1e6:.0f} GB/s")
