@@ -107,19 +107,19 @@ def current_stream() -> int:
 
 # ---- kernel-launch accounting (the claim reported by bench.py as `gpu_launches`) ----------------------------
 LAUNCHES = 0
-_PER_CALL = {"i4d_sp_score_map": 1, "i4d_sp_nms_candidates": 1, "i4d_sp_select_topk": 1, "i4d_sp_sample_descriptors": 1,
+_PER_CALL = {"i4d_sp_score_map": 1, "i4d_sp_conv1a_relu": 1, "i4d_sp_nms_candidates": 1, "i4d_sp_select_topk": 9, "i4d_sp_sample_descriptors": 1,
              "i4d_gemm_f32": 1, "i4d_attention_f32": 1, "i4d_layernorm_gelu": 1, "i4d_lg_posenc": 1, "i4d_lg_rotary": 1,
-             "i4d_sg_kenc_input": 1, "i4d_row_lse": 1, "i4d_col_lse": 2, "i4d_lg_assign": 10, "i4d_undistort_points": 1,
+             "i4d_sg_kenc_input": 1, "i4d_set_sinkhorn_mode": 0, "i4d_row_lse": 1, "i4d_col_lse": 2, "i4d_lg_assign": 10, "i4d_undistort_points": 1,
              "i4d_triangulate_iterative_ls": 1, "i4d_triangulate_dlt": 1, "i4d_tile_to_gray_f32": 1}
 
 
 def _count(name: str, args) -> int:
     if name in _PER_CALL:
         return _PER_CALL[name]
-    if name == "i4d_sinkhorn":
-        return 5 * int(args[4])
-    if name == "i4d_sg_assign":
-        return 5 * int(args[4]) + 5
+    if name in ("i4d_sinkhorn", "i4d_sg_assign"):
+        m, n, iters = int(args[1]), int(args[2]), int(args[4])
+        fused = n % 4 == 0 and 64 <= n <= 8192          # one persistent cooperative launch for all iterations
+        return (1 if fused else 5 * iters) + (5 if name == "i4d_sg_assign" else 0)
     if name == "i4d_fundamental_ransac":
         rounds = min(24, -(-int(args[5]) // 4096))
         return 1 + 5 * rounds + 1 + 2 * int(args[8]) + 1

@@ -373,57 +373,65 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
   }
 }
 
-// smallest eigenvector of the 9x9 moment matrix (cyclic Jacobi, f64), rank-2 projection, denormalisation
-__global__ void rs_polish_solve_kernel(RansacState* st) {
-  if (threadIdx.x != 0) return;
-  double C[9][9], V[9][9];
-  int t = 0;
-  double tr = 0;
-  for (int p = 0; p < 9; ++p)
-    for (int q = p; q < 9; ++q) { C[p][q] = C[q][p] = st->cov[t++]; }
-  for (int i = 0; i < 45; ++i) st->cov[i] = 0.0;
-  for (int p = 0; p < 9; ++p) tr += C[p][p];
-  if (!(tr > 0)) {  // no support: keep the previous model
-    return;
+// smallest eigenvector of the 9x9 moment matrix (cyclic Jacobi, f64), rank-2 projection, denormalisation.
+// One warp: the matrices live in shared memory, lane k owns row/column k of every plane rotation.
+__global__ void __launch_bounds__(32) rs_polish_solve_kernel(RansacState* st) {
+  __shared__ double C[9][9], V[9][9];
+  __shared__ double Fn_s[9];
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    int t = 0;
+    for (int p = 0; p < 9; ++p)
+      for (int q = p; q < 9; ++q) { C[p][q] = C[q][p] = st->cov[t++]; }
+    for (int i = 0; i < 45; ++i) st->cov[i] = 0.0;
   }
-  for (int p = 0; p < 9; ++p)
-    for (int q = 0; q < 9; ++q) V[p][q] = (p == q) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  if (lane < 9)
+    for (int q = 0; q < 9; ++q) V[lane][q] = (lane == q) ? 1.0 : 0.0;
+  __syncwarp();
+  double tr = 0;
+  for (int p = 0; p < 9; ++p) tr += C[p][p];
+  if (!(tr > 0)) return;              // no support: keep the previous model (uniform across the warp)
+  for (int sweep = 0; sweep < 24; ++sweep) {
     double off = 0;
     for (int p = 0; p < 8; ++p)
       for (int q = p + 1; q < 9; ++q) off += C[p][q] * C[p][q];
-    if (off < 1e-30 * tr * tr) break;
+    if (off < 1e-26 * tr * tr) break;   // off-diagonal mass relative to the trace: eigenvector good to ~1e-13
     for (int p = 0; p < 8; ++p)
       for (int q = p + 1; q < 9; ++q) {
-        if (C[p][q] == 0.0) continue;
-        double theta = (C[q][q] - C[p][p]) / (2.0 * C[p][q]);
-        double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-        for (int k = 0; k < 9; ++k) {
-          double ckp = C[k][p], ckq = C[k][q];
-          C[k][p] = c * ckp - s * ckq; C[k][q] = s * ckp + c * ckq;
+        const double cpq = C[p][q];
+        if (cpq == 0.0) continue;       // uniform
+        const double theta = (C[q][q] - C[p][p]) / (2.0 * cpq);
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+        __syncwarp();
+        if (lane < 9) {                 // columns p, q of row `lane`
+          const double ckp = C[lane][p], ckq = C[lane][q];
+          C[lane][p] = c * ckp - s * ckq; C[lane][q] = s * ckp + c * ckq;
+          const double vkp = V[lane][p], vkq = V[lane][q];
+          V[lane][p] = c * vkp - s * vkq; V[lane][q] = s * vkp + c * vkq;
         }
-        for (int k = 0; k < 9; ++k) {
-          double cpk = C[p][k], cqk = C[q][k];
-          C[p][k] = c * cpk - s * cqk; C[q][k] = s * cpk + c * cqk;
+        __syncwarp();
+        if (lane < 9) {                 // rows p, q of column `lane`
+          const double cpk = C[p][lane], cqk = C[q][lane];
+          C[p][lane] = c * cpk - s * cqk; C[q][lane] = s * cpk + c * cqk;
         }
-        for (int k = 0; k < 9; ++k) {
-          double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
-        }
+        __syncwarp();
       }
   }
-  int jm = 0;
-  for (int j = 1; j < 9; ++j)
-    if (C[j][j] < C[jm][jm]) jm = j;
-  double Fn[9];
-  for (int i = 0; i < 9; ++i) Fn[i] = V[i][jm];
-  rs_rank2(Fn);
-  double F[9];
-  rs_denormalise(Fn, st->T0, st->T1, F);
-  bool ok = true;
-  for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
-  if (ok) for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
+  if (lane == 0) {
+    int jm = 0;
+    for (int j = 1; j < 9; ++j)
+      if (C[j][j] < C[jm][jm]) jm = j;
+    for (int i = 0; i < 9; ++i) Fn_s[i] = V[i][jm];
+    double Fn[9];
+    for (int i = 0; i < 9; ++i) Fn[i] = Fn_s[i];
+    rs_rank2(Fn);
+    double F[9];
+    rs_denormalise(Fn, st->T0, st->T1, F);
+    bool ok = true;
+    for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
+    if (ok) for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
+  }
 }
 
 __global__ void rs_copy_best_kernel(RansacState* st) {

@@ -53,6 +53,8 @@ class SuperPointB200:
             w = state_dict[f"{name}.weight"].to(self.device, dtype=wdt).contiguous(memory_format=torch.channels_last)
             b = state_dict[f"{name}.bias"].to(self.device, dtype=wdt)
             self.w[name] = (w, b)
+        self.w1a = (state_dict["conv1a.weight"].to(self.device, torch.float32).contiguous(),
+                    state_dict["conv1a.bias"].to(self.device, torch.float32).contiguous())
         self._kws = {}
 
     # -- backbone (cuDNN through torch; channels-last so the heads come out HWC for the gather kernel) --
@@ -69,8 +71,13 @@ class SuperPointB200:
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = self.conv_precision != "f32"
         try:
-            x = image.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
-            x = self._conv(self._conv(x, "conv1a", 1), "conv1b", 1)
+            if self.conv_precision == "f32":
+                x = image.contiguous(memory_format=torch.channels_last)
+                x = self._conv(x, "conv1a", 1)
+            else:
+                # hand-written first layer: exact f32 FMAs, written straight in channels-last (no 1 GB transpose)
+                x = ops.sp_conv1a_relu(image, self.w1a[0], self.w1a[1], self.act_dtype)
+            x = self._conv(x, "conv1b", 1)
             x = F.max_pool2d(x, 2, 2)
             x = self._conv(self._conv(x, "conv2a", 1), "conv2b", 1)
             x = F.max_pool2d(x, 2, 2)

@@ -37,6 +37,16 @@ def sp_score_map(logits: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def sp_conv1a_relu(image: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+    """image [1,1,H,W] f32 -> relu(conv1a) as a channels-last [1,64,H,W] tensor of `out_dtype`."""
+    _chk(image, name="image")
+    H, W = image.shape[-2:]
+    out = torch.empty((1, H, W, 64), device=image.device, dtype=out_dtype)
+    code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[out_dtype]
+    N.call("i4d_sp_conv1a_relu", image, H, W, _chk(weight.reshape(64, 9), name="weight"), _chk(bias, name="bias"), out, code, _st())
+    return out.permute(0, 3, 1, 2)          # logical NCHW view of channels-last memory (no copy)
+
+
 class KeypointWorkspace:
     """Reusable device buffers for candidate compaction + top-k of one score map size."""
 

@@ -28,6 +28,12 @@ const char* i4d_last_error(void);
 /* SM count of the current device (0 if no device) — grids are sized from it. */
 int i4d_device_sm_count(void);
 
+/* ---- SuperPoint first layer ---------------------------------------------------------------------------- */
+/* superpoint.py:154 — relu(conv1a(image)): 1 -> 64 channels, 3x3, pad 1.  image [H,W] f32, weight [64,9] (= [64,1,3,3]),
+ * bias [64]; out [H,W,64] channels-last, out_dtype 0 = f32, 1 = f16, 2 = bf16. */
+int i4d_sp_conv1a_relu(const float* image, int H, int W, const float* weight, const float* bias, void* out_nhwc,
+                       int out_dtype, void* stream);
+
 /* ---- SuperPoint post-processing ----------------------------------------------------------------------- */
 /* thirdparty/SuperGlue/models/superpoint.py:169-172 — softmax over 65 channels, drop dustbin, 8x8 pixel shuffle.
  * logits [65,h,w] f32 -> scores [8h,8w] f32. */
