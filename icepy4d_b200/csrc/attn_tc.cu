@@ -61,6 +61,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -210,13 +225,16 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
         tc::mbar_wait(&pv_done, (j - 1) & 1);                               // P buffer free, O quiescent
         if (__any_sync(0xffffffffu, need)) {
           tc::tcgen05_fence_after();
-          uint32_t ov[32];
-          tc::tmem_ld32(tmem_O + lane_off + hf * 32, ov);
-          tc::tmem_ld_wait();
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {                                  // two 16-column halves: keeps the register peak low
+            uint32_t ov[16];
+            tmem_ld16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st32(tmem_O + lane_off + hf * 32, ov);
-          tmem_st_wait();
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
+            tmem_st_wait();
+          }
           l_part *= alpha;
         }
       }
