@@ -66,6 +66,11 @@ class SuperPointB200:
         y = F.conv2d(x, w, b, padding=pad)
         return F.relu_(y) if relu else y
 
+    def _pool(self, x):
+        if self.conv_precision != "f32" and x.is_contiguous(memory_format=torch.channels_last):
+            return ops.maxpool2x2_cl(x)           # hand-written: one 16-byte load per input pixel-channel-quad
+        return F.max_pool2d(x, 2, 2)
+
     def backbone(self, image: torch.Tensor):
         """image [1,1,H,W] f32 -> (logits [65,h,w] f32 contiguous, desc [h,w,256] f32 contiguous)."""
         prev = torch.backends.cudnn.allow_tf32
@@ -78,11 +83,11 @@ class SuperPointB200:
                 # hand-written first layer: exact f32 FMAs, written straight in channels-last (no 1 GB transpose)
                 x = ops.sp_conv1a_relu(image, self.w1a[0], self.w1a[1], self.act_dtype)
             x = self._conv(x, "conv1b", 1)
-            x = F.max_pool2d(x, 2, 2)
+            x = self._pool(x)
             x = self._conv(self._conv(x, "conv2a", 1), "conv2b", 1)
-            x = F.max_pool2d(x, 2, 2)
+            x = self._pool(x)
             x = self._conv(self._conv(x, "conv3a", 1), "conv3b", 1)
-            x = F.max_pool2d(x, 2, 2)
+            x = self._pool(x)
             x = self._conv(self._conv(x, "conv4a", 1), "conv4b", 1)
             logits = self._conv(self._conv(x, "convPa", 1).float(), "convPb", 0, relu=False)
             desc = self._conv(self._conv(x, "convDa", 1).float(), "convDb", 0, relu=False)

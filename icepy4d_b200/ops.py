@@ -47,6 +47,15 @@ def sp_conv1a_relu(image: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     return out.permute(0, 3, 1, 2)          # logical NCHW view of channels-last memory (no copy)
 
 
+def maxpool2x2_cl(x: torch.Tensor) -> torch.Tensor:
+    """x: [1,C,H,W] channels-last (post-ReLU) -> [1,C,H//2,W//2] channels-last."""
+    assert x.is_cuda and x.dim() == 4 and x.shape[0] == 1 and x.is_contiguous(memory_format=torch.channels_last)
+    _, C, H, W = x.shape
+    out = torch.empty((1, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
+    N.call("i4d_maxpool2x2_nhwc", x, H, W, C, out, x.element_size(), 1, _st())
+    return out.permute(0, 3, 1, 2)
+
+
 class KeypointWorkspace:
     """Reusable device buffers for candidate compaction + top-k of one score map size."""
 

@@ -34,6 +34,10 @@ int i4d_device_sm_count(void);
 int i4d_sp_conv1a_relu(const float* image, int H, int W, const float* weight, const float* bias, void* out_nhwc,
                        int out_dtype, void* stream);
 
+/* superpoint.py:156,159,162 — MaxPool2d(2,2) on a channels-last activation [H,W,C] -> [H/2,W/2,C].  elem_bytes 4 (f32) or
+ * 2 (f16/bf16, requires nonneg = 1: post-ReLU data, compared as bit patterns). */
+int i4d_maxpool2x2_nhwc(const void* in, int H, int W, int C, void* out, int elem_bytes, int nonneg, void* stream);
+
 /* ---- SuperPoint post-processing ----------------------------------------------------------------------- */
 /* thirdparty/SuperGlue/models/superpoint.py:169-172 — softmax over 65 channels, drop dustbin, 8x8 pixel shuffle.
  * logits [65,h,w] f32 -> scores [8h,8w] f32. */

@@ -250,3 +250,25 @@ def test_superglue_f32_matches_reference(golden_dir):
     assert np.array_equal(m0.cpu().numpy(), g["matches0"])        # identical match set vs the reference
     assert np.array_equal(m1.cpu().numpy(), g["matches1"])
     assert np.allclose(s0.cpu().numpy(), g["mscores0"], atol=1e-3)
+
+
+# ------------------------------------------------------------------ SuperPoint first layer / pooling
+@pytest.mark.parametrize("H,W", [(37, 53), (240, 320), (129, 64)])
+def test_conv1a_relu_and_maxpool(ops, H, W):
+    sd = weights.make_superpoint_state(1)
+    gen = torch.Generator().manual_seed(H + W)
+    img = torch.rand(1, 1, H, W, generator=gen)
+    ref = torch.relu(torch.nn.functional.conv2d(img, sd["conv1a.weight"], sd["conv1a.bias"] + 0.01, padding=1))
+    w, b = sd["conv1a.weight"].cuda().contiguous(), (sd["conv1a.bias"] + 0.01).cuda()
+    out = ops.sp_conv1a_relu(img.cuda(), w, b, torch.float32)
+    assert out.shape == (1, 64, H, W) and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(out.cpu(), ref, atol=2e-6)                          # 9 f32 FMAs per output
+    o16 = ops.sp_conv1a_relu(img.cuda(), w, b, torch.float16)
+    assert torch.allclose(o16.float().cpu(), ref, atol=2e-3)
+    # pooling is exact (pure comparisons), f32 and 16-bit, odd sizes floor like torch
+    p = ops.maxpool2x2_cl(out)
+    assert torch.equal(p.cpu(), torch.nn.functional.max_pool2d(out.cpu(), 2, 2))
+    p16 = ops.maxpool2x2_cl(o16)
+    assert torch.equal(p16.cpu(), torch.nn.functional.max_pool2d(o16.cpu().float(), 2, 2).half())
+    ob = ops.sp_conv1a_relu(img.cuda(), w, b, torch.bfloat16)
+    assert torch.equal(ops.maxpool2x2_cl(ob).cpu(), torch.nn.functional.max_pool2d(ob.cpu().float(), 2, 2).bfloat16())
