@@ -420,8 +420,8 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
 namespace cg = cooperative_groups;
 
 #define SK_THREADS 1024
-#define SK_ROWS 2                 // rows per stage
-#define SK_STAGES 3
+#define SK_ROWS 3                 // rows per stage
+#define SK_STAGES 2
 #define SK_MAXN 8192
 #define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
 #define SK_EXACT_ITERS 2
@@ -515,12 +515,16 @@ __device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consu
   for (int k = 0; k < SK_ROWS; ++k) {
     if (FULL || k < nr) {
       if (FAST) {
+        // e_ij = 2^(x_ij + v_j - m_i) is kept in registers: the column pass needs no second exponential, because
+        // 2^(x_ij + u_i - m_j) = e_ij * 2^(u_i + m_i - c_mu)   (m_j = c_mu - v_j): a rank-1 rescaling of the same kernel matrix.
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int g = 0; g < SK_GROUPS; ++g) {
           if (FULL || g * SK_THREADS + tid < n4) {
-            s0 += sk_ex2(x[k][g][0] + (vl[g][0] - mrow[k])) + sk_ex2(x[k][g][1] + (vl[g][1] - mrow[k]));
-            s1 += sk_ex2(x[k][g][2] + (vl[g][2] - mrow[k])) + sk_ex2(x[k][g][3] + (vl[g][3] - mrow[k]));
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) x[k][g][cc] = sk_ex2(x[k][g][cc] + (vl[g][cc] - mrow[k]));
+            s0 += x[k][g][0] + x[k][g][1];
+            s1 += x[k][g][2] + x[k][g][3];
           }
         }
         float sm = warp_sum(s0 + s1);
@@ -570,12 +574,13 @@ __device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consu
       }
       if (tid == 0) c.u[r_base + k] = ui;
       const float ul = ui * LOG2E;
+      const float ak = FAST ? sk_ex2(ul + mrow[k] - c.c_mu) : 0.f;     // row factor of the rank-1 rescaling (fast mode)
 #pragma unroll
       for (int g = 0; g < SK_GROUPS; ++g) {
         if (FULL || g * SK_THREADS + tid < n4) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            if (FAST) col[g][cc].s += sk_ex2(x[k][g][cc] + (ul - col[g][cc].m));
+            if (FAST) col[g][cc].s = fmaf(x[k][g][cc], ak, col[g][cc].s);
             else col[g][cc].add(x[k][g][cc] + ul);
           }
         }
@@ -691,33 +696,33 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
     {
       const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
-      // one warp per 8-column tile: lane = 8 * sub + col; each lane reduces the partials of CTAs c = sub, sub + 4, ...
-      // (32-byte coalesced loads), then a 2-step shuffle over `sub`.  No shared memory, no block barrier.
-      const int sub = lane >> 3, cl = lane & 7;
-      for (int tile = cta * (SK_THREADS / 32) + warp; tile * 8 < N; tile += G * (SK_THREADS / 32)) {
-        const int j = tile * 8 + cl;
+      // one warp per 2-column tile: lane = 2 * sub + col; each lane reduces the partials of CTAs c = sub, sub + 16, ...,
+      // then a 4-step shuffle over `sub`.  No shared memory, no block barrier, ~all warps of the grid busy.
+      const int sub = lane >> 1, cl = lane & 1;
+      for (int tile = cta * (SK_THREADS / 32) + warp; tile * 2 < N; tile += G * (SK_THREADS / 32)) {
+        const int j = tile * 2 + cl;
         if (fast) {
           float sm = 0.f;
           if (j < N) {
 #pragma unroll 4
-            for (int c = sub; c < G; c += 4) sm += __ldcg(ps + (size_t)c * N + j);
+            for (int c = sub; c < G; c += 16) sm += __ldcg(ps + (size_t)c * N + j);
           }
-          sm += __shfl_xor_sync(0xffffffffu, sm, 8);
-          sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+#pragma unroll
+          for (int o = 2; o < 32; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
           if (sub == 0 && j < N) {
             const float mj = c_mu - __ldcg(v + j) * LOG2E;            // the stabiliser used above (old v)
             sm += sk_ex2(extra_col - mj);
             if (!(sm > 0.f && sm < INFINITY)) atomicExch(flag, 1);
-            v[j] = norm - (mj + log2f(sm)) * LN2;
+            v[j] = norm - (mj + __log2f(sm)) * LN2;
           }
         } else {
           L2Acc a; a.init();
           if (j < N) {
 #pragma unroll 2
-            for (int c = sub; c < G; c += 4) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
+            for (int c = sub; c < G; c += 16) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
           }
-          a.merge(__shfl_xor_sync(0xffffffffu, a.m, 8), __shfl_xor_sync(0xffffffffu, a.s, 8));
-          a.merge(__shfl_xor_sync(0xffffffffu, a.m, 16), __shfl_xor_sync(0xffffffffu, a.s, 16));
+#pragma unroll
+          for (int o = 2; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
           if (sub == 0 && j < N) {
             a.add(extra_col);
             v[j] = norm - a.lse_ln();

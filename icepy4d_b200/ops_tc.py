@@ -58,8 +58,16 @@ class SuperGlueTensorCore:
     def __init__(self, w, device):
         self.dev = torch.device(device)
         h = lambda t: t.to(BF16).contiguous()
-        self.layers = [{"wqkv": h(L["wqkv"]), "bqkv": L["bqkv"], "wm": h(L["wm"]), "bm": L["bm"], "w1": h(L["w1"]), "b1": L["b1"],
-                        "w2": h(L["w2"]), "b2": L["b2"]} for L in w.layers]
+        # `merge` (superglue.py:107,115) is linear and feeds only the first MLP layer: fold it into that layer's weights,
+        #   W1 [x | merge(a)] + b1 = [W1x | W1m Wm] [x | a] + (b1 + W1m bm),   so the attention output goes straight into the
+        # [x | message] buffer and one GEMM per layer disappears.
+        self.layers = []
+        for L in w.layers:
+            w1x, w1m = L["w1"][:, :256], L["w1"][:, 256:]
+            w1f = torch.cat([w1x, w1m @ L["wm"]], 1)
+            b1f = L["b1"] + w1m @ L["bm"]
+            self.layers.append({"wqkv": h(L["wqkv"]), "bqkv": L["bqkv"], "w1": h(w1f), "b1": b1f.contiguous(),
+                                "w2": h(L["w2"]), "b2": L["b2"]})
         self.wf, self.bf = h(w.wf), w.bf
         self._buf = {}
 
@@ -83,8 +91,7 @@ class SuperGlueTensorCore:
         cross_p = [(0, n0, n0, n1), (n0, n1, 0, n0)]
         for l, L in enumerate(self.layers):
             gemm_tc(xm[:, :256], L["wqkv"], L["bqkv"], out16=qkv)
-            attention_tc(qkv, cross_p if l % 2 == 1 else self_p, att, 0, 256, 512)
-            gemm_tc(att, L["wm"], L["bm"], out16=xm[:, 256:])
+            attention_tc(qkv, cross_p if l % 2 == 1 else self_p, xm[:, 256:], 0, 256, 512)
             gemm_tc(xm, L["w1"], L["b1"], out16=hid, relu=True)
             gemm_tc(hid, L["w2"], L["b2"], residual=x32, out32=x32, out16=xm[:, :256])
             if collect is not None:
