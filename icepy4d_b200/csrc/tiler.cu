@@ -42,3 +42,72 @@ extern "C" __attribute__((visibility("default"))) int i4d_tile_to_gray_f32(const
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gaussian pyramid on u8 images, bit-exact with OpenCV's 8-bit cv2.pyrDown / cv2.pyrUp (used by the reference for
+// Quality.{LOW,MEDIUM,HIGHEST} and for the PRESELECTION low-resolution pass: matching/matchers.py:583-610, 516-531).
+//   pyrDown: 5x5 kernel [1 4 6 4 1] (x) [1 4 6 4 1], integer, (sum + 128) >> 8, BORDER_REFLECT_101, out = ((W+1)/2, (H+1)/2)
+//   pyrUp  : even samples p[i-1] + 6 p[i] + p[i+1], odd samples 4 p[i] + 4 p[i+1] per axis, (sum + 32) >> 6;
+//            reflect-101 at the low border, replicate at the high border (OpenCV's rule), out = (2W, 2H)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int refl101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i < 0 ? 0 : i;
+}
+
+__global__ void __launch_bounds__(256) pyr_down_kernel(const unsigned char* __restrict__ in, int H, int W, int C,
+                                                       unsigned char* __restrict__ out, int Ho, int Wo) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)Ho * Wo * C) return;
+  const int c = (int)(gid % C);
+  const long long p = gid / C;
+  const int xo = (int)(p % Wo), yo = (int)(p / Wo);
+  const int wgt[5] = {1, 4, 6, 4, 1};
+  int acc = 0;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    const int yy = refl101(2 * yo + dy - 2, H);
+    int row = 0;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) row += wgt[dx] * (int)__ldg(in + ((size_t)yy * W + refl101(2 * xo + dx - 2, W)) * C + c);
+    acc += wgt[dy] * row;
+  }
+  out[gid] = (unsigned char)((acc + 128) >> 8);
+}
+
+__global__ void __launch_bounds__(256) pyr_up_kernel(const unsigned char* __restrict__ in, int H, int W, int C,
+                                                     unsigned char* __restrict__ out) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)Ho * Wo * C) return;
+  const int c = (int)(gid % C);
+  const long long p = gid / C;
+  const int xo = (int)(p % Wo), yo = (int)(p / Wo);
+  const int i = yo >> 1, j = xo >> 1;
+  const int il = i > 0 ? i - 1 : (H > 1 ? 1 : 0), ir = i + 1 < H ? i + 1 : i;      // reflect-101 low, replicate high
+  const int jl = j > 0 ? j - 1 : (W > 1 ? 1 : 0), jr = j + 1 < W ? j + 1 : j;
+  auto px = [&](int y, int x) { return (int)__ldg(in + ((size_t)y * W + x) * C + c); };
+  auto hrow = [&](int y) { return (xo & 1) ? 4 * px(y, j) + 4 * px(y, jr) : px(y, jl) + 6 * px(y, j) + px(y, jr); };
+  const int acc = (yo & 1) ? 4 * hrow(i) + 4 * hrow(ir) : hrow(il) + 6 * hrow(i) + hrow(ir);
+  out[gid] = (unsigned char)((acc + 32) >> 6);
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_pyr_down_u8(const unsigned char* in, int H, int W, int C,
+                                                                     unsigned char* out, void* stream) {
+  I4D_CHECK_ARG(in && out && H > 0 && W > 0 && (C == 1 || C == 3), "bad arguments");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long n = (long long)Ho * Wo * C;
+  pyr_down_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, H, W, C, out, Ho, Wo);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_pyr_up_u8(const unsigned char* in, int H, int W, int C,
+                                                                   unsigned char* out, void* stream) {
+  I4D_CHECK_ARG(in && out && H > 0 && W > 0 && (C == 1 || C == 3), "bad arguments");
+  const long long n = (long long)4 * H * W * C;
+  pyr_up_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, H, W, C, out);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}

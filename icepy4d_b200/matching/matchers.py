@@ -171,8 +171,7 @@ class ImageMatcherBase(ImageMatcherABC):
         if self._do_viz:
             logger.warning("visualisation is outside the B200 hot path; do_viz_matches is ignored")
 
-        image0_, image1_ = self._resize_images(quality, image0, image1)
-        dev0, dev1 = self._upload(image0_), self._upload(image1_)
+        dev0, dev1 = self._resize_images_device(quality, self._upload(image0), self._upload(image1))
         mk0, mk1, s0, s1, conf, d0, d1, F = self.match_device(dev0, dev1, quality, tile_selection, **config)
         self._F = F.cpu().numpy().reshape(3, 3) if F is not None else None
         self._store_device_results(mk0, mk1, s0, s1, conf, d0, d1)
@@ -244,8 +243,18 @@ class ImageMatcherBase(ImageMatcherABC):
         t = torch.from_numpy(np.ascontiguousarray(image))
         return t.cuda(non_blocking=True)
 
+    def _resize_images_device(self, quality: Quality, dev0: torch.Tensor, dev1: torch.Tensor):
+        """matchers.py:583-610 on the device: bit-exact cv2.pyrUp / pyrDown kernels on the uploaded u8 images."""
+        if quality == Quality.HIGHEST:
+            return ops.pyr_up(dev0), ops.pyr_up(dev1)
+        if quality == Quality.MEDIUM:
+            return ops.pyr_down(dev0), ops.pyr_down(dev1)
+        if quality == Quality.LOW:
+            return ops.pyr_down(ops.pyr_down(dev0)), ops.pyr_down(ops.pyr_down(dev1))
+        return dev0, dev1
+
     def _resize_images(self, quality: Quality, image0: np.ndarray, image1: np.ndarray):
-        # matchers.py:583-610.  The Gaussian pyramid (cv2.pyrDown/pyrUp) stays on the host for now.
+        # host variant kept for API compatibility (matchers.py:583-610); match() uses the device kernels above.
         if quality == Quality.HIGHEST:
             return cv2.pyrUp(image0), cv2.pyrUp(image1)
         if quality == Quality.MEDIUM:
@@ -354,10 +363,11 @@ class ImageMatcherBase(ImageMatcherABC):
         if method == TileSelection.PRESELECTION:
             h = dev0.shape[0]
             n_down = 3 if h > 4000 else (2 if h > 2000 else 1)     # matchers.py:516-523 (the >8000 branch is dead code there)
-            i0, i1 = dev0.cpu().numpy(), dev1.cpu().numpy()
+            i0, i1 = dev0, dev1
             for _ in range(n_down):
-                i0, i1 = cv2.pyrDown(i0), cv2.pyrDown(i1)
-            f0, f1, mtc, _ = self._match_images(i0, i1, max_keypoints=4096)
+                i0, i1 = ops.pyr_down(i0), ops.pyr_down(i1)           # on the device, bit-exact with cv2.pyrDown
+            r = self._match_tensors(i0, i1, (0, 0, i0.shape[1], i0.shape[0]), (0, 0, i1.shape[1], i1.shape[0]), max_keypoints=4096)
+            f0, f1, mtc, _ = self._pair_to_numpy(r)
             vld = mtc > -1
             kp0 = f0.keypoints[vld] * float(2 ** n_down)
             kp1 = f1.keypoints[mtc[vld]] * float(2 ** n_down)

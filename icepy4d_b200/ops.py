@@ -295,3 +295,25 @@ def tile_to_gray_f32(image_u8: torch.Tensor, x0: int, y0: int, tw: int, th: int,
     out = torch.empty((1, 1, th, tw), device=image_u8.device, dtype=torch.float32)
     N.call("i4d_tile_to_gray_f32", image_u8, H, W, C, int(x0), int(y0), int(tw), int(th), int(mode), out, _st())
     return out
+
+
+def pyr_down(image_u8: torch.Tensor) -> torch.Tensor:
+    """cv2.pyrDown on a device u8 image [H,W] or [H,W,3] (bit-exact)."""
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()
+    H, W = image_u8.shape[:2]
+    C = 1 if image_u8.dim() == 2 else image_u8.shape[2]
+    shape = ((H + 1) // 2, (W + 1) // 2) + (() if image_u8.dim() == 2 else (C,))
+    out = torch.empty(shape, device=image_u8.device, dtype=torch.uint8)
+    N.call("i4d_pyr_down_u8", image_u8, H, W, C, out, _st())
+    return out
+
+
+def pyr_up(image_u8: torch.Tensor) -> torch.Tensor:
+    """cv2.pyrUp on a device u8 image [H,W] or [H,W,3] (bit-exact)."""
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()
+    H, W = image_u8.shape[:2]
+    C = 1 if image_u8.dim() == 2 else image_u8.shape[2]
+    shape = (2 * H, 2 * W) + (() if image_u8.dim() == 2 else (C,))
+    out = torch.empty(shape, device=image_u8.device, dtype=torch.uint8)
+    N.call("i4d_pyr_up_u8", image_u8, H, W, C, out, _st())
+    return out

@@ -155,6 +155,12 @@ int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double thres
 int i4d_tile_to_gray_f32(const unsigned char* image, int H, int W, int C, int x0, int y0, int tw, int th, int mode,
                          float* out, void* stream);
 
+/* matching/matchers.py:583-610 (Quality resize) and :526-531 (PRESELECTION pass) — cv2.pyrDown / cv2.pyrUp on 8-bit images,
+ * bit-exact with OpenCV's integer arithmetic and border rules.  image [H,W,C] u8 (C = 1 or 3).
+ * pyr_down: out [(H+1)/2, (W+1)/2, C];  pyr_up: out [2H, 2W, C]. */
+int i4d_pyr_down_u8(const unsigned char* in, int H, int W, int C, unsigned char* out, void* stream);
+int i4d_pyr_up_u8(const unsigned char* in, int H, int W, int C, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
