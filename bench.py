@@ -176,6 +176,7 @@ def _dominant_kernel_roofline(precision: str, peaks):
             "kernel": "sinkhorn_fused_kernel (100 iterations, 8192x8192 f32, one launch)", "ms_per_launch": ms_launch,
             "us_per_iteration": ms_launch * 1e3 / iters, "peak_source": peaks["source"],
             "algorithmic_bytes_per_launch": bytes_launch,
+            "frac_of_actual_traffic": (float(M) * N * 4 * iters / (ms_launch * 1e-3) / 1e9) / peaks["hbm_gbs"],
             "note": "traffic = one HBM read of the matrix per iteration (ncu dram__bytes_read 269 MB/iter, profiles/) + column partials"}
 
 
