@@ -1,0 +1,298 @@
+// SuperPoint backbone convolutions (3x3 pad 1, and the 1x1 heads) as implicit GEMMs on tcgen05 with SPLIT bf16
+// operands ("bf16x3"): every f32 value v is carried as hi = bf16(v), lo = bf16(v - hi), and
+//     x * w  ~=  x_hi*w_hi + x_hi*w_lo + x_lo*w_hi        (relative error ~2^-16, f32 accumulation in TMEM)
+// A plain TF32/bf16 convolution flips enough near-tie keypoints to drop the end-to-end match IoU against the f32
+// reference to 0.94-0.98; the split form measures 0.996-0.999 (scripts/split_precision_iou.py) at bf16 tensor-core rate.
+//
+// Layout.  Activations are channels-last bf16 planes [H][W][C] (one hi plane, one lo plane).  A CTA works on a region of
+// (8*T) x 16 output pixels.  For each 64-channel chunk one TMA box load per plane brings the region plus its 1-pixel halo
+// into shared memory as (8T+2)*18 rows of 128 bytes (128B swizzle); out-of-image coordinates are zero-filled by TMA,
+// which IS the convolution's zero padding.  The nine taps are then nine *views* of that one buffer: the UMMA descriptor's
+// start address is shifted by (dy*(8T+2) + dx) rows and its stride-byte-offset is one halo row, so operand row m maps to
+// pixel (m%8, m/8) of the tile (the swizzle XOR is a function of the absolute shared-memory address, so row-shifted
+// starts are legal: scripts/umma_shift_probe.cu).  Weights are packed per (tap, chunk) as [w_hi rows | w_lo rows] x 64
+// so that  x_hi * [w_hi | w_lo]  is ONE N = 2*N_T MMA; x_lo * w_hi is a second N = N_T MMA into the first half of the
+// same accumulator; the epilogue adds the two halves.
+//
+// Roles (256 threads, one persistent CTA per SM): warp 0 lane 0 = activation TMA producer, warp 1 lane 0 = weight TMA
+// producer, warp 2 lane 0 = MMA issuer, warps 4-7 = epilogue (tcgen05.ld -> +bias, ReLU, optional fused 2x2 max-pool via
+// warp shuffles -> split back to hi/lo bf16 or f32).  Accumulators are double-buffered in TMEM (all 512 columns), so the
+// epilogue of one region overlaps the MMAs of the next.
+//
+// Reference behaviour replaced: conv1b..convDb of thirdparty/SuperGlue/models/superpoint.py:154-168,193-196 (and the
+// LightGlue copy, lightglue/superpoint.py:155-170,189-192), which run as f32 cuDNN/MKL convolutions there.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/icepy4d_b200.h"
+
+#define CV_THREADS 256
+#define CV_TILE_H 16
+#define CV_A_SLOTS 2
+#define CV_B_STAGES 3
+
+struct ConvTcParams {
+  int H, W, KC, taps, NT, tiles_x, tiles_y, halo, relu, pool;
+  const float* bias;
+  __nv_bfloat16* y_hi; __nv_bfloat16* y_lo; int ld16;
+  float* y32; int ld32; int planar;
+  int cout;
+};
+
+template <int N_T, int T> struct ConvCfg {
+  static constexpr int ACC_COLS = 2 * N_T;                       // [x_hi*w_hi + x_lo*w_hi | x_hi*w_lo]
+  static constexpr int TMEM_COLS = 2 * T * ACC_COLS;             // double-buffered
+  static constexpr int BW_MAX = 8 * T + 2, BH_MAX = CV_TILE_H + 2;
+  static constexpr int A_PLANE = ((BW_MAX * BH_MAX * 128) + 1023) & ~1023;
+  static constexpr int A_SLOT = 2 * A_PLANE;
+  static constexpr int B_STAGE = 2 * N_T * 128;
+  static constexpr int SMEM = CV_A_SLOTS * A_SLOT + CV_B_STAGES * B_STAGE + 1024;
+  static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "TMEM allocation must be a power of two");
+  static_assert(SMEM <= 232448 - 512, "shared memory budget");
+};
+
+template <int N_T, int T>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi,
+                                                                 const __grid_constant__ CUtensorMap tmLo,
+                                                                 const __grid_constant__ CUtensorMap tmW, ConvTcParams p) {
+  using C = ConvCfg<N_T, T>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + CV_A_SLOTS * C::A_SLOT;
+  __shared__ __align__(8) uint64_t a_full[CV_A_SLOTS], a_empty[CV_A_SLOTS], b_full[CV_B_STAGES], b_empty[CV_B_STAGES],
+      t_full[2], t_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[512];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bw = 8 * T + 2 * p.halo, bh = CV_TILE_H + 2 * p.halo;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int units = tiles * p.NT;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo); tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < CV_A_SLOTS; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < CV_B_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 128); }
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.NT * N_T; i += CV_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 3) tc::tmem_alloc(&tmem_base_s, C::TMEM_COLS);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ---- activation producer: one (hi, lo) halo box per 64-channel chunk ----
+    if (lane == 0) {
+      const uint32_t bytes = 2u * (uint32_t)(bw * bh * 128);
+      int ai = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int rem = u % tiles;
+        const int x0 = (rem % p.tiles_x) * 8 * T - p.halo, y0 = (rem / p.tiles_x) * CV_TILE_H - p.halo;
+        for (int kc = 0; kc < p.KC; ++kc, ++ai) {
+          const int s = ai % CV_A_SLOTS;
+          tc::mbar_wait(&a_empty[s], ((ai / CV_A_SLOTS) & 1) ^ 1);
+          uint8_t* dst = a_base + s * C::A_SLOT;
+          tc::mbar_arrive_expect_tx(&a_full[s], bytes);
+          tc::tma_load_3d(dst, &tmHi, &a_full[s], kc * 64, x0, y0);
+          tc::tma_load_3d(dst + C::A_PLANE, &tmLo, &a_full[s], kc * 64, x0, y0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- weight producer: one [w_hi | w_lo] x 64 tile per (tap, chunk) ----
+    if (lane == 0) {
+      int bi = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int nt = u / tiles;
+        for (int kc = 0; kc < p.KC; ++kc)
+          for (int tap = 0; tap < p.taps; ++tap, ++bi) {
+            const int s = bi % CV_B_STAGES;
+            tc::mbar_wait(&b_empty[s], ((bi / CV_B_STAGES) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&b_full[s], C::B_STAGE);
+            tc::tma_load_2d(b_base + s * C::B_STAGE, &tmW, &b_full[s], 0, ((nt * p.taps + tap) * p.KC + kc) * 2 * N_T);
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      constexpr uint32_t idesc_cat = tc::make_idesc(128, 2 * N_T, 0, 0, 1);
+      constexpr uint32_t idesc_hi = tc::make_idesc(128, N_T, 0, 0, 1);
+      const uint32_t sbo = (uint32_t)bw * 128;
+      int ai = 0, bi = 0, ui = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+        const int ab = ui & 1;
+        tc::mbar_wait(&t_empty[ab], ((ui >> 1) & 1) ^ 1);
+        tc::tcgen05_fence_after();
+        for (int kc = 0; kc < p.KC; ++kc, ++ai) {
+          const int as = ai % CV_A_SLOTS;
+          tc::mbar_wait(&a_full[as], (ai / CV_A_SLOTS) & 1);
+          tc::tcgen05_fence_after();
+          const uint32_t a_slot = tc::smem_u32(a_base + as * C::A_SLOT);
+          for (int tap = 0; tap < p.taps; ++tap, ++bi) {
+            const int bs = bi % CV_B_STAGES;
+            tc::mbar_wait(&b_full[bs], (bi / CV_B_STAGES) & 1);
+            tc::tcgen05_fence_after();
+            const uint32_t b_addr = tc::smem_u32(b_base + bs * C::B_STAGE);
+            const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap % 3 : 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const uint32_t d = tmem_base + (uint32_t)((ab * T + t) * C::ACC_COLS);
+              const uint32_t a_hi = a_slot + (uint32_t)((dy * bw + dx + 8 * t) * 128);
+              const uint32_t a_lo = a_hi + C::A_PLANE;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                tc::umma_f16(d, tc::make_smem_desc_sw128(a_hi + k * 32, 16, sbo), db, idesc_cat, (kc | tap | k) ? 1u : 0u);
+                tc::umma_f16(d, tc::make_smem_desc_sw128(a_lo + k * 32, 16, sbo), db, idesc_hi, 1u);
+              }
+            }
+            tc::umma_commit(&b_empty[bs]);
+          }
+          tc::umma_commit(&a_empty[as]);
+        }
+        tc::umma_commit(&t_full[ab]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- epilogue: TMEM lane quarter q <-> tile rows 4q..4q+3 (8 pixels each) ----
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int px = m & 7, py = m >> 3;
+    const int Ho = p.pool ? (p.H >> 1) : p.H, Wo = p.pool ? (p.W >> 1) : p.W;
+    int ui = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+      const int ab = ui & 1;
+      const int nt = u / tiles, rem = u % tiles;
+      const int x0 = (rem % p.tiles_x) * 8 * T, y0 = (rem / p.tiles_x) * CV_TILE_H;
+      tc::mbar_wait(&t_full[ab], (ui >> 1) & 1);
+      tc::tcgen05_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const uint32_t d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * T + t) * C::ACC_COLS);
+        int gx = x0 + 8 * t + px, gy = y0 + py;
+        bool ok = gx < p.W && gy < p.H;
+        if (p.pool) {
+          ok = !(px & 1) && !(py & 1) && (gx >> 1) < Wo && (gy >> 1) < Ho;
+          gx >>= 1; gy >>= 1;
+        }
+        const size_t pix = (size_t)gy * Wo + gx;
+#pragma unroll 1
+        for (int c = 0; c < N_T / 32; ++c) {
+          uint32_t v1[32], v2[32];
+          tc::tmem_ld32(d + c * 32, v1);
+          tc::tmem_ld32(d + N_T + c * 32, v2);
+          tc::tmem_ld_wait();
+          const int ch0 = nt * N_T + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bias_s[ch0 + j];
+            if (p.relu) x = fmaxf(x, 0.f);
+            f[j] = x;
+          }
+          if (p.pool) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+              f[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+            }
+          }
+          if (ok && p.y_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f[j], f[j + 1]);
+              const float2 hf = __bfloat1622float2(h);
+              const __nv_bfloat162 l = __floats2bfloat162_rn(f[j] - hf.x, f[j + 1] - hf.y);
+              hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + pix * p.ld16 + ch0);
+            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + pix * p.ld16 + ch0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+          if (ok && p.y32) {
+            if (p.planar) {
+              const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ch0 + j < p.cout) p.y32[(size_t)(ch0 + j) * plane + pix] = f[j];
+            } else if (ch0 + 32 <= p.cout && (p.ld32 & 3) == 0) {
+              float4* o = reinterpret_cast<float4*>(p.y32 + pix * p.ld32 + ch0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ch0 + j < p.cout) p.y32[pix * p.ld32 + ch0 + j] = f[j];
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&t_empty[ab]);
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 3) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int N_T, int T>
+static int launch_conv(const CUtensorMap& tmHi, const CUtensorMap& tmLo, const CUtensorMap& tmW, ConvTcParams p, cudaStream_t st) {
+  using C = ConvCfg<N_T, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    I4D_CUDA_CALL(cudaFuncSetAttribute(conv_tc_kernel<N_T, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  p.tiles_x = i4d_cdiv(p.W, 8 * T);
+  p.tiles_y = i4d_cdiv(p.H, CV_TILE_H);
+  const long long units = (long long)p.tiles_x * p.tiles_y * p.NT;
+  const int grid = (int)(units < i4d_num_sms() ? units : i4d_num_sms());
+  conv_tc_kernel<N_T, T><<<grid, CV_THREADS, C::SMEM, st>>>(tmHi, tmLo, tmW, p);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_conv_tile_cout(int cout_pad) { return cout_pad == 64 ? 64 : 128; }
+
+extern "C" __attribute__((visibility("default"))) int i4d_conv_bf16x3_tc(
+    const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_packed, const float* bias, int cout_pad, int cout,
+    int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32, int y32_planar, void* stream) {
+  I4D_CHECK_ARG(x_hi && x_lo && w_packed && bias, "null pointer");
+  I4D_CHECK_ARG(H > 0 && W > 0 && Cin > 0 && Cin % 64 == 0, "Cin must be a positive multiple of 64");
+  I4D_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
+  I4D_CHECK_ARG(cout_pad > 0 && cout_pad % 64 == 0 && cout_pad <= 512 && cout > 0 && cout <= cout_pad, "bad output channel counts");
+  I4D_CHECK_ARG((y_hi != nullptr) == (y_lo != nullptr) && (y_hi || y32), "need split planes and/or an f32 output");
+  I4D_CHECK_ARG(!pool || (!y32 && H >= 2 && W >= 2), "the fused 2x2 max-pool writes split planes only");
+  I4D_CHECK_ARG(!y_hi || cout == cout_pad, "split-plane output needs cout == cout_pad");
+  I4D_CHECK_ARG(!y32 || y32_planar || ld32 >= cout, "ld32 too small");
+  const int n_t = i4d_conv_tile_cout(cout_pad);
+  I4D_CHECK_ARG(cout_pad % n_t == 0, "cout_pad must be 64 or a multiple of 128");
+  const int taps = ksize * ksize, halo = ksize / 2, T = n_t == 64 ? 2 : 1;
+  ConvTcParams p{};
+  p.H = H; p.W = W; p.KC = Cin / 64; p.taps = taps; p.NT = cout_pad / n_t; p.halo = halo; p.relu = relu; p.pool = pool;
+  p.bias = bias; p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
+  p.ld16 = cout_pad; p.y32 = y32; p.ld32 = ld32; p.planar = y32_planar; p.cout = cout;
+  CUtensorMap tmHi, tmLo, tmW;
+  const uint32_t bw = 8 * T + 2 * halo, bh = CV_TILE_H + 2 * halo;
+  if (int rc = i4d_make_tmap_hwc_bf16(&tmHi, x_hi, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, bh, bw)) return rc;
+  if (int rc = i4d_make_tmap_hwc_bf16(&tmLo, x_lo, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, bh, bw)) return rc;
+  const uint64_t wrows = (uint64_t)p.NT * taps * p.KC * 2 * n_t;
+  if (int rc = i4d_make_tmap_2d_bf16(&tmW, w_packed, wrows, 64, 64, 2 * n_t, 64)) return rc;
+  if (n_t == 64) return launch_conv<64, 2>(tmHi, tmLo, tmW, p, (cudaStream_t)stream);
+  return launch_conv<128, 1>(tmHi, tmLo, tmW, p, (cudaStream_t)stream);
+}

@@ -192,6 +192,24 @@ int i4d_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
   return I4D_OK;
 }
 
+int i4d_make_tmap_hwc_bf16(CUtensorMap* out, const void* base, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { i4d_set_error("cuTensorMapEncodeTiled entry point not available"); return I4D_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (C % 64) || box_h > 256 || box_w > 256) {
+    i4d_set_error("TMA image map: base %p must be 16-byte aligned, C %llu a multiple of 64, box <= 256", base, (unsigned long long)C);
+    return I4D_ERR_INVALID;
+  }
+  cuuint64_t dims[3] = {C, W, H};
+  cuuint64_t strides[2] = {C * 2, W * C * 2};
+  cuuint32_t box[3] = {64, box_w, box_h};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { i4d_set_error("cuTensorMapEncodeTiled (3D) failed (%d)", (int)r); return I4D_ERR_CUDA; }
+  return I4D_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
     const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr, float* C32, int ldc32,
     void* C16, int ldc16, int M, int N, int K, float alpha, int relu, void* stream) {

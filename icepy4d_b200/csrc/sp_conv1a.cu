@@ -7,6 +7,7 @@
 // (LightGlue copy: thirdparty/LightGlue/lightglue/superpoint.py:155).
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "../../include/icepy4d_b200.h"
 
 template <typename OutT> struct Pack4;
@@ -25,6 +26,20 @@ template <> struct Pack4<__nv_bfloat16> {
     __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
     uint2 v; v.x = *reinterpret_cast<uint32_t*>(&x); v.y = *reinterpret_cast<uint32_t*>(&y);
     *reinterpret_cast<uint2*>(p) = v;
+  }
+};
+
+// split bf16 planes (hi at p, lo at p + plane): the operand format of the tcgen05 convolutions in conv_tc.cu
+struct SplitBf16 { __nv_bfloat16 v; };
+template <> struct Pack4<SplitBf16> {
+  static __device__ __forceinline__ void store(SplitBf16* p, size_t plane, float a, float b, float c, float d) {
+    __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
+    const float2 xf = __bfloat1622float2(x), yf = __bfloat1622float2(y);
+    __nv_bfloat162 xl = __floats2bfloat162_rn(a - xf.x, b - xf.y), yl = __floats2bfloat162_rn(c - yf.x, d - yf.y);
+    uint2 v; v.x = *reinterpret_cast<uint32_t*>(&x); v.y = *reinterpret_cast<uint32_t*>(&y);
+    uint2 l; l.x = *reinterpret_cast<uint32_t*>(&xl); l.y = *reinterpret_cast<uint32_t*>(&yl);
+    *reinterpret_cast<uint2*>(p) = v;
+    *reinterpret_cast<uint2*>(p + plane) = l;
   }
 };
 
@@ -62,7 +77,10 @@ __global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict_
       for (int t = 0; t < 9; ++t) acc = fmaf(v[t], w[t], acc);
       o[c] = fmaxf(acc, 0.f);
     }
-    Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, o[0], o[1], o[2], o[3]);
+    if constexpr (std::is_same<OutT, SplitBf16>::value)
+      Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, (size_t)H * W * 64, o[0], o[1], o[2], o[3]);
+    else
+      Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -118,13 +136,14 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_conv1a_relu(const f
                                                                         const float* bias, void* out_nhwc, int out_dtype,
                                                                         void* stream) {
   I4D_CHECK_ARG(image && weight && bias && out_nhwc && H > 0 && W > 0, "null pointer or empty image");
-  I4D_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "out_dtype: 0 = f32, 1 = f16, 2 = bf16");
+  I4D_CHECK_ARG(out_dtype >= 0 && out_dtype <= 3, "out_dtype: 0 = f32, 1 = f16, 2 = bf16, 3 = split bf16 planes");
   const long long threads = (long long)H * W * 4;
   const int grid = i4d_cdiv(threads, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == 0) sp_conv1a_kernel<float><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<float*>(out_nhwc));
   else if (out_dtype == 1) sp_conv1a_kernel<__half><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__half*>(out_nhwc));
-  else sp_conv1a_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+  else if (out_dtype == 2) sp_conv1a_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+  else sp_conv1a_kernel<SplitBf16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<SplitBf16*>(out_nhwc));
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }

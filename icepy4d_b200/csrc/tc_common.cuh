@@ -56,6 +56,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3D tiled load (c0 innermost); coordinates are signed: out-of-bounds elements are zero-filled, which is how the
+// convolution gets its zero padding
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // one full warp, ncols = pow2 >= 32
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -118,3 +127,5 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // box = box_cols x box_rows elements, 128-byte swizzle (box_cols * 2 bytes must be 128).
 int i4d_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols);
+// channels-last bf16 image [H][W][C] (C innermost): box = 64 channels x box_w x box_h pixels, 128-byte swizzle, zero OOB fill
+int i4d_make_tmap_hwc_bf16(CUtensorMap* out, const void* base, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w);

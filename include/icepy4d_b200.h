@@ -30,13 +30,31 @@ int i4d_device_sm_count(void);
 
 /* ---- SuperPoint first layer ---------------------------------------------------------------------------- */
 /* superpoint.py:154 — relu(conv1a(image)): 1 -> 64 channels, 3x3, pad 1.  image [H,W] f32, weight [64,9] (= [64,1,3,3]),
- * bias [64]; out [H,W,64] channels-last, out_dtype 0 = f32, 1 = f16, 2 = bf16. */
+ * bias [64]; out [H,W,64] channels-last, out_dtype 0 = f32, 1 = f16, 2 = bf16, 3 = split bf16: out is [2][H,W,64], plane 0
+ * = bf16(v), plane 1 = bf16(v - plane 0), the operand format of i4d_conv_bf16x3_tc. */
 int i4d_sp_conv1a_relu(const float* image, int H, int W, const float* weight, const float* bias, void* out_nhwc,
                        int out_dtype, void* stream);
 
 /* superpoint.py:156,159,162 — MaxPool2d(2,2) on a channels-last activation [H,W,C] -> [H/2,W/2,C].  elem_bytes 4 (f32) or
  * 2 (f16/bf16, requires nonneg = 1: post-ReLU data, compared as bit patterns). */
 int i4d_maxpool2x2_nhwc(const void* in, int H, int W, int C, void* out, int elem_bytes, int nonneg, void* stream);
+
+/* superpoint.py:154-168 (conv1b .. conv4b, convPa, convDa: 3x3, pad 1) and :193-196 (convPb, convDb: 1x1) as tcgen05
+ * implicit GEMMs on SPLIT bf16 operands: every f32 value v travels as hi = bf16(v), lo = bf16(v - hi) and the kernel
+ * accumulates x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in f32 (relative error ~2^-16; a single TF32/bf16 product is not enough
+ * for the >= 99 % match-IoU bar).
+ *   x_hi, x_lo : bf16 [H][W][Cin] channels-last planes, Cin % 64 == 0
+ *   w_packed   : bf16 [(nt*taps + tap)*Cin/64 + kc][2*n_t][64] with n_t = i4d_conv_tile_cout(cout_pad), taps = ksize^2
+ *                (tap = ky*3 + kx); rows 0..n_t-1 of a block hold bf16(w[nt*n_t + r, kc*64 + k, ky, kx]), rows
+ *                n_t..2n_t-1 the bf16 remainder; output channels >= cout are zero
+ *   bias       : f32 [cout_pad]
+ *   outputs    : y_hi / y_lo bf16 planes [Ho][Wo][cout_pad] (requires cout == cout_pad; with pool = 1 the 2x2/stride-2
+ *                max-pool of superpoint.py:156,159,162 is fused: Ho = H/2, Wo = W/2) and/or y32 f32, either channels-last
+ *                [H][W][ld32] or planar [cout][H][W] (y32_planar = 1, the layout i4d_sp_score_map reads) */
+int i4d_conv_tile_cout(int cout_pad);
+int i4d_conv_bf16x3_tc(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_packed, const float* bias,
+                       int cout_pad, int cout, int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32,
+                       int y32_planar, void* stream);
 
 /* ---- SuperPoint post-processing ----------------------------------------------------------------------- */
 /* thirdparty/SuperGlue/models/superpoint.py:169-172 — softmax over 65 channels, drop dustbin, 8x8 pixel shuffle.
