@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(&q_full, FA_Q_BYTES);
       tc::tma_load_2d(sQ, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0);
       auto load_k = [&](int j) {
@@ -138,27 +138,28 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer (one elected lane: operands stay in uniform registers)
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_qk = tc::make_idesc(FA_BM, FA_BN, 0, 0, 1);   // A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = tc::make_idesc(FA_BM, FA_D, 0, 1, 1);    // A = P (K-major), B = V (MN-major)
-      const uint32_t aQ = tc::smem_u32(sQ), aP = tc::smem_u32(sP);
+      constexpr uint32_t hi_k = tc::desc_hi_sw128(1024);                     // K-major operands and MN-major V: SBO = 1024
+      const uint32_t dQ = tc::desc_lo_sw128(tc::smem_u32(sQ)), dP = tc::desc_lo_sw128(tc::smem_u32(sP));
+      const uint32_t dK0 = tc::desc_lo_sw128(tc::smem_u32(sK));
       auto issue_qk = [&](int j) {
         const int s = j % FA_KV_STAGES;
         tc::mbar_wait(&k_full[s], (j / FA_KV_STAGES) & 1);
         if (j > 0) tc::mbar_wait(&s_empty, (j - 1) & 1);                    // S_{j-1} has been read into registers
         tc::tcgen05_fence_after();
-        const uint32_t aK = tc::smem_u32(sK + s * FA_KV_BYTES);
+        const uint32_t dK = dK0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          tc::umma_f16(tmem_S, tc::make_smem_desc_sw128(aQ + k * 32, 16, 1024), tc::make_smem_desc_sw128(aK + k * 32, 16, 1024),
-                       idesc_qk, k ? 1u : 0u);
+        for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tmem_S, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
         tc::umma_commit(&k_empty[s]);                                       // K_j no longer needed once these retire
         tc::umma_commit(&s_full);
       };
       tc::mbar_wait(&q_full, 0);
       issue_qk(0);
-      const uint32_t aV = tc::smem_u32(sV);
+      // V descriptor: MN-major, 8-key groups 1024 B apart (SBO), one 64-wide N atom: LBO field = 1024 >> 4 as well
+      const uint32_t dV = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) issue_qk(j + 1);                                  // runs while the softmax warps exponentiate block j
         tc::mbar_wait(&v_full, j & 1);
@@ -166,11 +167,9 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
-          // A: P k-slice = 16 keys = 32 B inside the 128-B swizzle row of K-half (k / 4)
-          const uint64_t da = tc::make_smem_desc_sw128(aP + (k >> 2) * (FA_BM * 128) + (k & 3) * 32, 16, 1024);
-          // B: V rows [16k, 16k+16) x 64 dims, MN-major: 8-key groups are 1024 B apart (SBO), one 64-wide N atom (LBO unused)
-          const uint64_t db = tc::make_smem_desc_sw128(aV + k * 16 * 128, 1024, 1024);
-          tc::umma_f16(tmem_O, da, db, idesc_pv, (j | k) ? 1u : 0u);
+          // A: P k-slice = 16 keys = 32 B inside the 128-B swizzle row of K-half (k / 4);  B: V rows [16k, 16k+16) x 64 dims
+          tc::umma_f16_parts(tmem_O, dP + (uint32_t)(((k >> 2) * (FA_BM * 128) + (k & 3) * 32) >> 4), hi_k,
+                             dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (j | k) ? 1u : 0u);
         }
         tc::umma_commit(&v_empty);                                          // V buffer free
         tc::umma_commit(&pv_done);                                          // O includes block j; P buffer free

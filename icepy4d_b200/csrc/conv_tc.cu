@@ -14,8 +14,8 @@
 // so that  x_hi * [w_hi | w_lo]  is ONE N = 2*N_T MMA; x_lo * w_hi is a second N = N_T MMA into the first half of the
 // same accumulator; the epilogue adds the two halves.
 //
-// Roles (256 threads, one persistent CTA per SM): warp 0 lane 0 = activation TMA producer, warp 1 lane 0 = weight TMA
-// producer, warp 2 lane 0 = MMA issuer, warps 4-7 = epilogue (tcgen05.ld -> +bias, ReLU, optional fused 2x2 max-pool via
+// Roles (384 threads, one persistent CTA per SM): warp 0 (one elected lane) = activation TMA producer, warp 1 = weight TMA
+// producer, warp 2 = MMA issuer, warps 4-11 = epilogue (tcgen05.ld -> +bias, ReLU, optional fused 2x2 max-pool via
 // warp shuffles -> split back to hi/lo bf16 or f32).  Accumulators are double-buffered in TMEM (all 512 columns), so the
 // epilogue of one region overlaps the MMAs of the next.
 //
@@ -25,7 +25,7 @@
 #include "tc_common.cuh"
 #include "../../include/icepy4d_b200.h"
 
-#define CV_THREADS 256
+#define CV_THREADS 384
 #define CV_TILE_H 16
 #define CV_A_SLOTS 2
 #define CV_B_STAGES 3
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo); tc::prefetch_tmap(&tmW);
     for (int s = 0; s < CV_A_SLOTS; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < CV_B_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 256); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.NT * N_T; i += CV_THREADS) bias_s[i] = p.bias[i];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // ---- activation producer: one (hi, lo) halo box per 64-channel chunk ----
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t bytes = 2u * (uint32_t)(bw * bh * 128);
       int ai = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ---- weight producer: one [w_hi | w_lo] x 64 tile per (tap, chunk) ----
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int bi = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int nt = u / tiles;
@@ -119,40 +119,43 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 2) {
-    // ---- MMA issuer ----
-    if (lane == 0) {
+    // ---- MMA issuer: one elected lane; descriptors advance by adding (bytes >> 4) to a precomputed low word ----
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_cat = tc::make_idesc(128, 2 * N_T, 0, 0, 1);
       constexpr uint32_t idesc_hi = tc::make_idesc(128, N_T, 0, 0, 1);
-      const uint32_t sbo = (uint32_t)bw * 128;
+      constexpr uint32_t b_hiword = tc::desc_hi_sw128(1024);
+      const uint32_t a_hiword = tc::desc_hi_sw128((uint32_t)bw * 128);
+      const uint32_t a_lo0 = tc::desc_lo_sw128(tc::smem_u32(a_base)), b_lo0 = tc::desc_lo_sw128(tc::smem_u32(b_base));
+      const uint32_t row_step = (uint32_t)bw * 8;                      // one halo row, in 16-byte units
       int ai = 0, bi = 0, ui = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
         const int ab = ui & 1;
         tc::mbar_wait(&t_empty[ab], ((ui >> 1) & 1) ^ 1);
         tc::tcgen05_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(ab * T * C::ACC_COLS);
         for (int kc = 0; kc < p.KC; ++kc, ++ai) {
           const int as = ai % CV_A_SLOTS;
           tc::mbar_wait(&a_full[as], (ai / CV_A_SLOTS) & 1);
           tc::tcgen05_fence_after();
-          const uint32_t a_slot = tc::smem_u32(a_base + as * C::A_SLOT);
+          uint32_t a_tap = a_lo0 + (uint32_t)(as * (C::A_SLOT >> 4));   // tap (0,0); taps advance by 8 (dx) / row_step (dy)
+          int dx = 0;
           for (int tap = 0; tap < p.taps; ++tap, ++bi) {
             const int bs = bi % CV_B_STAGES;
             tc::mbar_wait(&b_full[bs], (bi / CV_B_STAGES) & 1);
             tc::tcgen05_fence_after();
-            const uint32_t b_addr = tc::smem_u32(b_base + bs * C::B_STAGE);
-            const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap % 3 : 0;
+            const uint32_t b_lo = b_lo0 + (uint32_t)(bs * (C::B_STAGE >> 4));
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const uint32_t d = tmem_base + (uint32_t)((ab * T + t) * C::ACC_COLS);
-              const uint32_t a_hi = a_slot + (uint32_t)((dy * bw + dx + 8 * t) * 128);
-              const uint32_t a_lo = a_hi + C::A_PLANE;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                tc::umma_f16(d, tc::make_smem_desc_sw128(a_hi + k * 32, 16, sbo), db, idesc_cat, (kc | tap | k) ? 1u : 0u);
-                tc::umma_f16(d, tc::make_smem_desc_sw128(a_lo + k * 32, 16, sbo), db, idesc_hi, 1u);
+                tc::umma_f16_parts(d0 + t * C::ACC_COLS, a_tap + t * 64 + k * 2, a_hiword, b_lo + k * 2, b_hiword, idesc_cat,
+                                   (kc | tap | k) ? 1u : 0u);
+                tc::umma_f16_parts(d0 + t * C::ACC_COLS, a_tap + (C::A_PLANE >> 4) + t * 64 + k * 2, a_hiword, b_lo + k * 2, b_hiword,
+                                   idesc_hi, 1u);
               }
             }
             tc::umma_commit(&b_empty[bs]);
+            if (++dx == 3) { dx = 0; a_tap += row_step - 16; } else a_tap += 8;
           }
           tc::umma_commit(&a_empty[as]);
         }
@@ -161,11 +164,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ---- epilogue: TMEM lane quarter q <-> tile rows 4q..4q+3 (8 pixels each) ----
-    const int q = warp & 3;
+    // ---- epilogue: 8 warps.  TMEM lane quarter q = warp % 4 <-> tile rows 4q..4q+3 (8 pixels each); the two warps of a
+    // quarter split the unit's T * N_T/32 (tile, 32-channel chunk) items, two each, and keep the second item's TMEM load
+    // in flight while the first is written out. ----
+    const int q = warp & 3, g = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int px = m & 7, py = m >> 3;
     const int Ho = p.pool ? (p.H >> 1) : p.H, Wo = p.pool ? (p.W >> 1) : p.W;
+    constexpr int CH = N_T / 32;                       // chunks per tile
+    static_assert(T * CH == 4, "two items per epilogue warp");
+    const bool odd = lane & 1, up = (lane >> 3) & 1;
     int ui = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
       const int ab = ui & 1;
@@ -173,76 +181,105 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       const int x0 = (rem % p.tiles_x) * 8 * T, y0 = (rem / p.tiles_x) * CV_TILE_H;
       tc::mbar_wait(&t_full[ab], (ui >> 1) & 1);
       tc::tcgen05_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < T; ++t) {
-        const uint32_t d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * T + t) * C::ACC_COLS);
-        int gx = x0 + 8 * t + px, gy = y0 + py;
-        bool ok = gx < p.W && gy < p.H;
-        if (p.pool) {
-          ok = !(px & 1) && !(py & 1) && (gx >> 1) < Wo && (gy >> 1) < Ho;
-          gx >>= 1; gy >>= 1;
+      const uint32_t d_unit = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * T * C::ACC_COLS);
+      uint32_t v1[32], v2[32];
+      float f[32];
+      auto issue = [&](int item) {
+        const uint32_t d = d_unit + (uint32_t)((item / CH) * C::ACC_COLS + (item % CH) * 32);
+        tc::tmem_ld32(d, v1);
+        tc::tmem_ld32(d + N_T, v2);
+      };
+      auto combine = [&](int item) {
+        const int ch0 = nt * N_T + (item % CH) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bias_s[ch0 + j];
+          f[j] = p.relu ? fmaxf(x, 0.f) : x;
         }
-        const size_t pix = (size_t)gy * Wo + gx;
-#pragma unroll 1
-        for (int c = 0; c < N_T / 32; ++c) {
-          uint32_t v1[32], v2[32];
-          tc::tmem_ld32(d + c * 32, v1);
-          tc::tmem_ld32(d + N_T + c * 32, v2);
-          tc::tmem_ld_wait();
-          const int ch0 = nt * N_T + c * 32;
-          float f[32];
+      };
+      auto write = [&](int item) {
+        const int t = item / CH, ch0 = nt * N_T + (item % CH) * 32;
+        int gx = x0 + 8 * t + px, gy = y0 + py;
+        if (p.pool) {
+          // 2x2 max over lanes (m, m^1, m^8, m^9): each exchange hands over half of the channels, so 24 shuffles instead of
+          // 64 and every lane ends up owning 8 pooled channels of the output pixel (16-byte stores from all lanes)
+          float k[16], z[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bias_s[ch0 + j];
-            if (p.relu) x = fmaxf(x, 0.f);
-            f[j] = x;
+          for (int j = 0; j < 16; ++j) {
+            const float r = __shfl_xor_sync(0xffffffffu, odd ? f[j] : f[j + 16], 1);
+            k[j] = fmaxf(odd ? f[j + 16] : f[j], r);
           }
-          if (p.pool) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-              f[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float r = __shfl_xor_sync(0xffffffffu, up ? k[j] : k[j + 8], 8);
+            z[j] = fmaxf(up ? k[j + 8] : k[j], r);
           }
-          if (ok && p.y_hi) {
-            uint32_t hi[16], lo[16];
+          gx >>= 1; gy >>= 1;
+          if (gx < Wo && gy < Ho) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f[j], f[j + 1]);
+            for (int j = 0; j < 8; j += 2) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(z[j], z[j + 1]);
               const float2 hf = __bfloat1622float2(h);
-              const __nv_bfloat162 l = __floats2bfloat162_rn(f[j] - hf.x, f[j + 1] - hf.y);
+              const __nv_bfloat162 l = __floats2bfloat162_rn(z[j] - hf.x, z[j + 1] - hf.y);
               hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
               lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + pix * p.ld16 + ch0);
-            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + pix * p.ld16 + ch0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
+            const size_t o = ((size_t)gy * Wo + gx) * p.ld16 + ch0 + (odd ? 16 : 0) + (up ? 8 : 0);
+            *reinterpret_cast<uint4*>(p.y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(p.y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          if (ok && p.y32) {
-            if (p.planar) {
-              const size_t plane = (size_t)p.H * p.W;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ch0 + j < p.cout) p.y32[(size_t)(ch0 + j) * plane + pix] = f[j];
-            } else if (ch0 + 32 <= p.cout && (p.ld32 & 3) == 0) {
-              float4* o = reinterpret_cast<float4*>(p.y32 + pix * p.ld32 + ch0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ch0 + j < p.cout) p.y32[pix * p.ld32 + ch0 + j] = f[j];
-            }
-          }
-          __syncwarp();
+          return;
         }
-      }
+        if (gx >= p.W || gy >= p.H) return;
+        const size_t pix = (size_t)gy * p.W + gx;
+        if (p.y_hi) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f[j], f[j + 1]);
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(f[j] - hf.x, f[j + 1] - hf.y);
+            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.y_hi + pix * p.ld16 + ch0);
+          uint4* ol = reinterpret_cast<uint4*>(p.y_lo + pix * p.ld16 + ch0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+        if (p.y32) {
+          if (p.planar) {
+            const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ch0 + j < p.cout) p.y32[(size_t)(ch0 + j) * plane + pix] = f[j];
+          } else if (ch0 + 32 <= p.cout && (p.ld32 & 3) == 0) {
+            float4* o = reinterpret_cast<float4*>(p.y32 + pix * p.ld32 + ch0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ch0 + j < p.cout) p.y32[pix * p.ld32 + ch0 + j] = f[j];
+          }
+        }
+      };
+      issue(2 * g);
+      tc::tmem_ld_wait();
+      combine(2 * g);
+      issue(2 * g + 1);
+      write(2 * g);
+      __syncwarp();
+      tc::tmem_ld_wait();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&t_empty[ab]);
+      combine(2 * g + 1);
+      tc::mbar_arrive(&t_empty[ab]);          // accumulator values are in registers: the MMA warp may overwrite them
+      write(2 * g + 1);
+      __syncwarp();
     }
   }
   tc::tcgen05_fence_before();

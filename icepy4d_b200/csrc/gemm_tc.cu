@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
   const uint32_t tmem_d = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % GT_STAGES;
         const uint32_t ph = (kb / GT_STAGES) & 1;
@@ -69,21 +69,18 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(GT_BM, GT_BN, 0, 0, 1);
+      constexpr uint32_t hi = tc::desc_hi_sw128(1024);
+      const uint32_t d0 = tc::desc_lo_sw128(tc::smem_u32(smem));
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % GT_STAGES;
         const uint32_t ph = (kb / GT_STAGES) & 1;
         tc::mbar_wait(&full_bar[s], ph);
         tc::tcgen05_fence_after();
-        const uint32_t sa = tc::smem_u32(smem + s * GT_STAGE_BYTES);
-        const uint32_t sb = sa + GT_BM * GT_BK * 2;
+        const uint32_t da = d0 + (uint32_t)(s * (GT_STAGE_BYTES >> 4)), db = da + ((GT_BM * GT_BK * 2) >> 4);
 #pragma unroll
-        for (int k = 0; k < GT_BK / 16; ++k) {
-          const uint64_t da = tc::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t db = tc::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-          tc::umma_f16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
-        }
+        for (int k = 0; k < GT_BK / 16; ++k) tc::umma_f16_parts(tmem_d, da + k * 2, hi, db + k * 2, hi, idesc, (kb | k) ? 1u : 0u);
         tc::umma_commit(&empty_bar[s]);       // smem stage reusable once these MMAs retire
       }
       tc::umma_commit(&accum_bar);            // accumulator complete

@@ -7,7 +7,6 @@
 // (LightGlue copy: thirdparty/LightGlue/lightglue/superpoint.py:155).
 #include "common.cuh"
 #include <cuda_fp16.h>
-#include <type_traits>
 #include "../../include/icepy4d_b200.h"
 
 template <typename OutT> struct Pack4;
@@ -26,20 +25,6 @@ template <> struct Pack4<__nv_bfloat16> {
     __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
     uint2 v; v.x = *reinterpret_cast<uint32_t*>(&x); v.y = *reinterpret_cast<uint32_t*>(&y);
     *reinterpret_cast<uint2*>(p) = v;
-  }
-};
-
-// split bf16 planes (hi at p, lo at p + plane): the operand format of the tcgen05 convolutions in conv_tc.cu
-struct SplitBf16 { __nv_bfloat16 v; };
-template <> struct Pack4<SplitBf16> {
-  static __device__ __forceinline__ void store(SplitBf16* p, size_t plane, float a, float b, float c, float d) {
-    __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
-    const float2 xf = __bfloat1622float2(x), yf = __bfloat1622float2(y);
-    __nv_bfloat162 xl = __floats2bfloat162_rn(a - xf.x, b - xf.y), yl = __floats2bfloat162_rn(c - yf.x, d - yf.y);
-    uint2 v; v.x = *reinterpret_cast<uint32_t*>(&x); v.y = *reinterpret_cast<uint32_t*>(&y);
-    uint2 l; l.x = *reinterpret_cast<uint32_t*>(&xl); l.y = *reinterpret_cast<uint32_t*>(&yl);
-    *reinterpret_cast<uint2*>(p) = v;
-    *reinterpret_cast<uint2*>(p + plane) = l;
   }
 };
 
@@ -77,10 +62,71 @@ __global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict_
       for (int t = 0; t < 9; ++t) acc = fmaf(v[t], w[t], acc);
       o[c] = fmaxf(acc, 0.f);
     }
-    if constexpr (std::is_same<OutT, SplitBf16>::value)
-      Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, (size_t)H * W * 64, o[0], o[1], o[2], o[3]);
-    else
-      Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, o[0], o[1], o[2], o[3]);
+    Pack4<OutT>::store(out + (size_t)pix * 64 + cg * 16 + q * 4, o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Split-plane variant, register-blocked: thread = (4 consecutive pixels, 8 channels).  The 72 weights of the 8 channels are
+// fetched once (18 LDS.128 from a [tap][channel] table) and reused for the 4 pixels, so the kernel is bound by its 16-byte
+// stores (8 lanes = the 128 contiguous bytes of one pixel per plane) instead of by shared-memory weight reads.
+__global__ void __launch_bounds__(256) sp_conv1a_split_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ wgt,
+                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) float w_s[9 * 64];
+  __shared__ __align__(16) float b_s[64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) w_s[(i % 9) * 64 + i / 9] = wgt[i];      // [ch][tap] -> [tap][ch]
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) b_s[i] = bias[i];
+  __syncthreads();
+  const int wq = (W + 3) >> 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(gid & 7);
+  const long long grp = gid >> 3;
+  if (grp >= (long long)H * wq) return;
+  const int y = (int)(grp / wq), x0 = (int)(grp - (long long)y * wq) * 4;
+  float v[3][6];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 6; ++dx) {
+      const int yy = y + dy - 1, xx = x0 + dx - 1;
+      v[dy][dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
+    }
+  float acc[4][8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(b_s + cg * 8), b1 = *reinterpret_cast<const float4*>(b_s + cg * 8 + 4);
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      acc[px][0] = b0.x; acc[px][1] = b0.y; acc[px][2] = b0.z; acc[px][3] = b0.w;
+      acc[px][4] = b1.x; acc[px][5] = b1.y; acc[px][6] = b1.z; acc[px][7] = b1.w;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = *reinterpret_cast<const float4*>(w_s + t * 64 + cg * 8), w1 = *reinterpret_cast<const float4*>(w_s + t * 64 + cg * 8 + 4);
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float a = v[t / 3][px + t % 3];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[px][c] = fmaf(a, w[c], acc[px][c]);
+    }
+  }
+  const size_t plane = (size_t)H * W * 64;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    if (x0 + px >= W) break;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const float a = fmaxf(acc[px][c], 0.f), b = fmaxf(acc[px][c + 1], 0.f);
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    __nv_bfloat16* o = out + ((size_t)y * W + x0 + px) * 64 + cg * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -143,7 +189,10 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_conv1a_relu(const f
   if (out_dtype == 0) sp_conv1a_kernel<float><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<float*>(out_nhwc));
   else if (out_dtype == 1) sp_conv1a_kernel<__half><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__half*>(out_nhwc));
   else if (out_dtype == 2) sp_conv1a_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
-  else sp_conv1a_kernel<SplitBf16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<SplitBf16*>(out_nhwc));
+  else {
+    const long long t8 = (long long)H * ((W + 3) >> 2) * 8;
+    sp_conv1a_split_kernel<<<i4d_cdiv(t8, 256), 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+  }
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
