@@ -395,33 +395,42 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
-
 // ====================================================================================================================
-// Fused persistent Sinkhorn (N <= 8192, N % 4 == 0): ONE read of the score matrix per iteration instead of two.
+// Fused persistent Sinkhorn (N <= 8192, N % 4 == 0): ONE read of the score matrix per iteration instead of two, and part
+// of that read served by L2.
 //
 // One CTA per SM (cooperative launch), each owning a contiguous band of rows.  Rows are streamed HBM -> shared memory
-// with cp.async.bulk (1-D TMA) through a 3-stage mbarrier ring of 2 rows (<= 64 KB) per stage.  For every stage:
-//   phase A  row log-sum-exp of (S_ij + v_j) from shared memory (8 warps per row, warp-shuffle reduction)  -> u_i
-//   phase B  the SAME shared-memory rows, now with the fresh u_i added, update the per-thread accumulators of the
-//            16 columns this thread owns (registers, for the whole band)
-// Phase A of stage st+1 shares a barrier interval with phase B of stage st (software pipeline).  After the band: column
-// partials -> workspace, grid barrier, all CTAs combine the partials into v_j (+ the dustbin terms), grid barrier.
+// with cp.async.bulk (1-D TMA) through a 3-stage mbarrier ring of 2 rows (<= 64 KB) per stage.  The band is walked
+// top-down on even iterations and bottom-up on odd ones (boustrophedon): the rows touched last in iteration t are the
+// first of iteration t+1, so the tail of every pass is still resident in the 126 MB L2 when it is needed again.
+// 512 threads; each thread owns the same 16 columns for the whole solve:
+//   phase A  (stage s)    e_ij = 2^(x_ij + v_j - m_i) from shared memory into registers, per-warp partial row sums ->
+//                         shared memory, one mbarrier arrive per warp
+//   phase B  (stage s-1)  after its own phase A of stage s a warp waits for the partials of stage s-1 (complete long before,
+//                         unless a warp lags by a whole stage), finishes the row sums itself -> row factor a_i = kfac / sum,
+//                         and updates its column accumulators += e_ij * a_i from the registers kept since stage s-1
+//   duty                  one warp per stage (round-robin) additionally writes u_i, checks the sums and refills the
+//                         shared-memory buffer the stage has released; nobody waits for it
+// No block-wide barrier in the steady state: warps run up to a stage apart.
 //
 // Two arithmetic modes, same result up to f32 rounding:
 //   exact : running (max, sum) per accumulator — used for the first two iterations (and always if the fast mode trips);
 //   fast  : a-priori stabilisers instead of running maxima.  After a column update sum_i exp(S_ij + u_i + v_j) = nu_j, so
 //           S_ij + v_j <= log nu_j - u_i: m_i = log(nu_max) - u_i(previous) bounds every term of row i from above; likewise
-//           m_j = log(mu_max) - v_j(previous) for the columns.  One FFMA + FADD + MUFU.EX2 + FADD per element and pass, no
-//           dependent max chain.  A sum that underflows to 0 (potential jump > ~80 nats between two iterations) or is not
-//           finite raises a flag: the whole solve restarts in exact mode, on the device, without host involvement.
-// Everything is kept in the log2 domain.  HBM traffic per iteration = M*N*4 bytes (algorithmic count of SURVEY.md §8d: 2*M*N*4).
+//           m_j = log(mu_max) - v_j(previous) for the columns.  The column pass needs no second exponential:
+//           2^(x_ij + u_i - m_j) = e_ij * 2^(u_i + m_i - c_mu) — a rank-1 rescaling of the same kernel matrix.  Packed
+//           f32x2 arithmetic (FFMA2/FADD2): 3.25 issue slots per matrix element.  A sum that underflows to 0 (potential
+//           jump > ~80 nats between two iterations) or is not finite raises a flag: the whole solve restarts in exact
+//           mode, on the device, without host involvement.
+// Everything is kept in the log2 domain.  HBM traffic per iteration <= M*N*4 bytes (algorithmic count of SURVEY.md §8d: 2*M*N*4).
 // ====================================================================================================================
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define SK_THREADS 1024
-#define SK_ROWS 3                 // rows per stage
-#define SK_STAGES 2
+#define SK_THREADS 512
+#define SK_WARPS (SK_THREADS / 32)
+#define SK_ROWS 2                 // rows per stage
+#define SK_STAGES 3
 #define SK_MAXN 8192
 #define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
 #define SK_EXACT_ITERS 2
@@ -458,6 +467,9 @@ __device__ __forceinline__ void sk_mbar_init(uint64_t* b, uint32_t c) {
 __device__ __forceinline__ void sk_mbar_expect(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sk_mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
 __device__ __forceinline__ void sk_mbar_wait(uint64_t* b, uint32_t parity) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
   uint32_t ok = 0;
@@ -474,33 +486,61 @@ __device__ __forceinline__ void sk_bulk_load(void* dst, const void* src, uint32_
                : "memory");
 }
 
-
 struct SkCtx {
-  const float* S; float* stage_buf; uint64_t* full; float (*part_m)[SK_ROWS][SK_THREADS / 32]; float (*part_s)[SK_ROWS][SK_THREADS / 32];
+  const float* S; float* stage_buf; uint64_t* full; uint64_t* bpart;
+  float (*part_m)[SK_ROWS][SK_WARPS]; float (*part_s)[SK_ROWS][SK_WARPS];
   float* u; const float* v; float* pm; float* ps; int* flag;
-  int M, N, n4, row0, row1, nstage_total, cta;
-  float norm, c_mu, c_nu, extra_row;
+  int M, N, n4, row0, row1, nst, cta;
+  float norm, c_mu, c_nu, extra_row, kfac;
   const float* uold_s;   // previous-iteration u of this CTA's band, pre-scaled by log2(e) (shared memory)
   uint32_t row_bytes;
 };
+// ring / barrier phase bookkeeping carried across stages, bands and iterations (one copy per thread, all identical)
+struct SkRing {
+  uint32_t seq;        // stages consumed so far (all iterations)
+  uint32_t buf;        // seq % SK_STAGES
+  uint32_t full_par;   // bit b: parity the next wait on full[b] expects
+  uint32_t fq;         // fast-mode stages so far: partial-sum slot fq & 1, duty warp fq % SK_WARPS
+  uint32_t bp_par;     // bit p: parity the next wait on bpart[p] expects
+  uint32_t total;      // stages to run in total
+  __device__ __forceinline__ void advance() { ++seq; buf = (buf == SK_STAGES - 1) ? 0u : buf + 1u; }
+};
 
-// One stage (SK_ROWS rows) of the band: elements of my columns -> registers, row-pass partials, ONE block barrier, then
-// every warp finishes the row reduction itself and runs the column pass from registers.  FAST = a-priori stabilisers,
+// Stages are numbered consecutively across iterations (S never changes, so the ring keeps streaming through the grid
+// barriers).  Stage `seq` lives in buffer seq % SK_STAGES and covers row block sk_idx(seq) of the band: forward on even
+// passes, backward on odd ones.
+__device__ __forceinline__ int sk_idx(uint32_t seq, int nst) {
+  const uint32_t pass = seq / (uint32_t)nst, r = seq - pass * (uint32_t)nst;
+  return (pass & 1u) ? (nst - 1 - (int)r) : (int)r;
+}
+// one thread: start the bulk loads of stage `seq`.  Invariant kept by the callers: stage seq + SK_STAGES is issued as soon as
+// every thread has taken stage seq out of shared memory.
+__device__ __forceinline__ void sk_issue(const SkCtx& c, uint32_t seq) {
+  const int buf = seq % SK_STAGES;
+  const int r = c.row0 + sk_idx(seq, c.nst) * SK_ROWS;
+  const int nr = min(SK_ROWS, c.row1 - r);
+  sk_mbar_expect(&c.full[buf], nr * c.row_bytes);
+  for (int k = 0; k < nr; ++k)
+    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.N, c.S + (size_t)(r + k) * c.N, c.row_bytes, &c.full[buf]);
+}
+__device__ __forceinline__ void sk_wait_full(const SkCtx& c, SkRing& rg) {
+  sk_mbar_wait(&c.full[rg.buf], (rg.full_par >> rg.buf) & 1u);
+  rg.full_par ^= 1u << rg.buf;
+}
+
+// ---- exact mode: one stage (SK_ROWS rows): elements of my columns -> registers, row-pass partials, ONE block barrier, then
+// every warp finishes the row reduction itself and runs the column pass from registers.
 // FULL = all SK_ROWS rows and all SK_GROUPS column groups are present (straight-line code without predicates).
-template <bool FAST, bool FULL>
-__device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consumed, uint32_t& issued, uint32_t total_seq,
-                                         const float (&vl)[SK_GROUPS][4], L2Acc (&col)[SK_GROUPS][4]) {
+template <bool FULL>
+__device__ __forceinline__ void sk_stage_exact(const SkCtx& c, int idx, SkRing& rg, const float (&vl)[SK_GROUPS][4],
+                                               L2Acc (&col)[SK_GROUPS][4]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = c.N, n4 = c.n4;
-  const uint32_t seq = consumed;
-  const int buf = seq % SK_STAGES;
-  const int r_base = c.row0 + st * SK_ROWS;
+  const int pp = rg.seq & 1;
+  const int r_base = c.row0 + idx * SK_ROWS;
   const int nr = FULL ? SK_ROWS : min(SK_ROWS, c.row1 - r_base);
-  const float* sb = c.stage_buf + (size_t)buf * SK_ROWS * N;
-  float mrow[SK_ROWS];
-#pragma unroll
-  for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FAST && (FULL || k < nr)) ? (c.c_nu - c.uold_s[st * SK_ROWS + k]) : 0.f;   // previous u
-  sk_mbar_wait(&c.full[buf], (seq / SK_STAGES) & 1);
+  const float* sb = c.stage_buf + (size_t)rg.buf * SK_ROWS * N;
+  sk_wait_full(c, rg);
   float x[SK_ROWS][SK_GROUPS][4];
 #pragma unroll
   for (int k = 0; k < SK_ROWS; ++k)
@@ -510,114 +550,224 @@ __device__ __forceinline__ void sk_stage(const SkCtx& c, int st, uint32_t& consu
       float4 t = (FULL || (k < nr && gi < n4)) ? reinterpret_cast<const float4*>(sb + (size_t)k * N)[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
       x[k][g][0] = t.x * LOG2E; x[k][g][1] = t.y * LOG2E; x[k][g][2] = t.z * LOG2E; x[k][g][3] = t.w * LOG2E;
     }
-  // ---- row pass partials (old v) ----
 #pragma unroll
   for (int k = 0; k < SK_ROWS; ++k) {
     if (FULL || k < nr) {
-      if (FAST) {
-        // e_ij = 2^(x_ij + v_j - m_i) is kept in registers: the column pass needs no second exponential, because
-        // 2^(x_ij + u_i - m_j) = e_ij * 2^(u_i + m_i - c_mu)   (m_j = c_mu - v_j): a rank-1 rescaling of the same kernel matrix.
-        float s0 = 0.f, s1 = 0.f;
+      L2Acc a, a1; a.init(); a1.init();
 #pragma unroll
-        for (int g = 0; g < SK_GROUPS; ++g) {
-          if (FULL || g * SK_THREADS + tid < n4) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) x[k][g][cc] = sk_ex2(x[k][g][cc] + (vl[g][cc] - mrow[k]));
-            s0 += x[k][g][0] + x[k][g][1];
-            s1 += x[k][g][2] + x[k][g][3];
-          }
+      for (int g = 0; g < SK_GROUPS; ++g) {
+        if (FULL || g * SK_THREADS + tid < n4) {
+          a.add(x[k][g][0] + vl[g][0]); a1.add(x[k][g][1] + vl[g][1]); a.add(x[k][g][2] + vl[g][2]); a1.add(x[k][g][3] + vl[g][3]);
         }
-        float sm = warp_sum(s0 + s1);
-        if (lane == 0) c.part_s[st & 1][k][warp] = sm;
-      } else {
-        L2Acc a, a1; a.init(); a1.init();
-#pragma unroll
-        for (int g = 0; g < SK_GROUPS; ++g) {
-          if (FULL || g * SK_THREADS + tid < n4) {
-            a.add(x[k][g][0] + vl[g][0]); a1.add(x[k][g][1] + vl[g][1]); a.add(x[k][g][2] + vl[g][2]); a1.add(x[k][g][3] + vl[g][3]);
-          }
-        }
-        a.merge(a1.m, a1.s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-        if (lane == 0) { c.part_m[st & 1][k][warp] = a.m; c.part_s[st & 1][k][warp] = a.s; }
       }
+      a.merge(a1.m, a1.s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+      if (lane == 0) { c.part_m[pp][k][warp] = a.m; c.part_s[pp][k][warp] = a.s; }
     }
   }
   __syncthreads();              // partials published; every thread has its elements in registers -> the buffer is free
-  ++consumed;
-  if (tid == 0 && issued < total_seq) {   // refill the buffer just released (wraps into the next iteration: S never changes)
-    const int st_idx = issued % c.nstage_total, nbuf = issued % SK_STAGES;
-    const int r = c.row0 + st_idx * SK_ROWS;
-    const int nrr = min(SK_ROWS, c.row1 - r);
-    sk_mbar_expect(&c.full[nbuf], nrr * c.row_bytes);
-    for (int k = 0; k < nrr; ++k)
-      sk_bulk_load(c.stage_buf + ((size_t)nbuf * SK_ROWS + k) * N, c.S + (size_t)(r + k) * N, c.row_bytes, &c.full[nbuf]);
-    ++issued;
-  }
-  // ---- every warp finishes the row reduction itself (no second barrier), then the column pass from registers ----
+  if (tid == 0 && rg.seq + SK_STAGES < rg.total) sk_issue(c, rg.seq + SK_STAGES);
 #pragma unroll
   for (int k = 0; k < SK_ROWS; ++k) {
     if (FULL || k < nr) {
-      float ui;
-      if (FAST) {
-        float sm = warp_sum(c.part_s[st & 1][k][lane]) + sk_ex2(c.extra_row - mrow[k]);
-        if (!(sm > 0.f && sm < INFINITY) && tid == 0) atomicExch(c.flag, 1);
-        ui = c.norm - (mrow[k] + __log2f(sm)) * LN2;
-      } else {
-        L2Acc a;
-        a.m = c.part_m[st & 1][k][lane]; a.s = c.part_s[st & 1][k][lane];
+      L2Acc a; a.init();
+      if (lane < SK_WARPS) { a.m = c.part_m[pp][k][lane]; a.s = c.part_s[pp][k][lane]; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-        a.add(c.extra_row);
-        ui = c.norm - a.lse_ln();
-      }
+      for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+      a.add(c.extra_row);
+      const float ui = c.norm - a.lse_ln();
       if (tid == 0) c.u[r_base + k] = ui;
       const float ul = ui * LOG2E;
-      const float ak = FAST ? sk_ex2(ul + mrow[k] - c.c_mu) : 0.f;     // row factor of the rank-1 rescaling (fast mode)
 #pragma unroll
       for (int g = 0; g < SK_GROUPS; ++g) {
         if (FULL || g * SK_THREADS + tid < n4) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            if (FAST) col[g][cc].s = fmaf(x[k][g][cc], ak, col[g][cc].s);
-            else col[g][cc].add(x[k][g][cc] + ul);
-          }
+          for (int cc = 0; cc < 4; ++cc) col[g][cc].add(x[k][g][cc] + ul);
         }
       }
     }
   }
+  rg.advance();
 }
 
-// One iteration's pass over this CTA's band (row pass + column pass), templated on the arithmetic mode so that no
-// per-element branch survives in the inner loops.
-template <bool FAST>
-__device__ __forceinline__ void sk_band(const SkCtx& c, uint32_t& consumed, uint32_t& issued, uint32_t total_seq) {
+__device__ __forceinline__ void sk_band_exact(const SkCtx& c, SkRing& rg, const float4 (&vraw)[SK_GROUPS]) {
   const int tid = threadIdx.x;
   const int N = c.N, n4 = c.n4;
   float vl[SK_GROUPS][4];                                          // old v of my columns, log2 domain
-  L2Acc col[SK_GROUPS][4];                                         // exact: (max, sum); fast: (stabiliser m_j, sum)
+  L2Acc col[SK_GROUPS][4];
 #pragma unroll
   for (int g = 0; g < SK_GROUPS; ++g) {
-    const int gi = g * SK_THREADS + tid;
-    float4 t = (gi < n4) ? __ldcg(reinterpret_cast<const float4*>(c.v) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 t = vraw[g];
     vl[g][0] = t.x * LOG2E; vl[g][1] = t.y * LOG2E; vl[g][2] = t.z * LOG2E; vl[g][3] = t.w * LOG2E;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) { col[g][cc].init(); if (FAST) col[g][cc].m = c.c_mu - vl[g][cc]; }
+    for (int cc = 0; cc < 4; ++cc) col[g][cc].init();
   }
   const bool full_cols = n4 == SK_GROUPS * SK_THREADS;
-  for (int st = 0; st < c.nstage_total; ++st) {
-    if (full_cols && c.row0 + (st + 1) * SK_ROWS <= c.row1) sk_stage<FAST, true>(c, st, consumed, issued, total_seq, vl, col);
-    else sk_stage<FAST, false>(c, st, consumed, issued, total_seq, vl, col);
+  const bool rev = ((rg.seq / (uint32_t)c.nst) & 1u) != 0;
+#pragma unroll 1
+  for (int st = 0; st < c.nst; ++st) {
+    const int idx = rev ? c.nst - 1 - st : st;
+    if (full_cols && c.row0 + (idx + 1) * SK_ROWS <= c.row1) sk_stage_exact<true>(c, idx, rg, vl, col);
+    else sk_stage_exact<false>(c, idx, rg, vl, col);
   }
-  // ---- column partials of this CTA ----
 #pragma unroll
   for (int g = 0; g < SK_GROUPS; ++g) {
     const int gi = g * SK_THREADS + tid;
     if (gi < n4) {
-      if (!FAST) reinterpret_cast<float4*>(c.pm + (size_t)c.cta * N)[gi] = make_float4(col[g][0].m, col[g][1].m, col[g][2].m, col[g][3].m);
+      reinterpret_cast<float4*>(c.pm + (size_t)c.cta * N)[gi] = make_float4(col[g][0].m, col[g][1].m, col[g][2].m, col[g][3].m);
       reinterpret_cast<float4*>(c.ps + (size_t)c.cta * N)[gi] = make_float4(col[g][0].s, col[g][1].s, col[g][2].s, col[g][3].s);
     }
+  }
+}
+
+// ---- fast mode --------------------------------------------------------------------------------------------------------
+// Column pass of a stage (row block `idx`, stage number seq, fast-stage number fq) from the registers kept since its
+// phase A: cs_j += e_ij * a_i.  Every warp finishes the row sums itself as soon as all partials are published (mbarrier
+// bpart): a_i = 2^(u_i + m_i - c_mu) = kfac / rowsum_i, one reciprocal.  The stage's duty warp (round-robin) also writes u_i,
+// checks the sums and refills the shared-memory buffer the stage has released; nobody waits for it.
+template <bool FULL>
+__device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t seq, uint32_t fq, SkRing& rg,
+                                             const float (&e)[SK_ROWS][SK_GROUPS][4], float2 (&cs)[SK_GROUPS][2]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t pp = fq & 1u, slot = fq & 3u;
+  const int row = lane >> 4;
+  const bool valid = FULL || (c.row0 + idx * SK_ROWS + row < c.row1);
+  const float mr = valid ? (c.c_nu - c.uold_s[idx * SK_ROWS + row]) : 0.f;
+  const float ex = sk_ex2(c.extra_row - mr);                        // dustbin column term
+  sk_mbar_wait(&c.bpart[pp], (rg.bp_par >> pp) & 1u);               // all warps: partials published, buffer emptied
+  rg.bp_par ^= 1u << pp;
+  const float2 pr = *reinterpret_cast<const float2*>(&c.part_s[slot][row][(lane & 7) * 2]);
+  float t = pr.x + pr.y;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  const float sm = t + ex;
+  const float a = valid ? __fdividef(c.kfac, sm) : 0.f;
+  const float a0 = __shfl_sync(0xffffffffu, a, 0), a1 = __shfl_sync(0xffffffffu, a, 16);
+  const float2 a0v = make_float2(a0, a0), a1v = make_float2(a1, a1);
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    cs[g][0] = __ffma2_rn(make_float2(e[0][g][0], e[0][g][1]), a0v, cs[g][0]);
+    cs[g][1] = __ffma2_rn(make_float2(e[0][g][2], e[0][g][3]), a0v, cs[g][1]);
+  }
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    cs[g][0] = __ffma2_rn(make_float2(e[1][g][0], e[1][g][1]), a1v, cs[g][0]);
+    cs[g][1] = __ffma2_rn(make_float2(e[1][g][2], e[1][g][3]), a1v, cs[g][1]);
+  }
+  if (warp == (int)(fq & (SK_WARPS - 1))) {                         // duty: off everybody's critical path
+    if (lane == 0 && seq + SK_STAGES < rg.total) sk_issue(c, seq + SK_STAGES);
+    if ((lane & 15) == 0 && valid) {
+      if (!(sm > 0.f && sm < INFINITY)) atomicExch(c.flag, 1);
+      c.u[c.row0 + idx * SK_ROWS + row] = c.norm - (mr + __log2f(sm)) * LN2;
+    }
+  }
+}
+
+// One stage: phase A of row block `idx` (results in e_cur), then the column pass of the previous stage (from e_prev): a
+// warp only waits for the slowest warp of the PREVIOUS stage after finishing its own share of this one.
+// FULL = both rows exist and every thread owns SK_GROUPS complete float4 column groups (N == SK_MAXN).
+template <bool FULL, bool HAVE_PREV, bool PREV_FULL>
+__device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_prev, SkRing& rg,
+                                              const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2],
+                                              float (&e_cur)[SK_ROWS][SK_GROUPS][4], const float (&e_prev)[SK_ROWS][SK_GROUPS][4]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = c.N, n4 = c.n4;
+  // partial sums go to slot fq % 4: a warp may run a stage ahead of another one that has arrived for stage s+1 but not yet read
+  // the partials of stage s, so a slot is only rewritten four stages later (behind the wait on stage s+2's barrier)
+  const uint32_t pp = rg.fq & 1u, slot = rg.fq & 3u;
+  const int nr = FULL ? SK_ROWS : min(SK_ROWS, c.row1 - (c.row0 + idx * SK_ROWS));
+  const float* sb = c.stage_buf + (size_t)rg.buf * SK_ROWS * N;
+  float mrow[SK_ROWS], rsum[SK_ROWS];
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FULL || k < nr) ? (c.c_nu - c.uold_s[idx * SK_ROWS + k]) : 0.f;   // previous u
+  sk_wait_full(c, rg);
+  const float2 l2e = make_float2(LOG2E, LOG2E);
+#pragma unroll
+  for (int k = 0; k < SK_ROWS; ++k) {
+    float2 s2 = make_float2(0.f, 0.f);
+    const float2 nm = make_float2(-mrow[k], -mrow[k]);
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g) {
+      const int gi = g * SK_THREADS + tid;
+      if (FULL || (k < nr && gi < n4)) {
+        const float4 t = reinterpret_cast<const float4*>(sb + (size_t)k * N)[gi];
+        const float2 a01 = __ffma2_rn(make_float2(t.x, t.y), l2e, __fadd2_rn(vl[g][0], nm));
+        const float2 a23 = __ffma2_rn(make_float2(t.z, t.w), l2e, __fadd2_rn(vl[g][1], nm));
+        e_cur[k][g][0] = sk_ex2(a01.x); e_cur[k][g][1] = sk_ex2(a01.y);
+        e_cur[k][g][2] = sk_ex2(a23.x); e_cur[k][g][3] = sk_ex2(a23.y);
+        s2 = __fadd2_rn(s2, make_float2(e_cur[k][g][0], e_cur[k][g][1]));
+        s2 = __fadd2_rn(s2, make_float2(e_cur[k][g][2], e_cur[k][g][3]));
+      } else {
+        e_cur[k][g][0] = e_cur[k][g][1] = e_cur[k][g][2] = e_cur[k][g][3] = 0.f;
+      }
+    }
+    rsum[k] = s2.x + s2.y;
+  }
+  // transposed warp reduction of the two row sums: lanes 0-15 end up with row 0, lanes 16-31 with row 1
+  const bool hi = (lane & 16) != 0;
+  float keep = hi ? rsum[1] : rsum[0];
+  const float send = hi ? rsum[0] : rsum[1];
+  keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+  if ((lane & 15) == 0) c.part_s[slot][lane >> 4][warp] = keep;
+  __syncwarp();
+  if (lane == 0) sk_mbar_arrive(&c.bpart[pp]);                       // release: this warp's partials, and its reads of the buffer
+  if (HAVE_PREV) sk_col_accum<PREV_FULL>(c, idx_prev, rg.seq - 1, rg.fq - 1, rg, e_prev, cs);
+  rg.advance();
+  ++rg.fq;
+}
+
+__device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const float4 (&vraw)[SK_GROUPS]) {
+  const int tid = threadIdx.x;
+  const int N = c.N, n4 = c.n4, nst = c.nst;
+  float2 vl[SK_GROUPS][2];                                         // old v of my columns, log2 domain
+  float2 cs[SK_GROUPS][2];                                         // column sums relative to the stabiliser m_j = c_mu - v_j
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    const float4 t = vraw[g];
+    vl[g][0] = make_float2(t.x * LOG2E, t.y * LOG2E); vl[g][1] = make_float2(t.z * LOG2E, t.w * LOG2E);
+    cs[g][0] = cs[g][1] = make_float2(0.f, 0.f);
+  }
+  const bool rev = ((rg.seq / (uint32_t)nst) & 1u) != 0;
+  // everything but (possibly) the band's last row block is complete: the ragged block — the first stage of a backward
+  // pass, the last of a forward one — takes the predicated instantiation
+  const bool all_full = (n4 == SK_GROUPS * SK_THREADS) && (c.row0 + nst * SK_ROWS == c.row1);
+  const int ragged = all_full ? -1 : ((n4 == SK_GROUPS * SK_THREADS) ? nst - 1 : -2);   // -2: every stage is predicated
+  float eA[SK_ROWS][SK_GROUPS][4], eB[SK_ROWS][SK_GROUPS][4];      // registers rotate between the two (loop unrolled by 2)
+#define SK_IDX(st) (rev ? nst - 1 - (st) : (st))
+#define SK_ISFULL(idx) (ragged == -1 || (ragged >= 0 && (idx) != ragged))
+#define SK_STAGE(st, cur, prev)                                                                              \
+  {                                                                                                          \
+    const int i_ = SK_IDX(st), ip_ = SK_IDX((st) - 1);                                                       \
+    const bool f_ = SK_ISFULL(i_), fp_ = SK_ISFULL(ip_);                                                     \
+    if (f_ && fp_) sk_stage_fast<true, true, true>(c, i_, ip_, rg, vl, cs, cur, prev);                      \
+    else if (f_) sk_stage_fast<true, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                       \
+    else sk_stage_fast<false, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                              \
+  }
+  if (SK_ISFULL(SK_IDX(0))) sk_stage_fast<true, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
+  else sk_stage_fast<false, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
+  int st = 1;
+#pragma unroll 1
+  for (; st + 1 < nst; st += 2) {
+    SK_STAGE(st, eB, eA);
+    SK_STAGE(st + 1, eA, eB);
+  }
+  if (st < nst) {
+    SK_STAGE(st, eB, eA);
+    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eB, cs);
+  } else {
+    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eA, cs);
+  }
+#undef SK_STAGE
+#undef SK_ISFULL
+#undef SK_IDX
+  // ---- column partials of this CTA ----
+#pragma unroll
+  for (int g = 0; g < SK_GROUPS; ++g) {
+    const int gi = g * SK_THREADS + tid;
+    if (gi < n4) reinterpret_cast<float4*>(c.ps + (size_t)c.cta * N)[gi] = make_float4(cs[g][0].x, cs[g][0].y, cs[g][1].x, cs[g][1].y);
   }
 }
 
@@ -626,53 +776,75 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
                                                                        int* flag, int rows_per_cta, int allow_fast) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
-  __shared__ __align__(8) uint64_t full[SK_STAGES];
-  __shared__ float part_m[2][SK_ROWS][SK_THREADS / 32], part_s[2][SK_ROWS][SK_THREADS / 32];
-  __shared__ float red_m[SK_THREADS / 32], red_s[SK_THREADS / 32];
-  __shared__ float uold_s[SK_MAX_BAND];
-  cg::grid_group grid = cg::this_grid();
+  __shared__ __align__(8) uint64_t full[SK_STAGES], bpart[2];
+  __shared__ __align__(8) float part_m[2][SK_ROWS][SK_WARPS], part_s[4][SK_ROWS][SK_WARPS];
+  __shared__ float red_m[SK_WARPS], red_s[SK_WARPS];
+  __shared__ __align__(8) float uold_s[SK_MAX_BAND];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int row0 = min(M, cta * rows_per_cta), row1 = min(M, row0 + rows_per_cta);
-  const int nstage_total = (row1 - row0 + SK_ROWS - 1) / SK_ROWS;              // stages per iteration for this CTA
+  const int nst = (row1 - row0 + SK_ROWS - 1) / SK_ROWS;                       // stages per iteration for this CTA (>= 1)
   const float norm = -logf((float)M + (float)N);
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
   const float c_mu = fmaxf(norm, log_mu_last) * LOG2E, c_nu = fmaxf(norm, log_nu_last) * LOG2E;   // log2 of the largest marginals
-  const uint32_t row_bytes = (uint32_t)N * 4u;
   const int n4 = N >> 2;
 
   if (tid == 0) {
     for (int s = 0; s < SK_STAGES; ++s) sk_mbar_init(&full[s], 1);
+    for (int s = 0; s < 2; ++s) sk_mbar_init(&bpart[s], SK_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  auto issue = [&](int st_idx, int buf) {       // thread 0 only: load stage `st_idx` of this CTA's band into buffer `buf`
-    const int r = row0 + st_idx * SK_ROWS;
-    const int nr = min(SK_ROWS, row1 - r);
-    sk_mbar_expect(&full[buf], nr * row_bytes);
-    for (int k = 0; k < nr; ++k)
-      sk_bulk_load(stage_buf + ((size_t)buf * SK_ROWS + k) * N, S + (size_t)(r + k) * N, row_bytes, &full[buf]);
-  };
-  // the band is re-streamed every iteration (S never changes): stages are numbered consecutively across iterations
-  uint32_t total_seq = (uint32_t)iters * (uint32_t)nstage_total;
-  uint32_t issued = 0, consumed = 0;
-  if (tid == 0)
-    while (issued < total_seq && issued < SK_STAGES) { issue(issued % nstage_total, issued % SK_STAGES); ++issued; }
-  bool fast_ok = allow_fast != 0;
-
   SkCtx ctx;
-  ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
+  ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.bpart = bpart;
+  ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
   ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
   ctx.uold_s = uold_s;
-  ctx.nstage_total = nstage_total; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = row_bytes;
+  ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)N * 4u;
+  ctx.kfac = exp2f(norm * LOG2E - c_mu);                             // a_i = 2^(u_i + m_i - c_mu) = kfac / rowsum_i
+
+  // the band is re-streamed every iteration: stages are counted across iterations
+  SkRing rg;
+  rg.seq = 0; rg.buf = 0; rg.full_par = 0; rg.fq = 0; rg.bp_par = 0;
+  rg.total = (uint32_t)iters * (uint32_t)nst;
+  if (tid == 0)
+    for (uint32_t s = 0; s < rg.total && s < SK_STAGES; ++s) sk_issue(ctx, s);
+  bool fast_ok = allow_fast != 0;
+
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(flag) + 1;      // monotonic arrival counter of the grid barrier (zeroed by the host)
+  unsigned int gtarget = 0;
+  // Grid barrier: one release-add + relaxed polling per CTA.  Cumulativity through the two block barriers makes every
+  // thread's earlier writes visible to every thread of the grid afterwards (readers use ld.global.cg).
+  auto grid_barrier = [&]() {
+    __syncthreads();
+    gtarget += (unsigned int)G;
+    if (tid == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gbar) : "memory");
+      unsigned int seen;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory");
+      } while (seen < gtarget);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+  };
 
   for (int it = 0; it < iters; ++it) {
     const bool fast = fast_ok && it >= SK_EXACT_ITERS;
+    // all the loads of the prologue are in flight together: v of my columns, the dustbin term, the band's previous u
+    float4 vraw[SK_GROUPS];
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g) {
+      const int gi = g * SK_THREADS + tid;
+      vraw[g] = (gi < n4) ? __ldcg(reinterpret_cast<const float4*>(v) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     ctx.extra_row = (alpha + __ldcg(v + N)) * LOG2E;                  // dustbin column term of every row LSE (old v)
-    // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA; small)
+    for (int i = tid; i < row1 - row0; i += SK_THREADS) uold_s[i] = __ldcg(u + row0 + i) * LOG2E;
+    // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA: its band is the short one)
     if (cta == G - 1) {
       L2Acc a; a.init();
+#pragma unroll 4
       for (int j = tid; j <= N; j += SK_THREADS) a.add((alpha + __ldcg(v + j)) * LOG2E);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
@@ -680,80 +852,83 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       __syncthreads();
       if (tid == 0) {
         L2Acc t; t.init();
-        for (int w = 0; w < SK_THREADS / 32; ++w) t.merge(red_m[w], red_s[w]);
+        for (int w = 0; w < SK_WARPS; ++w) t.merge(red_m[w], red_s[w]);
         u[M] = log_mu_last - t.lse_ln();
       }
-      __syncthreads();
     }
-    // Each thread owns the same SK_GROUPS float4 column groups in BOTH passes: a stage's elements are read from shared memory
-    // once into registers, used for the row pass (old v, in registers for the whole iteration) and — after the block-wide row
-    // reduction gives u — again for the column pass.
-    for (int i = tid; i < row1 - row0; i += SK_THREADS) uold_s[i] = __ldcg(u + row0 + i) * LOG2E;
     __syncthreads();
-    if (fast) sk_band<true>(ctx, consumed, issued, total_seq);
-    else sk_band<false>(ctx, consumed, issued, total_seq);
-    grid.sync();
+    if (fast) sk_band_fast(ctx, rg, vraw);
+    else sk_band_exact(ctx, rg, vraw);
+    grid_barrier();
     // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
     {
       const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
-      // one warp per 2-column tile: lane = 2 * sub + col; each lane reduces the partials of CTAs c = sub, sub + 16, ...,
-      // then a 4-step shuffle over `sub`.  No shared memory, no block barrier, ~all warps of the grid busy.
-      const int sub = lane >> 1, cl = lane & 1;
-      for (int tile = cta * (SK_THREADS / 32) + warp; tile * 2 < N; tile += G * (SK_THREADS / 32)) {
-        const int j = tile * 2 + cl;
+      // one warp per 4-column tile: lane l sums the partials of CTAs l, l + 32, ... for all four columns (independent 16-byte
+      // loads), a butterfly over the lanes finishes the sums and lanes 0..3 each finalise one column.
+      for (int tile = cta * SK_WARPS + warp; tile < n4; tile += G * SK_WARPS) {
         if (fast) {
-          float sm = 0.f;
-          if (j < N) {
-#pragma unroll 4
-            for (int c = sub; c < G; c += 16) sm += __ldcg(ps + (size_t)c * N + j);
+          float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+          for (int c = lane; c < G; c += 32) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(ps + (size_t)c * N) + tile);
+            sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
           }
 #pragma unroll
-          for (int o = 2; o < 32; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-          if (sub == 0 && j < N) {
+          for (int o = 16; o > 0; o >>= 1) {
+            sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
+            sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
+          }
+          if (lane < 4) {
+            const int j = tile * 4 + lane;
+            float sj = lane == 0 ? sm.x : lane == 1 ? sm.y : lane == 2 ? sm.z : sm.w;
             const float mj = c_mu - __ldcg(v + j) * LOG2E;            // the stabiliser used above (old v)
-            sm += sk_ex2(extra_col - mj);
-            if (!(sm > 0.f && sm < INFINITY)) atomicExch(flag, 1);
-            v[j] = norm - (mj + __log2f(sm)) * LN2;
+            sj += sk_ex2(extra_col - mj);
+            if (!(sj > 0.f && sj < INFINITY)) atomicExch(flag, 1);
+            v[j] = norm - (mj + __log2f(sj)) * LN2;
           }
         } else {
+          // lane = 4 * sub + column: 8 lanes share a column
+          const int sub = lane >> 2, j = tile * 4 + (lane & 3);
           L2Acc a; a.init();
-          if (j < N) {
 #pragma unroll 2
-            for (int c = sub; c < G; c += 16) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
-          }
+          for (int c = sub; c < G; c += 8) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
 #pragma unroll
-          for (int o = 2; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-          if (sub == 0 && j < N) {
+          for (int o = 4; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+          if (sub == 0) {
             a.add(extra_col);
             v[j] = norm - a.lse_ln();
           }
         }
       }
-      if (cta == G - 1) {
+      if (cta == G - 1) {                                             // v[N] = log_nu_last - LSE_{i <= M}(alpha + u_i)
         L2Acc a; a.init();
+#pragma unroll 4
         for (int i = tid; i <= M; i += SK_THREADS) a.add((alpha + __ldcg(u + i)) * LOG2E);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
         if (lane == 0) { red_m[warp] = a.m; red_s[warp] = a.s; }
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
           L2Acc t; t.init();
-          for (int w = 0; w < SK_THREADS / 32; ++w) t.merge(red_m[w], red_s[w]);
-          v[N] = log_nu_last - t.lse_ln();
+          if (lane < SK_WARPS) { t.m = red_m[lane]; t.s = red_s[lane]; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t.merge(__shfl_xor_sync(0xffffffffu, t.m, o), __shfl_xor_sync(0xffffffffu, t.s, o));
+          if (lane == 0) v[N] = log_nu_last - t.lse_ln();
         }
       }
     }
-    grid.sync();
+    grid_barrier();
     if (fast_ok && __ldcg(flag) != 0) {
       // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode
       fast_ok = false;
       for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
       for (int i = cta * SK_THREADS + tid; i <= M; i += G * SK_THREADS) u[i] = 0.f;
-      total_seq = consumed + (uint32_t)iters * (uint32_t)nstage_total;
-      if (tid == 0)
-        while (issued < total_seq && issued - consumed < SK_STAGES) { issue(issued % nstage_total, issued % SK_STAGES); ++issued; }
+      const uint32_t old_total = rg.total;
+      rg.total = rg.seq + (uint32_t)iters * (uint32_t)nst;
+      if (tid == 0)      // stages below min(old_total, seq + SK_STAGES) are already in flight
+        for (uint32_t s = min(old_total, rg.seq + SK_STAGES); s < rg.total && s < rg.seq + SK_STAGES; ++s) sk_issue(ctx, s);
       it = -1;
-      grid.sync();
+      grid_barrier();
     }
   }
 }
@@ -789,7 +964,7 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);
   float* pm = w.pm; float* ps = w.ps;
   int* flag = w.pi;
-  cudaMemsetAsync(flag, 0, sizeof(int), st);
+  cudaMemsetAsync(flag, 0, 2 * sizeof(int), st);   // [0] fast-mode trip flag, [1] grid-barrier arrival counter
   int allow_fast = g_sinkhorn_fast;
   void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
                   (void*)&flag, (void*)&rpc, (void*)&allow_fast};

@@ -16,6 +16,8 @@ __global__ void k(float* out, int iters) {
       if (MODE == 2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
       if (MODE == 3) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
       if (MODE == 4) asm volatile("ex2.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (MODE == 5 && (i & 1) == 0) { float2 t = __ffma2_rn(make_float2(a[i], a[i + 1]), make_float2(a[i], a[i + 1]), make_float2(a[i + 1], a[i])); a[i] = t.x; a[i + 1] = t.y; }
+      if (MODE == 6) { if (i < 6) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(a[i])); else asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); }
     }
   }
   float s = 0; for (int i = 0; i < 8; ++i) s += a[i] + __uint_as_float(h[i]);
@@ -43,5 +45,7 @@ int main() {
   run<2>("ex2.approx.ftz.f16x2", 2);
   run<3>("lg2.approx.ftz.f32", 1);
   run<1>("fma.rn.f32", 1);
+  run<5>("fma.rn.f32x2 (FFMA2)", 1);
+  run<6>("6 FFMA + 2 EX2 interleaved", 1);
   return 0;
 }

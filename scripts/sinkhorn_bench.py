@@ -1,0 +1,25 @@
+"""Fused Sinkhorn at cfg2 size (8192^2, 100 iterations): us/iteration with CUDA events (not under a profiler)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from icepy4d_b200 import ops
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+S = torch.randn(N, N, device="cuda") * 3
+ws = ops.AssignWorkspace(N, N, S.device)
+for mode in (0, 2):
+    ops.set_sinkhorn_mode(mode)
+    for _ in range(2):
+        ops.sinkhorn(S, 1.0, iters, ws)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        ops.sinkhorn(S, 1.0, iters, ws)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"mode {mode}: {ms:.3f} ms / {iters} iterations = {ms / iters * 1e3:.2f} us/iter, "
+          f"{2 * N * N * 4 * iters / ms / 1e6:.0f} GB/s algorithmic, {N * N * 4 * iters / ms / 1e6:.0f} GB/s single-read")
+ops.set_sinkhorn_mode(0)

@@ -196,6 +196,51 @@ def _sinkhorn_case(ops, M, N, iters):
     assert torch.allclose(s0, rs0, atol=1e-3) and torch.allclose(s1, rs1, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,iters", [(8192, 8192, 12), (8191, 8188, 7), (4100, 8192, 9), (3000, 2048, 11)])
+def test_sinkhorn_fused_vs_two_pass_large(ops, M, N, iters):
+    """Full cfg2 size (and ragged bands / partial column groups): the fused persistent kernel (boustrophedon bands,
+    mbarrier-decoupled warps, a-priori stabilisers) against the plain two-pass row/column kernels on the same matrix."""
+    gen = torch.Generator().manual_seed(M * 7 + N)
+    S = (torch.randn(M, N, generator=gen) * 3).cuda()
+    idx = torch.arange(0, min(M, N), 2)
+    S[idx, (idx * 7) % N] += 25.0
+    ops.set_sinkhorn_mode(1)
+    try:
+        u1, v1 = ops.sinkhorn(S, 1.0, iters)
+        m1 = [t.clone() for t in ops.sg_assign(S, 1.0, iters, 0.2)]
+    finally:
+        ops.set_sinkhorn_mode(0)
+    for mode in (0, 2):
+        ops.set_sinkhorn_mode(mode)
+        try:
+            u0, v0 = ops.sinkhorn(S, 1.0, iters)
+            m0 = ops.sg_assign(S, 1.0, iters, 0.2)
+        finally:
+            ops.set_sinkhorn_mode(0)
+        assert torch.isfinite(u0).all() and torch.isfinite(v0).all()
+        assert float((u0 - u1).abs().max()) < 2e-3 and float((v0 - v1).abs().max()) < 2e-3, mode
+        assert torch.equal(m0[0], m1[0]) and torch.equal(m0[1], m1[1]), mode
+        assert torch.allclose(m0[2], m1[2], atol=1e-3)
+
+
+def test_sinkhorn_fast_mode_restart(ops):
+    """Potentials that jump by hundreds of nats between iterations underflow the a-priori stabilisers: the fused kernel
+    must notice, restart in exact mode on the device and still agree with the two-pass kernels."""
+    M, N, iters = 600, 1024, 8
+    gen = torch.Generator().manual_seed(5)
+    S = (torch.randn(M, N, generator=gen) * 60).cuda()
+    S[::3] -= 400.0
+    S[:, ::5] += 300.0
+    ops.set_sinkhorn_mode(1)
+    try:
+        u1, v1 = ops.sinkhorn(S, 1.0, iters)
+    finally:
+        ops.set_sinkhorn_mode(0)
+    u0, v0 = ops.sinkhorn(S, 1.0, iters)
+    assert torch.isfinite(u0).all() and torch.isfinite(v0).all()
+    assert float((u0 - u1).abs().max()) < 5e-2 and float((v0 - v1).abs().max()) < 5e-2
+
+
 @pytest.mark.parametrize("M,N", [(3, 5), (256, 200), (700, 513)])
 def test_lg_assign(ops, M, N):
     gen = torch.Generator().manual_seed(M * 5 + N)
