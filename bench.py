@@ -150,8 +150,9 @@ def _dominant_kernel_roofline(precision: str, peaks):
     """Times the fused persistent Sinkhorn kernel (the HBM-bound kernel the 100-iteration optimal transport lives in: 600
     iterations over 8192x8192 f32 score matrices per epoch) with CUDA events on the launch stream.
     Algorithmic bytes per iteration = 2 * M * N * 4 (one read of the matrix per LSE pass, two passes per
-    iteration).  The kernel fuses both passes over one staged read, so its measured DRAM traffic (ncu, profiles/) is
-    M * N * 4 per iteration and `frac` can exceed 1 against the copy-bandwidth peak."""
+    iteration).  The kernel fuses both passes over one staged read and walks its row bands boustrophedon so that part of
+    every pass is served by L2: its measured DRAM traffic (ncu, profiles/r1_ncu_sinkhorn_v11.txt) is 193 MB per iteration
+    (0.72 * M * N * 4) and `frac` can exceed 1 against the copy-bandwidth peak."""
     from icepy4d_b200 import ops
 
     M = N = KP
@@ -172,12 +173,13 @@ def _dominant_kernel_roofline(precision: str, peaks):
     bytes_launch = 2.0 * M * N * 4 * iters
     gbs = bytes_launch / (ms_launch * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": float(M) * N * 4 * iters + 2.0 * 147 * N * 4 * iters,
+            "traffic": (193.1e6 + 6.6e6) * iters,
             "kernel": "sinkhorn_fused_kernel (100 iterations, 8192x8192 f32, one launch)", "ms_per_launch": ms_launch,
             "us_per_iteration": ms_launch * 1e3 / iters, "peak_source": peaks["source"],
             "algorithmic_bytes_per_launch": bytes_launch,
-            "frac_of_actual_traffic": (float(M) * N * 4 * iters / (ms_launch * 1e-3) / 1e9) / peaks["hbm_gbs"],
-            "note": "traffic = one HBM read of the matrix per iteration (ncu dram__bytes_read 269 MB/iter, profiles/) + column partials"}
+            "frac_of_actual_traffic": ((193.1e6 + 6.6e6) * iters / (ms_launch * 1e-3) / 1e9) / peaks["hbm_gbs"],
+            "note": "traffic = ncu dram__bytes_read 193.1 MB + dram__bytes_write 6.6 MB per iteration (profiles/r1_ncu_sinkhorn_v11.txt): "
+                    "one staged read of the matrix per iteration, 23 % of it served by L2 (boustrophedon bands)"}
 
 
 def run_ours(args):

@@ -424,8 +424,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
 //           mode, on the device, without host involvement.
 // Everything is kept in the log2 domain.  HBM traffic per iteration <= M*N*4 bytes (algorithmic count of SURVEY.md §8d: 2*M*N*4).
 // ====================================================================================================================
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include <stdlib.h>
 
 #define SK_THREADS 512
 #define SK_WARPS (SK_THREADS / 32)
@@ -433,8 +432,9 @@ namespace cg = cooperative_groups;
 #define SK_STAGES 3
 #define SK_MAXN 8192
 #define SK_GROUPS (SK_MAXN / 4 / SK_THREADS)   // float4 column groups per thread = 4
-#define SK_EXACT_ITERS 2
+#define SK_EXACT_ITERS 1
 #define SK_MAX_BAND 1024            // rows per CTA the previous-u staging buffer can hold
+#define SK_KEEP_PCT_DEFAULT 0
 
 __device__ __forceinline__ float sk_ex2(float x) {
   float y;
@@ -480,9 +480,10 @@ __device__ __forceinline__ void sk_mbar_wait(uint64_t* b, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
-__device__ __forceinline__ void sk_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+__device__ __forceinline__ void sk_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)),
+                 "l"(policy)
                : "memory");
 }
 
@@ -490,7 +491,7 @@ struct SkCtx {
   const float* S; float* stage_buf; uint64_t* full; uint64_t* bpart;
   float (*part_m)[SK_ROWS][SK_WARPS]; float (*part_s)[SK_ROWS][SK_WARPS];
   float* u; const float* v; float* pm; float* ps; int* flag;
-  int M, N, n4, row0, row1, nst, cta;
+  int M, N, n4, row0, row1, nst, cta, keep_rows;
   float norm, c_mu, c_nu, extra_row, kfac;
   const float* uold_s;   // previous-iteration u of this CTA's band, pre-scaled by log2(e) (shared memory)
   uint32_t row_bytes;
@@ -519,9 +520,13 @@ __device__ __forceinline__ void sk_issue(const SkCtx& c, uint32_t seq) {
   const int buf = seq % SK_STAGES;
   const int r = c.row0 + sk_idx(seq, c.nst) * SK_ROWS;
   const int nr = min(SK_ROWS, c.row1 - r);
+  // the first `keep_rows` rows of the band are asked to stay in L2 (evict_last), the rest to stream through (evict_first)
+  uint64_t policy;
+  if (r - c.row0 < c.keep_rows) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   sk_mbar_expect(&c.full[buf], nr * c.row_bytes);
   for (int k = 0; k < nr; ++k)
-    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.N, c.S + (size_t)(r + k) * c.N, c.row_bytes, &c.full[buf]);
+    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.N, c.S + (size_t)(r + k) * c.N, c.row_bytes, &c.full[buf], policy);
 }
 __device__ __forceinline__ void sk_wait_full(const SkCtx& c, SkRing& rg) {
   sk_mbar_wait(&c.full[rg.buf], (rg.full_par >> rg.buf) & 1u);
@@ -773,7 +778,7 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
 
 __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, float alpha,
                                                                        int iters, float* u, float* v, float* pm, float* ps,
-                                                                       int* flag, int rows_per_cta, int allow_fast) {
+                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
   __shared__ __align__(8) uint64_t full[SK_STAGES], bpart[2];
@@ -802,6 +807,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
   ctx.uold_s = uold_s;
   ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)N * 4u;
+  ctx.keep_rows = (row1 - row0) * keep_pct / 100;
   ctx.kfac = exp2f(norm * LOG2E - c_mu);                             // a_i = 2^(u_i + m_i - c_mu) = kfac / rowsum_i
 
   // the band is re-streamed every iteration: stages are counted across iterations
@@ -966,8 +972,14 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   int* flag = w.pi;
   cudaMemsetAsync(flag, 0, 2 * sizeof(int), st);   // [0] fast-mode trip flag, [1] grid-barrier arrival counter
   int allow_fast = g_sinkhorn_fast;
+  static int keep_pct = -1;      // share of every band pinned in L2 with evict_last (I4D_SK_KEEP_PCT overrides, for experiments)
+  if (keep_pct < 0) {
+    const char* e = getenv("I4D_SK_KEEP_PCT");
+    keep_pct = e ? atoi(e) : SK_KEEP_PCT_DEFAULT;
+    if (keep_pct < 0 || keep_pct > 100) keep_pct = SK_KEEP_PCT_DEFAULT;
+  }
   void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
-                  (void*)&flag, (void*)&rpc, (void*)&allow_fast};
+                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;

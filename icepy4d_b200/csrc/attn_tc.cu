@@ -51,6 +51,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -203,9 +208,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
           if (32 + i >= kvalid) v1[i] = 0xff800000u;
         }
       }
-      float mx = -INFINITY;
+      // 3-input max (FMNMX3): 32 instructions for the 64 values, four independent chains
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+      for (int i = 0; i < 32; ++i) mxa[i & 3] = fmax3(mxa[i & 3], __uint_as_float(v0[i]), __uint_as_float(v1[i]));
+      float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       xch[j & 1][hf][q] = mx;
       named_bar_sync(1 + quarter, 64);                                      // the two warps that share this lane quarter
       mx = fmaxf(mx, xch[j & 1][hf ^ 1][q]);
@@ -238,8 +245,9 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
         }
       }
       // p = exp2(s * c - m_run); f32 row sum; bf16 pack; swizzled store (8 chunks of 16 B = my K-half row)
-      float rs = 0.f;
-      const float nm = -m_run;
+      // packed f32x2 arithmetic (FFMA2 / FADD2): one issue slot per two elements for the scaling and the row sum
+      float2 rs2 = make_float2(0.f, 0.f);
+      const float2 nm2 = make_float2(-m_run, -m_run), sc2 = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         uint32_t pk[4];
@@ -248,16 +256,16 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
           const int i = t * 8 + e * 2;
           const uint32_t ra = (i < 32) ? v0[i & 31] : v1[i & 31];
           const uint32_t rb = (i + 1 < 32) ? v0[(i + 1) & 31] : v1[(i + 1) & 31];
-          const float a = ex2_approx(fmaf(__uint_as_float(ra), p.scale_log2, nm));
-          const float b = ex2_approx(fmaf(__uint_as_float(rb), p.scale_log2, nm));
-          rs += a + b;
-          __nv_bfloat162 pr2 = __floats2bfloat162_rn(a, b);
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(ra), __uint_as_float(rb)), sc2, nm2);
+          const float2 ab = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          rs2 = __fadd2_rn(rs2, ab);
+          __nv_bfloat162 pr2 = __floats2bfloat162_rn(ab.x, ab.y);
           pk[e] = *reinterpret_cast<uint32_t*>(&pr2);
         }
         const uint32_t addr = prow + ((((uint32_t)t) ^ rsw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       }
-      l_part += rs;
+      l_part += rs2.x + rs2.y;
       tc::tcgen05_fence_before();
       tc::fence_proxy_async_smem();                                         // make P_j visible to the tensor-core proxy
       tc::mbar_arrive(&p_full);

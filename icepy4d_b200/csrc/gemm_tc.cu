@@ -1,11 +1,17 @@
 // tcgen05 / TMA GEMM on sm_100a:  C[M,N] = alpha * A[M,K] * W[N,K]^T + bias[N]  (+ReLU) (+R[M,N] f32),
 // bf16 operands (both K-major), f32 accumulation in TMEM, outputs f32 and/or bf16 from one epilogue.
 //
-// One 128 x 128 output tile per CTA.  warp 0 / lane 0: TMA producer (A and W tiles of 128 x 64 bf16 = one 128-byte
-// swizzle row per matrix row) through a 3-stage mbarrier ring (3 stages); warp 1 / lane 0: issues tcgen05.mma (M128 N128 K16, four
-// per stage) and commits each stage back to the producer; all four warps then read the accumulator with tcgen05.ld
-// (warp w owns TMEM lanes 32w..32w+31 = output rows) and run the fused epilogue.  Two CTAs fit per SM (2 x 97 KB
-// smem, 2 x 128 TMEM columns), so one CTA's epilogue overlaps the other's main loop.
+// Persistent, warp-specialised: one CTA per SM walks 128 x 128 output tiles (n fastest, so neighbouring CTAs share A rows in L2).
+//   warp 0      TMA producer: A and W tiles of 128 x 64 bf16 (one 128-byte swizzle row per matrix row) through a 4-stage
+//               mbarrier ring; it runs ahead across tile boundaries
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma M128 N128 K16, four per stage, into one of TWO TMEM accumulators,
+//               so the main loop of tile i+1 overlaps the epilogue of tile i
+//   warps 2..5  epilogue, thread = output row: tcgen05.ld 32 columns at a time -> alpha, bias (staged in shared memory), ReLU,
+//               + residual (R chunk brought in by TMA) -> results staged in 128B-swizzled shared memory and written with
+//               TMA stores (full 128-byte lines; rows/columns beyond M/N are clipped by the tensor map), double buffered
+//               so the store of chunk c overlaps the arithmetic of chunk c+1.
+// The previous version (one tile per CTA, each thread storing its own row with 16-byte st.global) spent its time in setup
+// latency and 12-wavefront stores: 21-38 us per SuperGlue layer GEMM (profiles/).
 //
 // Reference behaviour replaced: the Conv1d(k=1)/Linear layers of thirdparty/SuperGlue/models/superglue.py:51-61,
 // 100-128, 276-280 and thirdparty/LightGlue/lightglue/lightglue.py:133-216, 253-287 (cuBLAS sgemm via torch there).
@@ -16,141 +22,199 @@
 #define GT_BM 128
 #define GT_BN 128
 #define GT_BK 64
-#define GT_STAGES 3
-#define GT_STAGE_BYTES ((GT_BM + GT_BN) * GT_BK * 2)
-#define GT_SMEM_BYTES (GT_STAGES * GT_STAGE_BYTES + 1024)
+#define GT_STAGES 4
+#define GT_THREADS 192
+#define GT_STAGE_BYTES ((GT_BM + GT_BN) * GT_BK * 2)          // 32 KB
+#define GT_CHUNK_BYTES (GT_BM * 128)                            // 16 KB: 128 rows x 128 B (32 f32 or 64 bf16 columns)
+#define GT_OFF_C16 (GT_STAGES * GT_STAGE_BYTES)                 // 2 boxes of 128 rows x 64 bf16
+#define GT_OFF_C32 (GT_OFF_C16 + 2 * GT_CHUNK_BYTES)            // 2 buffers of 128 rows x 32 f32
+#define GT_OFF_R (GT_OFF_C32 + 2 * GT_CHUNK_BYTES)              // 2 buffers of 128 rows x 32 f32
+#define GT_OFF_BIAS (GT_OFF_R + 2 * GT_CHUNK_BYTES)             // 2 x 128 f32
+#define GT_SMEM_BYTES (GT_OFF_BIAS + 2 * GT_BN * 4)   // the dynamic segment is 1024-byte aligned (extern __align__(1024)): no slack needed
 
 struct GemmTcParams {
   int M, N, K;
   float alpha;
   const float* bias;
-  const float* R; int ldr;
-  float* C32; int ldc32;
-  __nv_bfloat16* C16; int ldc16;
-  int relu;
+  int has_r, has_c32, has_c16, relu;
 };
 
-__global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmW, GemmTcParams p) {
+__device__ __forceinline__ void gt_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void gt_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmW,
+                                                                const __grid_constant__ CUtensorMap tmR,
+                                                                const __grid_constant__ CUtensorMap tmC32,
+                                                                const __grid_constant__ CUtensorMap tmC16, GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[GT_STAGES], empty_bar[GT_STAGES], accum_bar;
+  __shared__ __align__(8) uint64_t full_bar[GT_STAGES], empty_bar[GT_STAGES], acc_full[2], acc_empty[2], r_full[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
   const int kblocks = p.K / GT_BK;
+  const int tiles_n = (p.N + GT_BN - 1) / GT_BN, tiles_m = (p.M + GT_BM - 1) / GT_BM;
+  const int n_tiles = tiles_n * tiles_m;
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
+    if (p.has_r) tc::prefetch_tmap(&tmR);
+    if (p.has_c32) tc::prefetch_tmap(&tmC32);
+    if (p.has_c16) tc::prefetch_tmap(&tmC16);
     for (int s = 0; s < GT_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&accum_bar, 1);
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 4); tc::mbar_init(&r_full[b], 1); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, GT_BN);
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 2 * GT_BN);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
   if (warp == 0) {
+    // ------------------------------------------------ TMA producer
     if (tc::elect_one()) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % GT_STAGES;
-        const uint32_t ph = (kb / GT_STAGES) & 1;
-        tc::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * GT_STAGE_BYTES;
-        uint8_t* sb = sa + GT_BM * GT_BK * 2;
-        tc::mbar_arrive_expect_tx(&full_bar[s], GT_STAGE_BYTES);
-        tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * GT_BK, m0);
-        tc::tma_load_2d(sb, &tmW, &full_bar[s], kb * GT_BK, n0);
+      uint32_t kc = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+          const int s = kc % GT_STAGES;
+          tc::mbar_wait(&empty_bar[s], ((kc / GT_STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * GT_STAGE_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[s], GT_STAGE_BYTES);
+          tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * GT_BK, m0);
+          tc::tma_load_2d(sa + GT_BM * GT_BK * 2, &tmW, &full_bar[s], kb * GT_BK, n0);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(GT_BM, GT_BN, 0, 0, 1);
       constexpr uint32_t hi = tc::desc_hi_sw128(1024);
       const uint32_t d0 = tc::desc_lo_sw128(tc::smem_u32(smem));
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % GT_STAGES;
-        const uint32_t ph = (kb / GT_STAGES) & 1;
-        tc::mbar_wait(&full_bar[s], ph);
+      uint32_t kc = 0, i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const uint32_t b = i & 1;
+        tc::mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
         tc::tcgen05_fence_after();
-        const uint32_t da = d0 + (uint32_t)(s * (GT_STAGE_BYTES >> 4)), db = da + ((GT_BM * GT_BK * 2) >> 4);
+        const uint32_t acc = tmem_d + b * GT_BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+          const int s = kc % GT_STAGES;
+          tc::mbar_wait(&full_bar[s], (kc / GT_STAGES) & 1);
+          tc::tcgen05_fence_after();
+          const uint32_t da = d0 + (uint32_t)(s * (GT_STAGE_BYTES >> 4)), db = da + ((GT_BM * GT_BK * 2) >> 4);
 #pragma unroll
-        for (int k = 0; k < GT_BK / 16; ++k) tc::umma_f16_parts(tmem_d, da + k * 2, hi, db + k * 2, hi, idesc, (kb | k) ? 1u : 0u);
-        tc::umma_commit(&empty_bar[s]);       // smem stage reusable once these MMAs retire
+          for (int k = 0; k < GT_BK / 16; ++k) tc::umma_f16_parts(acc, da + k * 2, hi, db + k * 2, hi, idesc, (kb | k) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);       // smem stage reusable once these MMAs retire
+        }
+        tc::umma_commit(&acc_full[b]);          // accumulator complete
       }
-      tc::umma_commit(&accum_bar);            // accumulator complete
     }
     __syncwarp();
-  }
-
-  // ---- epilogue: all 4 warps ----
-  tc::mbar_wait(&accum_bar, 0);
-  tc::tcgen05_fence_after();
-  const int row = m0 + warp * 32 + lane;
-  const bool row_ok = row < p.M;
+  } else {
+    // ------------------------------------------------ epilogue: 4 warps, thread = output row of the tile
+    const int e = threadIdx.x - 64;                                  // 0..127
+    const int q = warp & 3;                                          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                                   // row of the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    uint8_t* sC16 = smem + GT_OFF_C16;
+    uint8_t* sC32 = smem + GT_OFF_C32;
+    uint8_t* sR = smem + GT_OFF_R;
+    float* sBias = reinterpret_cast<float*>(smem + GT_OFF_BIAS);
+    const bool leader = (e == 0);
+    uint32_t g = 0, i = 0;                                           // g: 32-column chunks consumed so far (all tiles)
+    // R chunk `gc` (counted over all of this CTA's tiles) -> buffer gc & 1
+    auto issue_r = [&](uint32_t gc) {
+      const uint32_t ti = gc >> 2, c = gc & 3;
+      const long long t = (long long)blockIdx.x + (long long)ti * gridDim.x;
+      if (t >= n_tiles) return;
+      const int m0 = (int)(t / tiles_n) * GT_BM, n0 = (int)(t % tiles_n) * GT_BN;
+      tc::mbar_arrive_expect_tx(&r_full[gc & 1], GT_CHUNK_BYTES);
+      tc::tma_load_2d(sR + (gc & 1) * GT_CHUNK_BYTES, &tmR, &r_full[gc & 1], n0 + (int)c * 32, m0);
+    };
+    if (leader && p.has_r) { issue_r(0); issue_r(1); }
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
+      const uint32_t b = i & 1;
+      float* bs = sBias + b * GT_BN;
+      bs[e] = p.bias ? __ldg(p.bias + min(n0 + e, p.N - 1)) : 0.f;
+      gt_epi_bar();                                                  // bias staged (its previous user, tile i-2, is long done)
+      tc::mbar_wait(&acc_full[b], (i >> 1) & 1);
+      tc::tcgen05_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < GT_BN / 32; ++c) {
-    uint32_t v[32];
-    tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c * 32, v);
-    tc::tmem_ld_wait();
-    const int nb = n0 + c * 32;
-    if (row_ok && nb < p.N) {
-      float f[32];
+      for (int c = 0; c < GT_BN / 32; ++c, ++g) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_d + lane_off + b * GT_BN + c * 32, v);
+        tc::tmem_ld_wait();
+        if (c == GT_BN / 32 - 1) {                                   // accumulator drained: hand it back to the MMA warp
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+        }
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = p.alpha * __uint_as_float(v[j]);
-        if (p.bias) x += __ldg(p.bias + min(nb + j, p.N - 1));
-        if (p.relu) x = fmaxf(x, 0.f);
-        f[j] = x;
-      }
-      const bool full = nb + 32 <= p.N;
-      if (p.R) {
-        const float* r = p.R + (size_t)row * p.ldr + nb;
-        if (full) {
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bs + c * 32 + j);
+          f[j] = fmaf(p.alpha, __uint_as_float(v[j]), bb.x); f[j + 1] = fmaf(p.alpha, __uint_as_float(v[j + 1]), bb.y);
+          f[j + 2] = fmaf(p.alpha, __uint_as_float(v[j + 2]), bb.z); f[j + 3] = fmaf(p.alpha, __uint_as_float(v[j + 3]), bb.w);
+        }
+        if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 t = *reinterpret_cast<const float4*>(r + j);
-            f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.has_r) {
+          tc::mbar_wait(&r_full[g & 1], (g >> 1) & 1);
+          const uint8_t* rb = sR + (g & 1) * GT_CHUNK_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rb + ((((uint32_t)j) ^ rsw) << 4));
+            f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
           }
-        } else {
-          for (int j = 0; j < 32 && nb + j < p.N; ++j) f[j] += r[j];
         }
-      }
-      if (p.C32) {
-        float* o = p.C32 + (size_t)row * p.ldc32 + nb;
-        if (full) {
+        // staging buffers about to be written were handed to TMA stores at least one chunk ago: the leader waited for those
+        // stores to finish reading before the previous barrier
+        if (p.has_c32) {
+          uint8_t* cb = sC32 + (g & 1) * GT_CHUNK_BYTES + row * 128;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && nb + j < p.N; ++j) o[j] = f[j];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(cb + ((((uint32_t)j) ^ rsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
-      }
-      if (p.C16) {
-        __nv_bfloat16* o = p.C16 + (size_t)row * p.ldc16 + nb;
-        if (full) {
+        if (p.has_c16) {
+          uint8_t* hb = sC16 + (c >> 1) * GT_CHUNK_BYTES + row * 128;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(f[j], f[j + 1]), b = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 c2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), d = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), b2 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 c2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), d = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
             uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+            pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
             pk.z = *reinterpret_cast<uint32_t*>(&c2); pk.w = *reinterpret_cast<uint32_t*>(&d);
-            *reinterpret_cast<uint4*>(o + j) = pk;
+            *reinterpret_cast<uint4*>(hb + ((((uint32_t)((c & 1) * 4 + j)) ^ rsw) << 4)) = pk;
           }
-        } else {
-          for (int j = 0; j < 32 && nb + j < p.N; ++j) o[j] = __float2bfloat16_rn(f[j]);
+        }
+        tc::fence_proxy_async_smem();                                // my staged results -> visible to the TMA engine
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores issued one chunk ago have read their buffers
+        gt_epi_bar();
+        if (leader) {
+          if (p.has_c32) gt_tma_store_2d(&tmC32, sC32 + (g & 1) * GT_CHUNK_BYTES, n0 + c * 32, m0);
+          if (p.has_c16 && (c & 1)) gt_tma_store_2d(&tmC16, sC16 + (c >> 1) * GT_CHUNK_BYTES, n0 + (c >> 1) * 64, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (p.has_r) issue_r(g + 2);                               // every reader of this R buffer has passed the barrier
         }
       }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_d, GT_BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_d, 2 * GT_BN);
 }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----------------------
@@ -170,23 +234,31 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int i4d_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                          uint32_t box_cols) {
+static int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                        uint32_t box_cols, CUtensorMapDataType dt, uint32_t esize) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { i4d_set_error("cuTensorMapEncodeTiled entry point not available"); return I4D_ERR_CUDA; }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * esize) & 15)) {
     i4d_set_error("TMA needs a 16-byte aligned base and row pitch (base %p, ld %llu)", base, (unsigned long long)ld);
     return I4D_ERR_INVALID;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { i4d_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return I4D_ERR_CUDA; }
   return I4D_OK;
+}
+int i4d_make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                          uint32_t box_cols) {
+  return make_tmap_2d(out, base, rows, cols, ld, box_rows, box_cols, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+// row-major f32 matrix: box = box_cols x box_rows elements (box_cols * 4 bytes must be 128)
+static int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                            uint32_t box_cols) {
+  return make_tmap_2d(out, base, rows, cols, ld, box_rows, box_cols, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
 int i4d_make_tmap_hwc_bf16(CUtensorMap* out, const void* base, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w) {
@@ -217,17 +289,22 @@ extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
   I4D_CHECK_ARG(!C32 || ((ldc32 & 3) == 0 && (reinterpret_cast<uintptr_t>(C32) & 15) == 0), "C32 must be 16-byte aligned, ldc32 % 4 == 0");
   I4D_CHECK_ARG(!C16 || ((ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(C16) & 15) == 0), "C16 must be 16-byte aligned, ldc16 % 8 == 0");
   I4D_CHECK_ARG(!R || ((ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0), "R must be 16-byte aligned, ldr % 4 == 0");
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmR, tmC32, tmC16;
   if (int rc = i4d_make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GT_BM, GT_BK)) return rc;
   if (int rc = i4d_make_tmap_2d_bf16(&tmW, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GT_BN, GT_BK)) return rc;
+  tmR = tmA; tmC32 = tmA; tmC16 = tmA;                                // placeholders for the operands that are absent
+  if (R) { if (int rc = make_tmap_2d_f32(&tmR, R, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, GT_BM, 32)) return rc; }
+  if (C32) { if (int rc = make_tmap_2d_f32(&tmC32, C32, (uint64_t)M, (uint64_t)N, (uint64_t)ldc32, GT_BM, 32)) return rc; }
+  if (C16) { if (int rc = i4d_make_tmap_2d_bf16(&tmC16, C16, (uint64_t)M, (uint64_t)N, (uint64_t)ldc16, GT_BM, 64)) return rc; }
   static bool attr_set = false;
   if (!attr_set) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
     attr_set = true;
   }
-  GemmTcParams p{M, N, K, alpha, bias, R, ldr, C32, ldc32, reinterpret_cast<__nv_bfloat16*>(C16), ldc16, relu};
-  dim3 grid(i4d_cdiv(N, GT_BN), i4d_cdiv(M, GT_BM));
-  gemm_tc_kernel<<<grid, 128, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+  GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu};
+  const int n_tiles = i4d_cdiv(N, GT_BN) * i4d_cdiv(M, GT_BM);
+  const int grid = n_tiles < i4d_num_sms() ? n_tiles : i4d_num_sms();
+  gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }

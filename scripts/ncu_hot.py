@@ -8,7 +8,12 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 src, smp, ex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hi + 1:]:
+    if r and r[0] == "Address":      # next kernel of a multi-kernel report: keep the first one only
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 tot = sum(int(r[smp]) for r in data)
 print(f"total samples {tot}, instructions {sum(int(r[ex]) for r in data)}")
 agg = {}

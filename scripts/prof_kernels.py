@@ -17,3 +17,16 @@ if which in ("attn", "all"):
     for _ in range(2):
         ops_tc.attention_tc(qkv, [(0, N, 0, N), (N, N, N, N)], att, 0, 256, 512)
     torch.cuda.synchronize()
+if which in ("gemm", "all"):
+    nt = 2 * N
+    x = torch.randn(nt, 512, device="cuda").bfloat16()
+    x32 = torch.randn(nt, 256, device="cuda")
+    for (K, Nn, res) in ((256, 768, False), (512, 512, False), (512, 256, True)):
+        W = torch.randn(Nn, K, device="cuda").bfloat16(); b = torch.randn(Nn, device="cuda")
+        o = torch.empty(nt, Nn, device="cuda", dtype=torch.bfloat16)
+        for _ in range(2):
+            if res:
+                ops_tc.gemm_tc(x[:, :K], W, b, residual=x32, out32=x32, out16=o)
+            else:
+                ops_tc.gemm_tc(x[:, :K], W, b, out16=o, relu=True)
+    torch.cuda.synchronize()

@@ -40,6 +40,27 @@ def test_gemm_tc(tc, M, N, K):
     assert float(out[:, N:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,N,K", [(4000, 768, 256), (16384, 256, 512), (3333, 520, 128)])
+def test_gemm_tc_persistent_many_tiles(tc, M, N, K):
+    """More output tiles than SMs: every CTA walks several tiles (double-buffered TMEM accumulators, TMA-store epilogue), with
+    the residual read and written IN PLACE (the SuperGlue residual stream) and a bf16 shadow written into a column slice."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).bfloat16()
+    W = (torch.randn(N, K, generator=gen) / K ** 0.5).bfloat16()
+    b, R = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
+    ref = A.double() @ W.double().t() + b.double() + R.double()
+    x32 = R.cuda().clone()
+    wide = torch.zeros(M, N + 256, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc(A.cuda(), W.cuda(), b.cuda(), residual=x32, out32=x32, out16=wide[:, :N])
+    assert torch.allclose(x32.cpu().double(), ref, atol=2e-4 * K ** 0.5, rtol=1e-5)
+    assert torch.allclose(wide[:, :N].cpu().double(), ref, atol=0.05, rtol=1e-2)
+    assert float(wide[:, N:].abs().max()) == 0.0
+    # bf16-only output with ReLU, no residual (the QKV / first MLP layer form)
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc(A.cuda(), W.cuda(), b.cuda(), out16=o16, relu=True)
+    assert torch.allclose(o16.cpu().double(), torch.relu(A.double() @ W.double().t() + b.double()), atol=0.05, rtol=1e-2)
+
+
 def _attn_ref(q, k, v, scale=0.125):
     qh, kh, vh = (t.double().view(t.shape[0], 4, 64).permute(1, 0, 2) for t in (q, k, v))
     return (torch.softmax(qh @ kh.transpose(1, 2) * scale, -1) @ vh).permute(1, 0, 2).reshape(q.shape[0], 256)
