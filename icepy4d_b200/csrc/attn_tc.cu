@@ -8,19 +8,25 @@
 // over X serves all three operands.  gridDim = (ceil(maxNq/128), heads, n_problems) so both images of a SuperGlue /
 // LightGlue layer (self or cross) run in one launch.
 //
-// CTA = 128 query rows x 1 head, 320 threads, two CTAs per SM:
-//   warp 0      TMA producer: Q once, then K_j (2-stage ring) and V_j (single buffer) blocks of 128 keys
-//   warp 1      MMA issuer (one lane): S_j = Q K_j^T (M128 N128 K64 -> 4 tcgen05.mma) into TMEM[0,128);
-//               O += P_j V_j (M128 N64 K128 -> 8 tcgen05.mma, V is the MN-major B operand) accumulating in TMEM[128,192)
-//   warps 2..9  softmax: TWO threads per query row (TMEM lane), 64 keys each.  S is read from TMEM exactly once
-//               (TMEM reads, 64 B/clk/SM, and MUFU.EX2, 16/clk/SM, are the two co-limiting units at head_dim 64),
-//               released immediately so that QK_{j+1} overlaps the exponentials of block j.  Row max exchanged
-//               between the two threads of a row through shared memory; p = exp2(s*c - m) packed to bf16 and stored
-//               in the 128B-swizzled K-major layout the MMA reads.  The running max is LAZY: O (in TMEM) and the row
-//               sum are only rescaled when the max grows by more than 2^8, so the TMEM read-modify-write of O is rare.
+// At head_dim 64 the exponentials, not the tensor cores, are the critical resource: a 128 x 128 score block costs 512 clk of
+// tcgen05.mma but 1024 clk of MUFU.EX2 (16 / clk / SM, measured).  The kernel is therefore organised around keeping the
+// MUFU pipe busy: one CTA per SM (128 queries x 1 head, 320 threads) with TWO softmax warp groups that ping-pong over the
+// key blocks, so one group's TMEM loads / row maxima / barrier traffic hide behind the other group's exponentials.
+//   warp 0      TMA producer: Q once, then K_j and V_j blocks of 128 keys through two 3-stage rings
+//   warp 1      MMA issuer (one elected lane): S_j = Q K_j^T (M128 N128 K64) into TMEM S[j & 1] (two score buffers);
+//               O += P_j V_j (M128 N64 K128, V is the MN-major B operand) accumulating in TMEM; issue order
+//               ... PV_{j-1}, QK_{j+2}, PV_j ... so the scores of a group's next block are ready when it returns
+//   warps 2..5  softmax group 0 (even key blocks), warps 6..9 group 1 (odd key blocks): ONE thread per query row holds the
+//               block's 128 scores in registers (read from TMEM once, the buffer is released immediately).  The running row
+//               maximum is shared between the two groups through shared memory (block j publishes m_j, block j+1 consumes
+//               it: a short handshake before the long exponential phase) and is LAZY: O (in TMEM) and the row sums are
+//               rescaled only when the maximum grows by more than 2^8.  p = exp2(s*c - m) with packed f32x2 arithmetic
+//               (FFMA2 / FADD2 / FMNMX3), packed to bf16 and stored in the 128B-swizzled K-major layout the MMA reads,
+//               into one of two P buffers.
 //
 // Reference behaviour replaced: `attention()` + MultiHeadedAttention of thirdparty/SuperGlue/models/superglue.py:87-116
 // (materialises a 4 x N x M f32 tensor) and Attention/SelfBlock/CrossBlock of thirdparty/LightGlue/lightglue/lightglue.py:92-216.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/icepy4d_b200.h"
@@ -28,15 +34,21 @@
 #define FA_BM 128
 #define FA_BN 128
 #define FA_D 64
-#define FA_KV_STAGES 2
-#define FA_THREADS 320
+#define FA_KV_STAGES 3
+#define FA_THREADS 576
 #define FA_Q_BYTES (FA_BM * FA_D * 2)           // 16 KB
 #define FA_KV_BYTES (FA_BN * FA_D * 2)          // 16 KB each for K and V
-#define FA_P_BYTES (FA_BM * FA_BN * 2)          // 32 KB (two 16 KB K-halves)
-#define FA_SMEM_BYTES (FA_Q_BYTES + FA_KV_STAGES * FA_KV_BYTES + FA_KV_BYTES + FA_P_BYTES + 1024)   // Q | K x2 | V | P = 96 KB (+ align)
-#define FA_TMEM_COLS 256                        // S: [0,128)  O: [128,192)
+#define FA_P_BYTES (FA_BM * FA_BN * 2)          // 32 KB (two 16 KB K-halves), two buffers
+#define FA_SMEM_BYTES (FA_Q_BYTES + 2 * FA_KV_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024)   // Q | K x3 | V x3 | P x2 = 176 KB (+ align)
+#define FA_TMEM_COLS 512                        // S0: [0,128)  S1: [128,256)  O: [256,320)
 #define FA_MAX_PROBLEMS 4
 #define FA_TAU 8.0f                             // lazy-rescale threshold (log2 units)
+// Share of the exponentials evaluated on the FMA pipe instead of MUFU (Cody-Waite range reduction + degree-3 minimax
+// polynomial, relative error 7.7e-5 — far below the bf16 rounding of P): bit e of the mask selects pair e of every 8-element
+// chunk; even / odd chunks use the low / high nibble.  MUFU.EX2 (16 / clk / SM) is the critical pipe of this kernel.
+#ifndef FA_POLY_MASK
+#define FA_POLY_MASK 0x00
+#endif
 
 struct AttnProblem { int q_row0, nq, k_row0, nk; };
 struct AttnParams {
@@ -50,6 +62,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x for a pair on the FMA / ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 polynomial; 2^n by adding n
+// to the exponent field (the magic-number addition leaves n in the low mantissa bits of r)
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float magic = 12582912.f;                                   // 1.5 * 2^23
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 r = __fadd2_rn(x, make_float2(magic, magic));
+  const float2 fi = __fadd2_rn(r, make_float2(-magic, -magic));
+  const float2 f = __fadd2_rn(x, make_float2(-fi.x, -fi.y));
+  float2 pl = __ffma2_rn(f, make_float2(0.05508868f, 0.05508868f), make_float2(0.24260405f, 0.24260405f));
+  pl = __ffma2_rn(pl, f, make_float2(0.69327624f, 0.69327624f));
+  pl = __ffma2_rn(pl, f, make_float2(0.99992894f, 0.99992894f));
+  return make_float2(__int_as_float(__float_as_int(pl.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(pl.y) + (__float_as_int(r.y) << 23)));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -84,16 +110,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-__global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmX, AttnParams p) {
+__device__ __forceinline__ void tmem_ld32x(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int POLY_MASK>
+__global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmX, AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + FA_Q_BYTES;                                   // K ring: stage s at sK + s*16K (double buffered)
-  uint8_t* sV = sK + FA_KV_STAGES * FA_KV_BYTES;                   // V: single buffer (needed only from P_j to PV_j)
-  uint8_t* sP = sV + FA_KV_BYTES;
-  __shared__ __align__(8) uint64_t q_full, k_full[FA_KV_STAGES], k_empty[FA_KV_STAGES], v_full, v_empty, s_full, s_empty, p_full, pv_done;
+  uint8_t* sK = sQ + FA_Q_BYTES;                                   // K ring: stage s at sK + s*16K
+  uint8_t* sV = sK + FA_KV_STAGES * FA_KV_BYTES;                   // V ring
+  uint8_t* sP = sV + FA_KV_STAGES * FA_KV_BYTES;                   // P buffers: block j -> sP + (j & 1) * 32K
+  __shared__ __align__(8) uint64_t q_full, k_full[FA_KV_STAGES], k_empty[FA_KV_STAGES], v_full[FA_KV_STAGES], v_empty[FA_KV_STAGES];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2], m_ready[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float xch[2][2][FA_BM];                               // [block parity][column half][row]: row-max exchange
+  __shared__ float mrun_s[FA_BM];                                  // running row maximum after the latest block (log2 units)
+  __shared__ float lsum_s[4][FA_BM];                               // per (group, column half) row sums for the final exchange
+  __shared__ float xch[2][2][2][FA_BM];                            // [group][block parity of the group][column half][row]: row-max exchange
 
   const AttnProblem pr = p.prob[blockIdx.z];
   const int q0 = blockIdx.x * FA_BM;
@@ -105,13 +147,14 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmX);
     tc::mbar_init(&q_full, 1);
-    for (int s = 0; s < FA_KV_STAGES; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
-    tc::mbar_init(&v_full, 1);
-    tc::mbar_init(&v_empty, 1);
-    tc::mbar_init(&s_full, 1);
-    tc::mbar_init(&s_empty, 256);
-    tc::mbar_init(&p_full, 256);
-    tc::mbar_init(&pv_done, 1);
+    for (int s = 0; s < FA_KV_STAGES; ++s) {
+      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
+      tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&s_full[b], 1); tc::mbar_init(&s_empty[b], 256); tc::mbar_init(&p_full[b], 256);
+      tc::mbar_init(&pv_done[b], 1); tc::mbar_init(&m_ready[b], 256);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, FA_TMEM_COLS);
@@ -119,7 +162,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+  const uint32_t tmem_O = tmem + 256;
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -132,13 +175,16 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
         tc::mbar_arrive_expect_tx(&k_full[s], FA_KV_BYTES);
         tc::tma_load_2d(sK + s * FA_KV_BYTES, &tmX, &k_full[s], p.k_col + h * FA_D, pr.k_row0 + j * FA_BN);
       };
-      load_k(0);
-      if (nblk > 1) load_k(1);
+      auto load_v = [&](int j) {
+        const int s = j % FA_KV_STAGES;
+        tc::mbar_wait(&v_empty[s], ((j / FA_KV_STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&v_full[s], FA_KV_BYTES);
+        tc::tma_load_2d(sV + s * FA_KV_BYTES, &tmX, &v_full[s], p.v_col + h * FA_D, pr.k_row0 + j * FA_BN);
+      };
+      for (int j = 0; j < FA_KV_STAGES && j < nblk; ++j) load_k(j);
       for (int j = 0; j < nblk; ++j) {
-        tc::mbar_wait(&v_empty, (j & 1) ^ 1);                                // PV_{j-1} retired
-        tc::mbar_arrive_expect_tx(&v_full, FA_KV_BYTES);
-        tc::tma_load_2d(sV, &tmX, &v_full, p.v_col + h * FA_D, pr.k_row0 + j * FA_BN);
-        if (j + 2 < nblk) load_k(j + 2);                                     // stage freed when QK_j retired
+        load_v(j);
+        if (j + FA_KV_STAGES < nblk) load_k(j + FA_KV_STAGES);
       }
     }
     __syncwarp();
@@ -148,116 +194,132 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
       constexpr uint32_t idesc_qk = tc::make_idesc(FA_BM, FA_BN, 0, 0, 1);   // A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = tc::make_idesc(FA_BM, FA_D, 0, 1, 1);    // A = P (K-major), B = V (MN-major)
       constexpr uint32_t hi_k = tc::desc_hi_sw128(1024);                     // K-major operands and MN-major V: SBO = 1024
-      const uint32_t dQ = tc::desc_lo_sw128(tc::smem_u32(sQ)), dP = tc::desc_lo_sw128(tc::smem_u32(sP));
+      const uint32_t dQ = tc::desc_lo_sw128(tc::smem_u32(sQ)), dP0 = tc::desc_lo_sw128(tc::smem_u32(sP));
       const uint32_t dK0 = tc::desc_lo_sw128(tc::smem_u32(sK));
-      auto issue_qk = [&](int j) {
+      // V descriptor: MN-major, 8-key groups 1024 B apart (SBO), one 64-wide N atom: LBO field = 1024 >> 4 as well
+      const uint32_t dV0 = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
+      auto issue_qk = [&](int j) {                                          // S[j & 1] = Q K_j^T
         const int s = j % FA_KV_STAGES;
         tc::mbar_wait(&k_full[s], (j / FA_KV_STAGES) & 1);
-        if (j > 0) tc::mbar_wait(&s_empty, (j - 1) & 1);                    // S_{j-1} has been read into registers
+        if (j >= 2) tc::mbar_wait(&s_empty[j & 1], ((j - 2) >> 1) & 1);    // S_{j-2} has been read into registers
         tc::tcgen05_fence_after();
         const uint32_t dK = dK0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
+        const uint32_t tS = tmem + (uint32_t)(j & 1) * FA_BN;
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tmem_S, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
+        for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tS, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
         tc::umma_commit(&k_empty[s]);                                       // K_j no longer needed once these retire
-        tc::umma_commit(&s_full);
+        tc::umma_commit(&s_full[j & 1]);
       };
       tc::mbar_wait(&q_full, 0);
       issue_qk(0);
-      // V descriptor: MN-major, 8-key groups 1024 B apart (SBO), one 64-wide N atom: LBO field = 1024 >> 4 as well
-      const uint32_t dV = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
+      if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_qk(j + 1);                                  // runs while the softmax warps exponentiate block j
-        tc::mbar_wait(&v_full, j & 1);
-        tc::mbar_wait(&p_full, j & 1);                                      // P_j in shared memory, O rescaled if needed
+        // QK_{j+2} goes in front of PV_j: its score buffer S[j & 1] is released early in block j (right after the TMEM load),
+        // so the scores are ready when the group that owns blocks j, j + 2, ... returns from its exponentials
+        if (j + 2 < nblk) issue_qk(j + 2);
+        const int s = j % FA_KV_STAGES;
+        tc::mbar_wait(&v_full[s], (j / FA_KV_STAGES) & 1);
+        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);                        // P_j in shared memory, O rescaled if needed
         tc::tcgen05_fence_after();
+        const uint32_t dP = dP0 + (uint32_t)((j & 1) * (FA_P_BYTES >> 4));
+        const uint32_t dV = dV0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
           // A: P k-slice = 16 keys = 32 B inside the 128-B swizzle row of K-half (k / 4);  B: V rows [16k, 16k+16) x 64 dims
           tc::umma_f16_parts(tmem_O, dP + (uint32_t)(((k >> 2) * (FA_BM * 128) + (k & 3) * 32) >> 4), hi_k,
                              dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (j | k) ? 1u : 0u);
         }
-        tc::umma_commit(&v_empty);                                          // V buffer free
-        tc::umma_commit(&pv_done);                                          // O includes block j; P buffer free
+        tc::umma_commit(&v_empty[s]);                                       // V stage free
+        tc::umma_commit(&pv_done[j & 1]);                                   // O includes block j; P buffer free
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------ softmax: two threads per query row
+    // ------------------------------------------------ softmax: group g (8 warps) owns key blocks j = g, g + 2, ...;
+    // TWO threads per query row (TMEM lane), 64 keys each: 16 softmax warps per SM keep the issue slots and the MUFU pipe fed
+    const int sw = warp - 2;                                                // 0..15
+    const int g = sw >> 3;
+    const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
     const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
-    const int hf = (warp - 2) >> 2;                                         // column half: keys [64 hf, 64 hf + 64) of the block
     const int q = quarter * 32 + lane;                                      // TMEM lane == tile row
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t rsw = (uint32_t)(q & 7);
-    const uint32_t prow = tc::smem_u32(sP) + (uint32_t)hf * (FA_BM * 128) + (uint32_t)(q >> 3) * 1024 + (uint32_t)(q & 7) * 128;
-    float m_run = -INFINITY, l_part = 0.f;
+    const uint32_t prow0 = tc::smem_u32(sP) + (uint32_t)hf * (FA_BM * 128) + (uint32_t)(q >> 3) * 1024 + (uint32_t)(q & 7) * 128;
+    const int pair_bar = 2 + g * 4 + quarter;                               // named barrier of the two warps that share my rows
+    float m_mine = -INFINITY, l_part = 0.f;                                 // l_part is relative to m_mine
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 
-    for (int j = 0; j < nblk; ++j) {
-      tc::mbar_wait(&s_full, j & 1);
+    for (int j = g; j < nblk; j += 2) {
+      const uint32_t b = (uint32_t)j & 1u, ph = ((uint32_t)j >> 1) & 1u;
+      tc::mbar_wait(&s_full[b], ph);
       tc::tcgen05_fence_after();
-      uint32_t v0[32], v1[32];
-      tc::tmem_ld32(tmem_S + lane_off + hf * 64, v0);
-      tc::tmem_ld32(tmem_S + lane_off + hf * 64 + 32, v1);
+      uint32_t v[64];
+      const uint32_t tS = tmem + lane_off + b * FA_BN + hf * 64;
+      tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
       tc::tmem_ld_wait();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&s_empty);                                            // QK_{j+1} may overwrite S now
-      const int kvalid = min(64, max(0, pr.nk - j * FA_BN - hf * 64));      // keys of my half that exist
+      tc::mbar_arrive(&s_empty[b]);                                         // QK_{j+2} may overwrite this score buffer now
+      const int kvalid = pr.nk - j * FA_BN - hf * 64;                       // keys of my half that exist
       if (kvalid < 64) {                                                    // only in the last block
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= kvalid) v0[i] = 0xff800000u;                             // -inf
-          if (32 + i >= kvalid) v1[i] = 0xff800000u;
-        }
+        for (int i = 0; i < 64; ++i)
+          if (i >= kvalid) v[i] = 0xff800000u;                              // -inf
       }
-      // 3-input max (FMNMX3): 32 instructions for the 64 values, four independent chains
       float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mxa[i & 3] = fmax3(mxa[i & 3], __uint_as_float(v0[i]), __uint_as_float(v1[i]));
+      for (int i = 0; i < 64; i += 2) mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
       float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      xch[j & 1][hf][q] = mx;
-      named_bar_sync(1 + quarter, 64);                                      // the two warps that share this lane quarter
-      mx = fmaxf(mx, xch[j & 1][hf ^ 1][q]);
+      const int xp = (j >> 1) & 1;
+      xch[g][xp][hf][q] = mx;
+      named_bar_sync(pair_bar, 64);                                         // the two warps that share this lane quarter
+      mx = fmaxf(mx, xch[g][xp][hf ^ 1][q]);
       const float m_blk = mx * p.scale_log2;
-      // lazy running max: rescale only when this block's max exceeds the reference max by more than 2^TAU
-      float alpha = 1.f;
+      // ---- running maximum handshake with the other group (lazy: move only when the block exceeds it by more than 2^TAU)
+      float m_prev = -INFINITY, m_new = m_blk;
       bool need = false;
-      if (j == 0) {
-        m_run = m_blk;
-      } else if (m_blk > m_run + FA_TAU) {
-        alpha = ex2_approx(m_run - m_blk);
-        m_run = m_blk;
-        need = true;
-      }
       if (j > 0) {
-        tc::mbar_wait(&pv_done, (j - 1) & 1);                               // P buffer free, O quiescent
-        if (__any_sync(0xffffffffu, need)) {
-          tc::tcgen05_fence_after();
+        tc::mbar_wait(&m_ready[b ^ 1], (((uint32_t)(j - 1)) >> 1) & 1u);
+        m_prev = mrun_s[q];
+        if (m_blk > m_prev + FA_TAU) need = true; else m_new = m_prev;
+        named_bar_sync(pair_bar, 64);                                       // my partner has read m_prev before I overwrite it
+      }
+      if (hf == 0) mrun_s[q] = m_new;
+      tc::mbar_arrive(&m_ready[b]);
+      if (m_new != m_mine) {                                                // bring my partial row sum to the new reference
+        l_part = (m_mine == -INFINITY) ? 0.f : l_part * ex2_approx(m_mine - m_new);
+        m_mine = m_new;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // O (TMEM) is relative to m_prev: rescale my half of the row once PV_{j-1} has retired (PV_j cannot start before my
+        // p_full arrival)
+        tc::mbar_wait(&pv_done[b ^ 1], (((uint32_t)(j - 1)) >> 1) & 1u);
+        tc::tcgen05_fence_after();
+        const float alpha = need ? ex2_approx(m_prev - m_new) : 1.f;
 #pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {                                  // two 16-column halves: keeps the register peak low
-            uint32_t ov[16];
-            tmem_ld16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
-            tc::tmem_ld_wait();
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t ov[16];
+          tmem_ld16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
+          tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
-            tmem_st_wait();
-          }
-          l_part *= alpha;
+          for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st16(tmem_O + lane_off + hf * 32 + hh * 16, ov);
+          tmem_st_wait();
         }
       }
-      // p = exp2(s * c - m_run); f32 row sum; bf16 pack; swizzled store (8 chunks of 16 B = my K-half row)
-      // packed f32x2 arithmetic (FFMA2 / FADD2): one issue slot per two elements for the scaling and the row sum
+      if (j >= 2) tc::mbar_wait(&pv_done[b], (((uint32_t)(j - 2)) >> 1) & 1u);   // P buffer b free (PV_{j-2} retired)
+      // p = exp2(s * c - m); f32 row sum; bf16 pack; swizzled store (8 chunks of 16 B = my K-half row)
       float2 rs2 = make_float2(0.f, 0.f);
-      const float2 nm2 = make_float2(-m_run, -m_run), sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_new, -m_new);
+      const uint32_t prow = prow0 + b * FA_P_BYTES;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = t * 8 + e * 2;
-          const uint32_t ra = (i < 32) ? v0[i & 31] : v1[i & 31];
-          const uint32_t rb = (i + 1 < 32) ? v0[(i + 1) & 31] : v1[(i + 1) & 31];
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(ra), __uint_as_float(rb)), sc2, nm2);
-          const float2 ab = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+          const bool poly = (((t & 1) ? (POLY_MASK >> 4) : POLY_MASK) >> e) & 1;      // compile-time after unrolling
+          const float2 ab = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
           rs2 = __fadd2_rn(rs2, ab);
           __nv_bfloat162 pr2 = __floats2bfloat162_rn(ab.x, ab.y);
           pk[e] = *reinterpret_cast<uint32_t*>(&pr2);
@@ -268,30 +330,36 @@ __global__ void __launch_bounds__(FA_THREADS, 2) attn_tc_kernel(const __grid_con
       l_part += rs2.x + rs2.y;
       tc::tcgen05_fence_before();
       tc::fence_proxy_async_smem();                                         // make P_j visible to the tensor-core proxy
-      tc::mbar_arrive(&p_full);
+      tc::mbar_arrive(&p_full[b]);
     }
-    // epilogue: O / l -> bf16.  Each thread owns 32 of the 64 output dims of its row.
-    tc::mbar_wait(&pv_done, (nblk - 1) & 1);
-    tc::tcgen05_fence_after();
-    xch[nblk & 1][hf][q] = l_part;
-    named_bar_sync(1 + quarter, 64);
-    const float l = l_part + xch[nblk & 1][hf ^ 1][q];
-    uint32_t ov[32];
-    tc::tmem_ld32(tmem_O + lane_off + hf * 32, ov);
-    tc::tmem_ld_wait();
-    if (q0 + q < pr.nq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst = p.O + (size_t)(pr.q_row0 + q0 + q) * p.ldo + h * FA_D + hf * 32;
+    // ---- final: bring all four partial row sums to the final maximum, exchange, normalise O
+    {
+      const uint32_t jl = (uint32_t)(nblk - 1);
+      tc::mbar_wait(&m_ready[jl & 1], (jl >> 1) & 1u);
+      const float m_fin = mrun_s[q];
+      lsum_s[g * 2 + hf][q] = (m_mine == -INFINITY) ? 0.f : l_part * ex2_approx(m_mine - m_fin);
+      asm volatile("bar.sync 1, 512;" ::: "memory");                        // the sixteen softmax warps
+      const float l = (lsum_s[0][q] + lsum_s[1][q]) + (lsum_s[2][q] + lsum_s[3][q]);
+      tc::mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1u);
+      tc::tcgen05_fence_after();
+      const int c0 = (g * 2 + hf) * 16;                                     // four threads per row: 16 of the 64 output dims each
+      uint32_t ov[16];
+      tmem_ld16(tmem_O + lane_off + c0, ov);
+      tc::tmem_ld_wait();
+      if (q0 + q < pr.nq) {
+        const float inv = 1.f / l;
+        __nv_bfloat16* dst = p.O + (size_t)(pr.q_row0 + q0 + q) * p.ldo + h * FA_D + c0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 pk;
-        __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
-        __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-        __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-        __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-        pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-        pk.z = *reinterpret_cast<uint32_t*>(&c2); pk.w = *reinterpret_cast<uint32_t*>(&d);
-        *reinterpret_cast<uint4*>(dst + i) = pk;
+        for (int i = 0; i < 16; i += 8) {
+          uint4 pk;
+          __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+          __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+          __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+          pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
+          pk.z = *reinterpret_cast<uint32_t*>(&c2); pk.w = *reinterpret_cast<uint32_t*>(&d);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
       }
     }
   }
@@ -326,13 +394,27 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   p.O = reinterpret_cast<__nv_bfloat16*>(O); p.ldo = ldo;
   CUtensorMap tmX;
   if (int rc = i4d_make_tmap_2d_bf16(&tmX, X, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, FA_BN, FA_D)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    attr_set = true;
+  // share of exponentials on the FMA pipe: FA_POLY_MASK by default; I4D_FA_POLY=0|25|37|50 selects another build (experiments)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("I4D_FA_POLY");
+    const int pct = e ? atoi(e) : -1;
+    variant = pct == 0 ? 0 : pct == 25 ? 1 : pct == 37 ? 2 : pct == 50 ? 3 : 4;
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<FA_POLY_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }
   dim3 grid(i4d_cdiv(max_nq, FA_BM), heads, n_problems);
-  attn_tc_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, (cudaStream_t)stream>>>(tmX, p);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (variant) {
+    case 0: attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 1: attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 2: attn_tc_kernel<0xA8><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 3: attn_tc_kernel<0xAA><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    default: attn_tc_kernel<FA_POLY_MASK><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+  }
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
