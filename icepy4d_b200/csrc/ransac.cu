@@ -373,65 +373,70 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
   }
 }
 
-// smallest eigenvector of the 9x9 moment matrix (cyclic Jacobi, f64), rank-2 projection, denormalisation.
-// One warp: the matrices live in shared memory, lane k owns row/column k of every plane rotation.
+// Smallest eigenvector of the 9x9 moment matrix, rank-2 projection, denormalisation.
+// The matrix is symmetric positive semi-definite with one eigenvalue far below the rest (the epipolar constraint), so inverse
+// iteration on C + eps*I (one Cholesky factorisation, two triangular solves per step, f64) converges in a handful of steps —
+// ~10 us on one thread where the cyclic Jacobi sweep this replaces took ~100 us per polish iteration (20 per verification).
 __global__ void __launch_bounds__(32) rs_polish_solve_kernel(RansacState* st) {
-  __shared__ double C[9][9], V[9][9];
-  __shared__ double Fn_s[9];
-  const int lane = threadIdx.x;
-  if (lane == 0) {
+  if (threadIdx.x != 0) return;
+  double L[9][9];
+  double tr = 0;
+  {
     int t = 0;
     for (int p = 0; p < 9; ++p)
-      for (int q = p; q < 9; ++q) { C[p][q] = C[q][p] = st->cov[t++]; }
+      for (int q = p; q < 9; ++q) { L[q][p] = st->cov[t]; L[p][q] = st->cov[t]; ++t; }
     for (int i = 0; i < 45; ++i) st->cov[i] = 0.0;
+    for (int p = 0; p < 9; ++p) tr += L[p][p];
   }
-  if (lane < 9)
-    for (int q = 0; q < 9; ++q) V[lane][q] = (lane == q) ? 1.0 : 0.0;
-  __syncwarp();
-  double tr = 0;
-  for (int p = 0; p < 9; ++p) tr += C[p][p];
-  if (!(tr > 0)) return;              // no support: keep the previous model (uniform across the warp)
-  for (int sweep = 0; sweep < 24; ++sweep) {
-    double off = 0;
-    for (int p = 0; p < 8; ++p)
-      for (int q = p + 1; q < 9; ++q) off += C[p][q] * C[p][q];
-    if (off < 1e-26 * tr * tr) break;   // off-diagonal mass relative to the trace: eigenvector good to ~1e-13
-    for (int p = 0; p < 8; ++p)
-      for (int q = p + 1; q < 9; ++q) {
-        const double cpq = C[p][q];
-        if (cpq == 0.0) continue;       // uniform
-        const double theta = (C[q][q] - C[p][p]) / (2.0 * cpq);
-        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-        __syncwarp();
-        if (lane < 9) {                 // columns p, q of row `lane`
-          const double ckp = C[lane][p], ckq = C[lane][q];
-          C[lane][p] = c * ckp - s * ckq; C[lane][q] = s * ckp + c * ckq;
-          const double vkp = V[lane][p], vkq = V[lane][q];
-          V[lane][p] = c * vkp - s * vkq; V[lane][q] = s * vkp + c * vkq;
-        }
-        __syncwarp();
-        if (lane < 9) {                 // rows p, q of column `lane`
-          const double cpk = C[p][lane], cqk = C[q][lane];
-          C[p][lane] = c * cpk - s * cqk; C[q][lane] = s * cpk + c * cqk;
-        }
-        __syncwarp();
-      }
+  if (!(tr > 0)) return;              // no support: keep the previous model
+  const double eps = 1e-13 * tr;
+  // Cholesky of C + eps I (lower triangle, in place)
+  for (int j = 0; j < 9; ++j) {
+    double d = L[j][j] + eps;
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 0)) d = eps;            // rank-deficient input: regularise the pivot
+    d = sqrt(d);
+    L[j][j] = d;
+    const double inv = 1.0 / d;
+    for (int i = j + 1; i < 9; ++i) {
+      double v = L[i][j];
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
   }
-  if (lane == 0) {
-    int jm = 0;
-    for (int j = 1; j < 9; ++j)
-      if (C[j][j] < C[jm][jm]) jm = j;
-    for (int i = 0; i < 9; ++i) Fn_s[i] = V[i][jm];
-    double Fn[9];
-    for (int i = 0; i < 9; ++i) Fn[i] = Fn_s[i];
-    rs_rank2(Fn);
-    double F[9];
-    rs_denormalise(Fn, st->T0, st->T1, F);
-    bool ok = true;
-    for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
-    if (ok) for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
+  double x[9], y[9];
+  for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;       // generic start (not orthogonal to the null direction)
+  for (int it = 0; it < 16; ++it) {
+    for (int i = 0; i < 9; ++i) {                                  // L y = x
+      double v = x[i];
+      for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+      y[i] = v / L[i][i];
+    }
+    for (int i = 8; i >= 0; --i) {                                 // L^T z = y (z overwrites y)
+      double v = y[i];
+      for (int k = i + 1; k < 9; ++k) v -= L[k][i] * y[k];
+      y[i] = v / L[i][i];
+    }
+    double nrm = 0;
+    for (int i = 0; i < 9; ++i) nrm += y[i] * y[i];
+    nrm = 1.0 / sqrt(nrm);
+    double diff = 0, diffn = 0;
+    for (int i = 0; i < 9; ++i) {
+      const double z = y[i] * nrm;
+      diff += (z - x[i]) * (z - x[i]);
+      diffn += (z + x[i]) * (z + x[i]);
+      x[i] = z;
+    }
+    if (it > 0 && fmin(diff, diffn) < 1e-28) break;               // converged up to sign
   }
+  double Fn[9];
+  for (int i = 0; i < 9; ++i) Fn[i] = x[i];
+  rs_rank2(Fn);
+  double F[9];
+  rs_denormalise(Fn, st->T0, st->T1, F);
+  bool ok = true;
+  for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
+  if (ok) for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
 }
 
 __global__ void rs_copy_best_kernel(RansacState* st) {

@@ -171,8 +171,16 @@ class ImageMatcherBase(ImageMatcherABC):
         if self._do_viz:
             logger.warning("visualisation is outside the B200 hot path; do_viz_matches is ignored")
 
-        dev0, dev1 = self._resize_images_device(quality, self._upload(image0), self._upload(image1))
-        mk0, mk1, s0, s1, conf, d0, d1, F = self.match_device(dev0, dev1, quality, tile_selection, **config)
+        if quality == Quality.HIGH and tile_selection in (TileSelection.GRID, TileSelection.EXHAUSTIVE):
+            # tiles are cut straight from the uploaded images: upload in row bands on a copy stream (band order = tile order) and
+            # let every tile wait only for its own rows, so SuperPoint starts after the first band instead of after 144 MB
+            dev0, dev1 = self._upload_banded(image0, image1, config.get("grid", [1, 1]))
+        else:
+            dev0, dev1 = self._resize_images_device(quality, self._upload(image0), self._upload(image1))
+        try:
+            mk0, mk1, s0, s1, conf, d0, d1, F = self.match_device(dev0, dev1, quality, tile_selection, **config)
+        finally:
+            self._row_events = {}
         self._F = F.cpu().numpy().reshape(3, 3) if F is not None else None
         self._store_device_results(mk0, mk1, s0, s1, conf, d0, d1)
         if self._save_dir is not None:
@@ -243,6 +251,51 @@ class ImageMatcherBase(ImageMatcherABC):
         t = torch.from_numpy(np.ascontiguousarray(image))
         return t.cuda(non_blocking=True)
 
+    def _upload_banded(self, image0: np.ndarray, image1: np.ndarray, grid):
+        """H2D of both images in `grid[0]` row bands each, alternating between the images (the order in which the tile loop
+        touches them), on a dedicated copy stream.  Every band records an event; `_tile_tensor` makes the compute stream wait
+        for the bands a tile overlaps.  With pageable host memory the copies are synchronous and this degrades to `_upload`."""
+        imgs = []
+        for image in (image0, image1):
+            assert isinstance(image, np.ndarray), "images must be NumPy arrays"
+            if image.dtype != np.uint8:
+                raise TypeError("images must be uint8 (H x W or H x W x 3)")
+            if image.ndim == 3 and image.shape[2] not in (1, 3):
+                raise ValueError(f"Not an image: {image.shape}")
+            imgs.append(torch.from_numpy(np.ascontiguousarray(image)))
+        devs = [torch.empty(t.shape, dtype=torch.uint8, device="cuda") for t in imgs]
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cs, cur = self._copy_stream, torch.cuda.current_stream()
+        cs.wait_stream(cur)                                           # the destination buffers belong to the compute stream
+        nb = max(1, int(grid[0]))
+        self._row_events = {d.data_ptr(): [] for d in devs}
+        with torch.cuda.stream(cs):
+            for b in range(nb):
+                for t, d in zip(imgs, devs):
+                    h = t.shape[0]
+                    r0, r1 = (h * b) // nb, (h * (b + 1)) // nb
+                    d[r0:r1].copy_(t[r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    self._row_events[d.data_ptr()].append((r1, ev))
+        for d in devs:
+            d.record_stream(cs)
+        return devs[0], devs[1]
+
+    def _wait_rows(self, dev_img: torch.Tensor, y1: int):
+        """Compute stream waits for the upload bands covering rows [0, y1) of a banded image (no-op otherwise)."""
+        evs = getattr(self, "_row_events", {}).get(dev_img.data_ptr())
+        if not evs:
+            return
+        cur = torch.cuda.current_stream()
+        while evs:
+            r1, ev = evs[0]
+            cur.wait_event(ev)
+            evs.pop(0)
+            if r1 >= y1:
+                break
+
     def _resize_images_device(self, quality: Quality, dev0: torch.Tensor, dev1: torch.Tensor):
         """matchers.py:583-610 on the device: bit-exact cv2.pyrUp / pyrDown kernels on the uploaded u8 images."""
         if quality == Quality.HIGHEST:
@@ -265,6 +318,7 @@ class ImageMatcherBase(ImageMatcherABC):
 
     def _tile_tensor(self, dev_img: torch.Tensor, rect) -> torch.Tensor:
         x0, y0, tw, th = rect
+        self._wait_rows(dev_img, y0 + th)
         return ops.tile_to_gray_f32(dev_img, x0, y0, tw, th, self.GRAY_MODE)
 
     # -- subclass hooks --

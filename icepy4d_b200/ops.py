@@ -338,6 +338,24 @@ def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.
     return F, mask, n_inl
 
 
+def essential_pose(E: torch.Tensor, xn0: torch.Tensor, xn1: torch.Tensor, threshold_norm: float, distance_threshold: float = 1e9):
+    """E [9] f64 device, xn0 / xn1 [n,2] f32 normalised -> (E_proj [9], R [9], t [3] f64, mask [n] u8, n_good int32[2]) on the device."""
+    _chk(xn0, name="xn0"), _chk(xn1, name="xn1")
+    assert E.is_cuda and E.dtype == torch.float64 and E.numel() == 9
+    n = xn0.shape[0]
+    dev = xn0.device
+    nbytes = N.lib().i4d_pose_workspace_bytes(n)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    Eo = torch.empty(9, device=dev, dtype=torch.float64)
+    R = torch.empty(9, device=dev, dtype=torch.float64)
+    t = torch.empty(3, device=dev, dtype=torch.float64)
+    mask = torch.empty(n, device=dev, dtype=torch.uint8)
+    n_good = torch.zeros(2, device=dev, dtype=torch.int32)
+    N.call("i4d_essential_pose", E.contiguous(), xn0, xn1, n, float(threshold_norm), float(distance_threshold), Eo, R, t, mask,
+           n_good, ws, ws.numel(), _st())
+    return Eo, R, t, mask, n_good
+
+
 def tile_to_gray_f32(image_u8: torch.Tensor, x0: int, y0: int, tw: int, th: int, mode: int) -> torch.Tensor:
     """image [H,W,C] or [H,W] u8 on the device -> [1,1,th,tw] f32 network input."""
     assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()

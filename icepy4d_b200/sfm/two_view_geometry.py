@@ -2,7 +2,7 @@
 
 Returns (F [3,3] f64, inlMask [N] bool) and replaces `self.features[i]` by the inliers, like the reference.  The
 reference's MAGSAC branch raises IndexError because its mask is [N,1] (Appendix D.6); here the mask is [N] bool as in
-`geometric_verification`.  `estimate_pose` (5-point essential matrix) is the "next" row of SURVEY.md §8f."""
+`geometric_verification`.  `estimate_pose` follows two_view_geometry.py:52-109 on top of sfm.geometry.estimate_pose."""
 from __future__ import annotations
 
 import logging
@@ -33,5 +33,30 @@ class RelativeOrientation:
         self.features[1] = self.features[1][self.inlMask]
         return (self.F, self.inlMask)
 
-    def estimate_pose(self, *a, **k):
-        raise NotImplementedError("estimate_pose (essential-matrix RANSAC + recoverPose) is outside round 1 (SURVEY.md §8f rank 1)")
+    def estimate_pose(self, threshold: float = 1.0, confidence: float = 0.9999, scale_factor=None):
+        """two_view_geometry.py:52-109: essential-matrix relative orientation, then camera 1's extrinsics are replaced by the
+        estimated ones chained with camera 0's pose (same Camera calls as the reference, so its Camera class works here)."""
+        from .geometry import estimate_pose
+
+        assert self.cameras[0].extrinsics is not None, \
+            "Extrinsics matrix is not available for camera 0. Please, compute it before running RelativeOrientation estimation."
+        R, t, valid = estimate_pose(self.features[0], self.features[1], self.cameras[0].K, self.cameras[1].K,
+                                    thresh=threshold, conf=confidence)
+        logging.info(f"Relative Orientation - valid points: {valid.sum()}/{len(valid)}")
+        if scale_factor is not None:
+            t = t * scale_factor
+        else:
+            logging.warning("No scaling factor (e.g., computed from camera baseline) is provided. "
+                            "Two-view-geometry estimated up to a scale factor.")
+        extrinsics = self.cameras[1].Rt_to_extrinsics(R, t)
+        self.cameras[1].update_extrinsics(extrinsics)
+        cam2toWorld = self.cameras[0].pose @ self.cameras[1].pose
+        extrinsics = self.cameras[1].pose_to_extrinsics(cam2toWorld)
+        self.cameras[1].update_extrinsics(extrinsics)
+        logging.info("Relative orientation Succeded.")
+        return valid
+
+    def get_scale_factor_from_baseline(self, baseline_world: float):
+        """two_view_geometry.py:111-125"""
+        baseline = np.linalg.norm(np.asarray(self.cameras[0].C) - np.asarray(self.cameras[1].C))
+        return baseline_world / baseline

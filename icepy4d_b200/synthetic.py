@@ -52,6 +52,34 @@ class SimpleCamera:
     def P(self) -> np.ndarray:
         return self.K @ np.hstack([self.R, self.t.reshape(3, 1)])
 
+    # the extrinsics / pose helpers RelativeOrientation.estimate_pose calls on a Camera (camera.py:139-207, 263-330)
+    @property
+    def extrinsics(self) -> np.ndarray:
+        return self.Rt_to_extrinsics(self.R, self.t)
+
+    @property
+    def pose(self) -> np.ndarray:
+        return np.linalg.inv(self.extrinsics)
+
+    @property
+    def C(self) -> np.ndarray:
+        return self.pose[0:3, 3:4]
+
+    @staticmethod
+    def Rt_to_extrinsics(R, t) -> np.ndarray:
+        E = np.eye(4)
+        E[:3, :3] = np.asarray(R, dtype=np.float64)
+        E[:3, 3] = np.asarray(t, dtype=np.float64).reshape(3)
+        return E
+
+    @staticmethod
+    def pose_to_extrinsics(pose) -> np.ndarray:
+        return np.linalg.inv(np.asarray(pose, dtype=np.float64))
+
+    def update_extrinsics(self, extrinsics) -> None:
+        self.R = np.asarray(extrinsics)[:3, :3].copy()
+        self.t = np.asarray(extrinsics)[:3, 3].copy()
+
 
 def _look_at(C, target):
     z = target - C
@@ -74,12 +102,14 @@ def _project(X, cam: SimpleCamera):
     return np.stack([xd * cam.K[0, 0] + cam.K[0, 2], yd * cam.K[1, 1] + cam.K[1, 2]], 1), Xc[:, 2]
 
 
-def two_view_scene(n: int = 200_000, seed: int = 7, noise_px: float = 0.3, outlier_frac: float = 0.4):
-    """Returns dict(cams=[cam0, cam1], pts0 [n,2] f32, pts1 [n,2] f32, X [n,3] f64, inlier [n] bool)."""
+def two_view_scene(n: int = 200_000, seed: int = 7, noise_px: float = 0.3, outlier_frac: float = 0.4, distortion: bool = True):
+    """Returns dict(cams=[cam0, cam1], pts0 [n,2] f32, pts1 [n,2] f32, X [n,3] f64, inlier [n] bool).
+    distortion=False gives ideal pinhole cameras (relative-orientation tests work on undistorted coordinates)."""
     rng = np.random.default_rng(seed)
-    cam0 = SimpleCamera(CAM1_K, CAM1_DIST, np.eye(3), np.zeros(3))
+    d0, d1 = (CAM1_DIST, CAM2_DIST) if distortion else (np.zeros(5), np.zeros(5))
+    cam0 = SimpleCamera(CAM1_K, d0, np.eye(3), np.zeros(3))
     R1, t1 = _look_at(np.array([250.0, 0.0, 30.0]), np.array([100.0, 0.0, 600.0]))
-    cam1 = SimpleCamera(CAM2_K, CAM2_DIST, R1, t1)
+    cam1 = SimpleCamera(CAM2_K, d1, R1, t1)
     Xs, p0s, p1s = [], [], []
     have = 0
     while have < n:

@@ -164,6 +164,17 @@ int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double thres
                            unsigned char* mask, int* n_inliers, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* sfm/geometry.py:31-76 (cv2.findEssentialMat inlier rule + cv2.recoverPose) — relative pose from an essential-matrix
+ * estimate.  E_in [9] f64 (device, row-major, any scale), xn0 / xn1 [n,2] f32 K-normalised coordinates.  Projects E onto the
+ * essential manifold, marks Sampson inliers (error < threshold_norm^2), votes the four (R, t) candidates by cheirality over
+ * the inliers (depth in both cameras in (0, distance_threshold)) and keeps the best in OpenCV's candidate order.
+ * Outputs (device): E_out [9], R_out [9] row-major, t_out [3] (unit), mask [n] u8 = inlier AND in front of both cameras,
+ * n_good [2] = {votes of the chosen candidate, Sampson inliers}. */
+size_t i4d_pose_workspace_bytes(int n);
+int i4d_essential_pose(const double* E_in, const float* xn0, const float* xn1, int n, double threshold_norm,
+                       double distance_threshold, double* E_out, double* R_out, double* t_out, unsigned char* mask,
+                       int* n_good, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- tiler front end ---------------------------------------------------------------------------------- */
 /* matching/tiling.py:123-135 (extract_patch) fused with the grey conversion and the /255 tensor conversion:
  *   mode 0 (SuperGlueMatcher, matchers.py:911-917,263-274): cv2.cvtColor(RGB2GRAY) fixed point on u8, then /255.

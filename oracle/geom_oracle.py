@@ -103,3 +103,22 @@ def sampson_distance(F: np.ndarray, m0: np.ndarray, m1: np.ndarray) -> np.ndarra
     num = np.sum(x1 * Fx0, 1) ** 2
     den = Fx0[:, 0] ** 2 + Fx0[:, 1] ** 2 + Ftx1[:, 0] ** 2 + Ftx1[:, 1] ** 2
     return np.sqrt(num / den)
+
+
+def estimate_pose(kpts0: np.ndarray, kpts1: np.ndarray, K0: np.ndarray, K1: np.ndarray, thresh: float, conf: float = 0.9999):
+    """sfm/geometry.py:31-76 restated: K-normalise, cv2.findEssentialMat(RANSAC, thresh / mean focal), cv2.recoverPose with
+    the in/out mask; returns (R [3,3], t [3], inliers [N] bool) of the candidate with most points in front."""
+    if len(kpts0) < 5:
+        return None
+    f_mean = np.mean([K0[0, 0], K1[1, 1], K0[0, 0], K1[1, 1]])
+    norm_thresh = thresh / f_mean
+    kpts0 = (kpts0 - K0[[0, 1], [2, 2]][None]) / K0[[0, 1], [0, 1]][None]
+    kpts1 = (kpts1 - K1[[0, 1], [2, 2]][None]) / K1[[0, 1], [0, 1]][None]
+    E, mask = cv2.findEssentialMat(kpts0, kpts1, np.eye(3), threshold=norm_thresh, prob=conf, method=cv2.RANSAC)
+    assert E is not None, "Unable to estimate Essential matrix"
+    best, ret = 0, None
+    for _E in np.split(E, len(E) / 3):
+        n, R, t, _ = cv2.recoverPose(_E, kpts0, kpts1, np.eye(3), 1e9, mask=mask)
+        if n > best:
+            best, ret = n, (R, t[:, 0], mask.ravel() > 0)
+    return ret

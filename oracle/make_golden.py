@@ -179,6 +179,20 @@ def golden_geometry():
           "tri rel err", float(np.median(np.linalg.norm(X_it - sc["X"][inl][:600], axis=1) / np.linalg.norm(sc["X"][inl][:600], axis=1))))
 
 
+def golden_pose():
+    """sfm/geometry.py:31-76 run from the reference itself on an ideal-pinhole two-view scene with 30 % outliers."""
+    ref_shims.install_shims()
+    from icepy4d.sfm.geometry import estimate_pose
+
+    sc = synthetic.two_view_scene(n=4000, seed=31, noise_px=0.3, outlier_frac=0.3, distortion=False)
+    cams = sc["cams"]
+    R, t, inl = estimate_pose(sc["pts0"].astype(np.float64), sc["pts1"].astype(np.float64), cams[0].K, cams[1].K, 1.0, 0.9999)
+    np.savez_compressed(os.path.join(OUT, "pose.npz"), pts0=sc["pts0"], pts1=sc["pts1"], inlier=sc["inlier"], K0=cams[0].K,
+                        K1=cams[1].K, R_true=cams[1].R, t_true=cams[1].t, R=R, t=t, mask=inl)
+    ang = np.degrees(np.arccos(np.clip((np.trace(R @ cams[1].R.T) - 1) / 2, -1, 1)))
+    print("pose: inliers", int(inl.sum()), "of", len(inl), "true", int(sc["inlier"].sum()), "rotation error deg", float(ang))
+
+
 if __name__ == "__main__":
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -186,6 +200,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_tiler_quality()
     golden_geometry()
+    golden_pose()
     golden_superpoint_superglue()
     golden_lightglue()
     golden_matchers()
