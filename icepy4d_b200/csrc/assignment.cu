@@ -850,8 +850,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA: its band is the short one)
     if (cta == G - 1) {
       L2Acc a; a.init();
-#pragma unroll 4
-      for (int j = tid; j <= N; j += SK_THREADS) a.add((alpha + __ldcg(v + j)) * LOG2E);
+      for (int j0 = tid; j0 <= N; j0 += 16 * SK_THREADS) {
+        float vv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int j = j0 + k * SK_THREADS; vv[k] = (j <= N) ? __ldcg(v + j) : -INFINITY; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (vv[k] != -INFINITY) a.add((alpha + vv[k]) * LOG2E);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
       if (lane == 0) { red_m[warp] = a.m; red_s[warp] = a.s; }
@@ -907,9 +912,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
         }
       }
       if (cta == G - 1) {                                             // v[N] = log_nu_last - LSE_{i <= M}(alpha + u_i)
+        // (the last CTA owns the short band and no column tile at N = 8192: this reduction is off the other CTAs' critical
+        // path as long as it is one L2 round trip — all loads first, then the dependent accumulation)
         L2Acc a; a.init();
-#pragma unroll 4
-        for (int i = tid; i <= M; i += SK_THREADS) a.add((alpha + __ldcg(u + i)) * LOG2E);
+        for (int i0 = tid; i0 <= M; i0 += 16 * SK_THREADS) {
+          float uu[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { const int i = i0 + k * SK_THREADS; uu[k] = (i <= M) ? __ldcg(u + i) : -INFINITY; }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (uu[k] != -INFINITY) a.add((alpha + uu[k]) * LOG2E);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
         if (lane == 0) { red_m[warp] = a.m; red_s[warp] = a.s; }

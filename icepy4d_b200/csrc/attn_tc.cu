@@ -56,7 +56,15 @@ struct AttnParams {
   int q_col, k_col, v_col;
   float scale_log2;                 // scale * log2(e)
   __nv_bfloat16* O; int ldo;        // O rows are indexed like Q rows (q_row0 + i)
+  // work decomposition: item = (problem * heads + head) * n_qt + q-tile.  CTAs [0, n_whole) run whole items; the items behind
+  // them — the ragged last wave of the one-CTA-per-SM schedule — are split in two along the keys (CTA pairs) and merged by
+  // whichever half finishes second, so that wave costs half a tile time instead of a whole one.
+  int n_qt, heads, n_whole;
+  float* part;                      // per half: O [128][64] f32 (unnormalised, relative to m), m [128], l [128]
+  int* counters;                    // per split item: arrival counter (zeroed before the launch)
 };
+#define FA_PART_FLOATS (FA_BM * FA_D + 2 * FA_BM)
+#define FA_MAX_SPLITS 128
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -133,15 +141,27 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t q_full, k_full[FA_KV_STAGES], k_empty[FA_KV_STAGES], v_full[FA_KV_STAGES], v_empty[FA_KV_STAGES];
   __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2], m_ready[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int merge_flag_s;
   __shared__ float mrun_s[FA_BM];                                  // running row maximum after the latest block (log2 units)
   __shared__ float lsum_s[4][FA_BM];                               // per (group, column half) row sums for the final exchange
   __shared__ float xch[2][2][2][FA_BM];                            // [group][block parity of the group][column half][row]: row-max exchange
 
-  const AttnProblem pr = p.prob[blockIdx.z];
-  const int q0 = blockIdx.x * FA_BM;
-  if (q0 >= pr.nq) return;                                        // uniform per CTA: safe before any barrier
+  int item = blockIdx.x, split = -1, half = 0;
+  if (item >= p.n_whole) {
+    const int k = item - p.n_whole;
+    split = k >> 1; half = k & 1;
+    item = p.n_whole + split;
+  }
+  const int qt = item % p.n_qt, h = (item / p.n_qt) % p.heads;
+  AttnProblem pr = p.prob[item / (p.n_qt * p.heads)];
+  const int q0 = qt * FA_BM;
+  if (q0 >= pr.nq) return;                                        // uniform per CTA (both halves of a split item): safe before any barrier
+  if (split >= 0) {                                               // my half of the key blocks
+    const int nb0 = ((pr.nk + FA_BN - 1) / FA_BN + 1) >> 1;
+    if (half == 0) pr.nk = min(pr.nk, nb0 * FA_BN);
+    else { pr.k_row0 += nb0 * FA_BN; pr.nk -= nb0 * FA_BN; }
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y;
   const int nblk = (pr.nk + FA_BN - 1) / FA_BN;
 
   if (threadIdx.x == 0) {
@@ -346,8 +366,39 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       uint32_t ov[16];
       tmem_ld16(tmem_O + lane_off + c0, ov);
       tc::tmem_ld_wait();
-      if (q0 + q < pr.nq) {
-        const float inv = 1.f / l;
+      float inv = 1.f / l;
+      bool store = true;
+      if (split >= 0) {
+        // ---- split item: publish my half (O, m, l); the half that arrives second merges both and writes the output
+        float* mine = p.part + (size_t)(split * 2 + half) * FA_PART_FLOATS;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(mine + q * FA_D + c0 + i) =
+              make_float4(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]), __uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
+        if (g == 0 && hf == 0) { mine[FA_BM * FA_D + q] = m_fin; mine[FA_BM * FA_D + FA_BM + q] = l; }
+        __threadfence();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 64) merge_flag_s = atomicAdd(p.counters + split, 1);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        store = merge_flag_s != 0;                                          // uniform over the CTA
+        if (store) {
+          __threadfence();
+          const float* oth = p.part + (size_t)(split * 2 + (half ^ 1)) * FA_PART_FLOATS;
+          const float mo = __ldcg(oth + FA_BM * FA_D + q), lo = __ldcg(oth + FA_BM * FA_D + FA_BM + q);
+          const float mm = fmaxf(m_fin, mo);
+          const float wa = ex2_approx(m_fin - mm), wb = ex2_approx(mo - mm);
+          inv = 1.f / (l * wa + lo * wb);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 o4 = __ldcg(reinterpret_cast<const float4*>(oth + q * FA_D + c0 + i));
+            ov[i] = __float_as_uint(__uint_as_float(ov[i]) * wa + o4.x * wb);
+            ov[i + 1] = __float_as_uint(__uint_as_float(ov[i + 1]) * wa + o4.y * wb);
+            ov[i + 2] = __float_as_uint(__uint_as_float(ov[i + 2]) * wa + o4.z * wb);
+            ov[i + 3] = __float_as_uint(__uint_as_float(ov[i + 3]) * wa + o4.w * wb);
+          }
+        }
+      }
+      if (store && q0 + q < pr.nq) {
         __nv_bfloat16* dst = p.O + (size_t)(pr.q_row0 + q0 + q) * p.ldo + h * FA_D + c0;
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
@@ -368,15 +419,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem, FA_TMEM_COLS);
 }
 
+extern "C" __attribute__((visibility("default"))) size_t i4d_attention_workspace_bytes(void) {
+  return (size_t)FA_MAX_SPLITS * 2 * FA_PART_FLOATS * sizeof(float) + FA_MAX_SPLITS * sizeof(int) + 256;
+}
+
 extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
     const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads, const int* problems_host, int n_problems,
-    float scale, void* O, int ldo, void* stream) {
+    float scale, void* O, int ldo, void* workspace, size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(X && O && problems_host, "null pointer");
   I4D_CHECK_ARG(n_problems >= 1 && n_problems <= FA_MAX_PROBLEMS && heads >= 1, "1..4 problems, heads >= 1");
   I4D_CHECK_ARG((ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "O must be 16-byte aligned with ldo % 8 == 0");
   I4D_CHECK_ARG(q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0, "column offsets must be multiples of 8");
   AttnParams p;
-  int max_nq = 0;
+  int max_nq = 0, min_nk = 0x7fffffff;
   for (int z = 0; z < FA_MAX_PROBLEMS; ++z) {
     if (z < n_problems) {
       p.prob[z] = AttnProblem{problems_host[4 * z], problems_host[4 * z + 1], problems_host[4 * z + 2], problems_host[4 * z + 3]};
@@ -384,6 +439,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
       I4D_CHECK_ARG(p.prob[z].q_row0 >= 0 && p.prob[z].k_row0 >= 0 && p.prob[z].q_row0 + p.prob[z].nq <= rows &&
                     p.prob[z].k_row0 + p.prob[z].nk <= rows, "row ranges outside the buffer");
       if (p.prob[z].nq > max_nq) max_nq = p.prob[z].nq;
+      if (p.prob[z].nk < min_nk) min_nk = p.prob[z].nk;
     } else {
       p.prob[z] = AttnProblem{0, 0, 0, 1};
     }
@@ -394,27 +450,35 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   p.O = reinterpret_cast<__nv_bfloat16*>(O); p.ldo = ldo;
   CUtensorMap tmX;
   if (int rc = i4d_make_tmap_2d_bf16(&tmX, X, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, FA_BN, FA_D)) return rc;
-  // share of exponentials on the FMA pipe: FA_POLY_MASK by default; I4D_FA_POLY=0|25|37|50 selects another build (experiments)
+  cudaStream_t st = (cudaStream_t)stream;
+  // one CTA per SM: n_items CTAs run in ceil(n_items / SMs) waves.  When the last wave fills less than half of the SMs its
+  // items are split in two along the keys (needs the caller's workspace and >= 4 key blocks per problem)
+  p.n_qt = i4d_cdiv(max_nq, FA_BM); p.heads = heads;
+  const int n_items = p.n_qt * heads * n_problems, sms = i4d_num_sms();
+  int rem = n_items % sms;
+  if (!(workspace && workspace_bytes >= i4d_attention_workspace_bytes() && n_items > sms && rem > 0 && 2 * rem <= sms &&
+        rem <= FA_MAX_SPLITS && min_nk >= 4 * FA_BN))
+    rem = 0;
+  p.n_whole = n_items - rem;
+  p.part = nullptr; p.counters = nullptr;
+  if (rem) {
+    uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    p.counters = reinterpret_cast<int*>(w);
+    p.part = reinterpret_cast<float*>(w + ((FA_MAX_SPLITS * sizeof(int) + 255) & ~(size_t)255) - 0);
+    I4D_CUDA_CALL(cudaMemsetAsync(p.counters, 0, FA_MAX_SPLITS * sizeof(int), st));
+  }
+  // share of exponentials on the FMA pipe: none by default (measured: no gain, the kernel is latency-bound around the MUFU pipe,
+  // DESIGN.md); I4D_FA_POLY=25 selects the 25 % build for experiments
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("I4D_FA_POLY");
-    const int pct = e ? atoi(e) : -1;
-    variant = pct == 0 ? 0 : pct == 25 ? 1 : pct == 37 ? 2 : pct == 50 ? 3 : 4;
+    variant = (e && atoi(e) == 25) ? 1 : 0;
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<FA_POLY_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }
-  dim3 grid(i4d_cdiv(max_nq, FA_BM), heads, n_problems);
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (variant) {
-    case 0: attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 1: attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 2: attn_tc_kernel<0xA8><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 3: attn_tc_kernel<0xAA><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    default: attn_tc_kernel<FA_POLY_MASK><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-  }
+  const int grid = n_items + rem;
+  if (variant == 1) attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
+  else attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }

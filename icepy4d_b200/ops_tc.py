@@ -14,6 +14,9 @@ from . import ops
 BF16 = torch.bfloat16
 
 
+_ATTN_WS = {}
+
+
 def _st():
     return N.current_stream()
 
@@ -38,8 +41,12 @@ def attention_tc(X: torch.Tensor, problems: Sequence[Tuple[int, int, int, int]],
     """X [rows, ld] bf16 holding Q/K/V column blocks; problems = [(q_row0, nq, k_row0, nk), ...]; out [rows, >=64*heads] bf16."""
     assert X.dtype == BF16 and out.dtype == BF16 and X.is_contiguous() and out.stride(1) == 1
     pr = np.ascontiguousarray(np.asarray(problems, dtype=np.int32).reshape(-1))
+    key = (X.device.index, torch.cuda.current_stream().cuda_stream)      # one split-merge scratch per device and stream
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        ws = _ATTN_WS[key] = torch.empty(N.lib().i4d_attention_workspace_bytes(), device=X.device, dtype=torch.uint8)
     N.call("i4d_attention_bf16_tc", X, X.shape[0], X.shape[1], int(q_col), int(k_col), int(v_col), int(heads), pr, len(problems),
-           float(scale), out, out.stride(0), _st())
+           float(scale), out, out.stride(0), ws, ws.numel(), _st())
     return out
 
 

@@ -110,10 +110,13 @@ int i4d_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float
                      void* stream);
 /* Flash attention, head_dim 64, on one bf16 buffer X [rows, ld] holding Q, K and V as column blocks
  * (q_col/k_col/v_col + 64*head).  problems_host: n_problems x {q_row0, nq, k_row0, nk} (host ints, 1..4 problems run in
- * one launch: both images of a self/cross layer).  O [rows, ldo] bf16, row-indexed like Q.
+ * one launch: both images of a self/cross layer).  O [rows, ldo] bf16, row-indexed like Q.  `workspace` (nullable,
+ * i4d_attention_workspace_bytes()) lets the kernel split the ragged last wave of its one-CTA-per-SM schedule along the keys.
  * Replaces superglue.py:87-93 and lightglue.py:108-130 on the throughput path. */
+size_t i4d_attention_workspace_bytes(void);
 int i4d_attention_bf16_tc(const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads,
-                          const int* problems_host, int n_problems, float scale, void* O, int ldo, void* stream);
+                          const int* problems_host, int n_problems, float scale, void* O, int ldo, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* row-major f32 -> bf16 with leading dimensions (cols % 4 == 0). */
 int i4d_f32_to_bf16(const float* X, int ldx, void* Y, int ldy, int rows, int cols, void* stream);
 

@@ -66,7 +66,7 @@ def _attn_ref(q, k, v, scale=0.125):
     return (torch.softmax(qh @ kh.transpose(1, 2) * scale, -1) @ vh).permute(1, 0, 2).reshape(q.shape[0], 256)
 
 
-@pytest.mark.parametrize("n0,n1", [(128, 128), (300, 200), (1000, 777), (64, 1), (513, 1025)])
+@pytest.mark.parametrize("n0,n1", [(128, 128), (300, 200), (1000, 777), (64, 1), (513, 1025), (2400, 2300)])   # the last one: 152 work items -> 4 are split along the keys and merged
 def test_attention_tc_self_and_cross(tc, n0, n1):
     gen = torch.Generator().manual_seed(n0 * 3 + n1)
     nt = n0 + n1
