@@ -30,6 +30,16 @@ def split_bf16(x, n):
     return parts
 
 
+def split_f16(x, n):
+    parts = []
+    r = x
+    for _ in range(n):
+        p = r.to(torch.float16).float()
+        parts.append(p)
+        r = r - p
+    return parts
+
+
 def tf32_round(x):
     i = x.view(torch.int32)
     i = (i + 0x1000) & ~0x1FFF        # round-to-nearest on the 13 dropped bits
@@ -55,6 +65,18 @@ def emu_conv(self, x, name, pad, relu=True):
     elif kind == "bf16x2":      # activations split, weights single bf16: x1*w1 + x2*w1
         x1, x2 = split_bf16(x, 2); (w1,) = split_bf16(w, 1)
         y = F.conv2d(x1, w1, b, padding=pad) + F.conv2d(x2, w1, None, padding=pad)
+    elif kind == "f16x1":       # single fp16 operands (11-bit mantissa both)
+        (x1,) = split_f16(x, 1); (w1,) = split_f16(w, 1)
+        y = F.conv2d(x1, w1, b, padding=pad)
+    elif kind == "f16x2":       # activations split in two fp16, weights single fp16: x1*w1 + x2*w1
+        x1, x2 = split_f16(x, 2); (w1,) = split_f16(w, 1)
+        y = F.conv2d(x1, w1, b, padding=pad) + F.conv2d(x2, w1, None, padding=pad)
+    elif kind == "f16x2w":      # weights split, activations single fp16: x1*w1 + x1*w2
+        (x1,) = split_f16(x, 1); w1, w2 = split_f16(w, 2)
+        y = F.conv2d(x1, w1, b, padding=pad) + F.conv2d(x1, w2, None, padding=pad)
+    elif kind == "f16x3":
+        x1, x2 = split_f16(x, 2); w1, w2 = split_f16(w, 2)
+        y = F.conv2d(x1, w1, b, padding=pad) + F.conv2d(x2, w1, None, padding=pad) + F.conv2d(x1, w2, None, padding=pad)
     elif kind == "bf16x6":
         x1, x2, x3 = split_bf16(x, 3); w1, w2, w3 = split_bf16(w, 3)
         y = F.conv2d(x1, w1, b, padding=pad)
@@ -84,9 +106,12 @@ def run(label):
 orig_backbone = sp_mod.SuperPointB200.backbone
 sp_mod.SuperPointB200._conv = emu_conv
 sp_mod.SuperPointB200._pool = lambda self, x: F.max_pool2d(x, 2, 2)
-for kind in ("f32", "tf32", "bf16x2", "bf16x3", "bf16x6"):
+KINDS = tuple(sys.argv[1].split(",")) if len(sys.argv) > 1 else ("f32", "tf32", "bf16x2", "bf16x3", "bf16x6")
+for kind in KINDS:
     MODE.update(kind=kind, f32_layers=())
     run(f"backbone {kind}")
+if len(sys.argv) > 1:
+    sys.exit(0)
 for layers in (("conv1a", "conv1b"), ("conv1a", "conv1b", "conv2a", "conv2b"), ("convPa", "convPb"), ("convPa", "convPb", "convDa", "convDb"),
                ("conv4a", "conv4b", "convPa", "convPb", "convDa", "convDb")):
     MODE.update(kind="tf32", f32_layers=layers)
