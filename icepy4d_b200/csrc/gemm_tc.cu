@@ -6,15 +6,19 @@
 //               mbarrier ring; it runs ahead across tile boundaries
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma M128 N128 K16, four per stage, into one of TWO TMEM accumulators,
 //               so the main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2..5  epilogue, thread = output row: tcgen05.ld 32 columns at a time -> alpha, bias (staged in shared memory), ReLU,
+//   warps 2..9  epilogue (two warpgroups, each takes every other 32-column chunk), thread = output row: tcgen05.ld 32 columns at a time -> alpha, bias (staged in shared memory), ReLU,
 //               + residual (R chunk brought in by TMA) -> results staged in 128B-swizzled shared memory and written with
-//               TMA stores (full 128-byte lines; rows/columns beyond M/N are clipped by the tensor map), double buffered
-//               so the store of chunk c overlaps the arithmetic of chunk c+1.
+//               TMA stores (full 128-byte lines; rows/columns beyond M/N are clipped by the tensor map).  The staging boxes
+//               form rings (8 boxes of 16 KB shared by the residual loads and the f32 / bf16 stores; the f32 and the bf16
+//               stores are issued by two different threads so each has its own bulk-group FIFO): a box is rewritten only
+//               several stores later — waiting for the PREVIOUS store to release its box (a ~2500-clk round trip through the
+//               TMA unit) cost 80 % of the time of the first version of this epilogue.
 // The previous version (one tile per CTA, each thread storing its own row with 16-byte st.global) spent its time in setup
 // latency and 12-wavefront stores: 21-38 us per SuperGlue layer GEMM (profiles/).
 //
 // Reference behaviour replaced: the Conv1d(k=1)/Linear layers of thirdparty/SuperGlue/models/superglue.py:51-61,
 // 100-128, 276-280 and thirdparty/LightGlue/lightglue/lightglue.py:133-216, 253-287 (cuBLAS sgemm via torch there).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/icepy4d_b200.h"
@@ -22,28 +26,34 @@
 #define GT_BM 128
 #define GT_BN 128
 #define GT_BK 64
-#define GT_STAGES 4
-#define GT_THREADS 192
+#define GT_STAGES 3
+#define GT_THREADS 320
 #define GT_STAGE_BYTES ((GT_BM + GT_BN) * GT_BK * 2)          // 32 KB
-#define GT_CHUNK_BYTES (GT_BM * 128)                            // 16 KB: 128 rows x 128 B (32 f32 or 64 bf16 columns)
-#define GT_OFF_C16 (GT_STAGES * GT_STAGE_BYTES)                 // 2 boxes of 128 rows x 64 bf16
-#define GT_OFF_C32 (GT_OFF_C16 + 2 * GT_CHUNK_BYTES)            // 2 buffers of 128 rows x 32 f32
-#define GT_OFF_R (GT_OFF_C32 + 2 * GT_CHUNK_BYTES)              // 2 buffers of 128 rows x 32 f32
-#define GT_OFF_BIAS (GT_OFF_R + 2 * GT_CHUNK_BYTES)             // 2 x 128 f32
-#define GT_SMEM_BYTES (GT_OFF_BIAS + 2 * GT_BN * 4)   // the dynamic segment is 1024-byte aligned (extern __align__(1024)): no slack needed
+#define GT_CHUNK_BYTES (GT_BM * 128)                            // 16 KB box: 128 rows x 128 B (32 f32 or 64 bf16 columns)
+#define GT_NBOX 8                                               // staging pool shared by the R loads and the C32 / C16 stores
+#define GT_OFF_POOL (GT_STAGES * GT_STAGE_BYTES)
+#define GT_OFF_BIAS (GT_OFF_POOL + GT_NBOX * GT_CHUNK_BYTES)    // 2 x 128 f32
+#define GT_SMEM_BYTES (GT_OFF_BIAS + 2 * GT_BN * 4)             // the dynamic segment is 1024-byte aligned (extern __align__(1024))
 
 struct GemmTcParams {
   int M, N, K;
   float alpha;
   const float* bias;
   int has_r, has_c32, has_c16, relu;
+  int dbg;   // experiments only (I4D_GEMM_DBG): 1 = no TMA stores, 2 = no proxy fence, 4 = no staging writes, 8 = no epilogue barrier
 };
 
 __device__ __forceinline__ void gt_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void gt_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void gt_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void gt_wait_read(int pending) {          // cp.async.bulk.wait_group.read needs an immediate
+  if (pending >= 6) asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory");
+  else if (pending >= 4) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+  else if (pending >= 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (p.has_c32) tc::prefetch_tmap(&tmC32);
     if (p.has_c16) tc::prefetch_tmap(&tmC16);
     for (int s = 0; s < GT_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 4); tc::mbar_init(&r_full[b], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 8); tc::mbar_init(&r_full[b], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, 2 * GT_BN);
@@ -119,19 +129,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------ epilogue: 4 warps, thread = output row of the tile
-    const int e = threadIdx.x - 64;                                  // 0..127
+    // ------------------------------------------------ epilogue: 8 warps = two warpgroups; thread = output row of the tile,
+    // warpgroup wg takes the 32-column chunks c = wg, wg + 2 of every tile (one "step" = two chunks side by side)
+    const int e = threadIdx.x - 64;                                  // 0..255
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;                                          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                                   // row of the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t rsw = (uint32_t)(row & 7);
-    uint8_t* sC16 = smem + GT_OFF_C16;
-    uint8_t* sC32 = smem + GT_OFF_C32;
-    uint8_t* sR = smem + GT_OFF_R;
+    // staging pool of 16 KB boxes: [R x2 if has_r][C32 ring][C16 ring]
+    const int nR = p.has_r ? 2 : 0;
+    const int n32 = p.has_c32 ? (p.has_c16 ? 4 : GT_NBOX - nR) : 0;
+    const int n16 = p.has_c16 ? GT_NBOX - nR - n32 : 0;
+    uint8_t* sR = smem + GT_OFF_POOL;
+    uint8_t* sC32 = sR + nR * GT_CHUNK_BYTES;
+    uint8_t* sC16 = sC32 + n32 * GT_CHUNK_BYTES;
     float* sBias = reinterpret_cast<float*>(smem + GT_OFF_BIAS);
-    const bool leader = (e == 0);
-    uint32_t g = 0, i = 0;                                           // g: 32-column chunks consumed so far (all tiles)
-    // R chunk `gc` (counted over all of this CTA's tiles) -> buffer gc & 1
+    const bool lead32 = (e == 0), lead16 = (e == 32);                // two leaders: each owns the bulk-group FIFO of its stores
+    uint32_t i = 0;
+    // R chunk `gc` (counted over all of this CTA's tiles, 4 per tile) -> buffer gc & 1
     auto issue_r = [&](uint32_t gc) {
       const uint32_t ti = gc >> 2, c = gc & 3;
       const long long t = (long long)blockIdx.x + (long long)ti * gridDim.x;
@@ -140,21 +156,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::mbar_arrive_expect_tx(&r_full[gc & 1], GT_CHUNK_BYTES);
       tc::tma_load_2d(sR + (gc & 1) * GT_CHUNK_BYTES, &tmR, &r_full[gc & 1], n0 + (int)c * 32, m0);
     };
-    if (leader && p.has_r) { issue_r(0); issue_r(1); }
+    if (lead32 && p.has_r) { issue_r(0); issue_r(1); }
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
       const uint32_t b = i & 1;
       float* bs = sBias + b * GT_BN;
-      bs[e] = p.bias ? __ldg(p.bias + min(n0 + e, p.N - 1)) : 0.f;
+      if (e < GT_BN) bs[e] = p.bias ? __ldg(p.bias + min(n0 + e, p.N - 1)) : 0.f;
       gt_epi_bar();                                                  // bias staged (its previous user, tile i-2, is long done)
       tc::mbar_wait(&acc_full[b], (i >> 1) & 1);
       tc::tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < GT_BN / 32; ++c, ++g) {
+      for (int st = 0; st < 2; ++st) {
+        const int c = 2 * st + wg;                                   // my chunk of this step
+        const uint32_t S = 2 * i + st;                               // global step index
+        const uint32_t g = 2 * S + wg;                               // global chunk index
         uint32_t v[32];
         tc::tmem_ld32(tmem_d + lane_off + b * GT_BN + c * 32, v);
         tc::tmem_ld_wait();
-        if (c == GT_BN / 32 - 1) {                                   // accumulator drained: hand it back to the MMA warp
+        if (st == 1) {                                               // accumulator drained: hand it back to the MMA warp
           tc::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
@@ -171,24 +190,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (p.has_r) {
-          tc::mbar_wait(&r_full[g & 1], (g >> 1) & 1);
-          const uint8_t* rb = sR + (g & 1) * GT_CHUNK_BYTES + row * 128;
+          tc::mbar_wait(&r_full[wg], S & 1);                         // R chunk g lives in buffer g & 1 = wg; its S-th use
+          const uint8_t* rb = sR + wg * GT_CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 r4 = *reinterpret_cast<const float4*>(rb + ((((uint32_t)j) ^ rsw) << 4));
             f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
           }
         }
-        // staging buffers about to be written were handed to TMA stores at least one chunk ago: the leader waited for those
-        // stores to finish reading before the previous barrier
+        // The boxes written below were released by their previous stores: the leaders waited for that before the barrier of the
+        // PREVIOUS step (C32 box g % n32: store g - n32; C16 box S % n16: store S - n16).
         if (p.has_c32) {
-          uint8_t* cb = sC32 + (g & 1) * GT_CHUNK_BYTES + row * 128;
+          uint8_t* cb = sC32 + (g % (uint32_t)n32) * GT_CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(cb + ((((uint32_t)j) ^ rsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
-        if (p.has_c16) {
-          uint8_t* hb = sC16 + (c >> 1) * GT_CHUNK_BYTES + row * 128;
+        if (p.has_c16 && !(p.dbg & 4)) {
+          uint8_t* hb = sC16 + (S % (uint32_t)n16) * GT_CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 a = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), b2 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
@@ -196,21 +215,34 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             uint4 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
             pk.z = *reinterpret_cast<uint32_t*>(&c2); pk.w = *reinterpret_cast<uint32_t*>(&d);
-            *reinterpret_cast<uint4*>(hb + ((((uint32_t)((c & 1) * 4 + j)) ^ rsw) << 4)) = pk;
+            *reinterpret_cast<uint4*>(hb + ((((uint32_t)(wg * 4 + j)) ^ rsw) << 4)) = pk;
           }
         }
-        tc::fence_proxy_async_smem();                                // my staged results -> visible to the TMA engine
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores issued one chunk ago have read their buffers
-        gt_epi_bar();
-        if (leader) {
-          if (p.has_c32) gt_tma_store_2d(&tmC32, sC32 + (g & 1) * GT_CHUNK_BYTES, n0 + c * 32, m0);
-          if (p.has_c16 && (c & 1)) gt_tma_store_2d(&tmC16, sC16 + (c >> 1) * GT_CHUNK_BYTES, n0 + (c >> 1) * 64, m0);
+        if (!(p.dbg & 2)) tc::fence_proxy_async_smem();              // my staged results -> visible to the TMA engine
+        // ring discipline: before anybody writes the next step's boxes, the stores that last used them must have read them.
+        //   C32 (two stores per step): next step writes boxes (g0+2, g0+3) % n32, last used by stores g0+2-n32, g0+3-n32; this
+        //        leader has issued stores <= g0-1, so at most n32 - 4 of them may still be pending.
+        //   C16 (one store per step): next step writes box (S+1) % n16, last used by store S+1-n16: at most n16 - 2 pending.
+        if (lead32 && p.has_c32) gt_wait_read(n32 - 4);
+        if (lead16 && p.has_c16) gt_wait_read(n16 - 2);
+        if (!(p.dbg & 8)) gt_epi_bar();
+        if (lead32) {
+          if (p.has_c32) {
+            const uint32_t g0 = 2 * S;
+            gt_tma_store_2d(&tmC32, sC32 + (g0 % (uint32_t)n32) * GT_CHUNK_BYTES, n0 + (2 * st) * 32, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            gt_tma_store_2d(&tmC32, sC32 + ((g0 + 1) % (uint32_t)n32) * GT_CHUNK_BYTES, n0 + (2 * st + 1) * 32, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (p.has_r) { issue_r(2 * S + 2); issue_r(2 * S + 3); }   // every reader of both R buffers has passed the barrier
+        }
+        if (lead16 && p.has_c16 && !(p.dbg & 1)) {
+          gt_tma_store_2d(&tmC16, sC16 + (S % (uint32_t)n16) * GT_CHUNK_BYTES, n0 + st * 64, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (p.has_r) issue_r(g + 2);                               // every reader of this R buffer has passed the barrier
         }
       }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lead32 || lead16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -301,7 +333,9 @@ extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
     I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
     attr_set = true;
   }
-  GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("I4D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+  GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu, dbg};
   const int n_tiles = i4d_cdiv(N, GT_BN) * i4d_cdiv(M, GT_BM);
   const int grid = n_tiles < i4d_num_sms() ? n_tiles : i4d_num_sms();
   gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
