@@ -778,7 +778,7 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
 
 __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, float alpha,
                                                                        int iters, float* u, float* v, float* pm, float* ps,
-                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct) {
+                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct, int dbg) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
   __shared__ __align__(8) uint64_t full[SK_STAGES], bpart[2];
@@ -870,13 +870,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     __syncthreads();
     if (fast) sk_band_fast(ctx, rg, vraw);
     else sk_band_exact(ctx, rg, vraw);
-    grid_barrier();
+    if (!(dbg & 4)) grid_barrier(); else __syncthreads();
     // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
     {
       const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
       // one warp per 4-column tile: lane l sums the partials of CTAs l, l + 32, ... for all four columns (independent 16-byte
       // loads), a butterfly over the lanes finishes the sums and lanes 0..3 each finalise one column.
-      for (int tile = cta * SK_WARPS + warp; tile < n4; tile += G * SK_WARPS) {
+      for (int tile = cta * SK_WARPS + warp; tile < ((dbg & 1) ? 0 : n4); tile += G * SK_WARPS) {
         if (fast) {
           float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 5
@@ -935,8 +935,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
         }
       }
     }
-    grid_barrier();
-    if (fast_ok && __ldcg(flag) != 0) {
+    if (!(dbg & 2)) grid_barrier(); else __syncthreads();
+    if (fast_ok && __ldcg(flag) != 0 && !dbg) {
       // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode
       fast_ok = false;
       for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
@@ -990,8 +990,10 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
     keep_pct = e ? atoi(e) : SK_KEEP_PCT_DEFAULT;
     if (keep_pct < 0 || keep_pct > 100) keep_pct = SK_KEEP_PCT_DEFAULT;
   }
+  static int dbg = -1;           // timing experiments only (I4D_SK_DBG): 1 = no column combine, 2 = no second grid barrier, 4 = no first one
+  if (dbg < 0) { const char* e = getenv("I4D_SK_DBG"); dbg = e ? atoi(e) : 0; }
   void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
-                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct};
+                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct, (void*)&dbg};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;
