@@ -7,6 +7,8 @@
 //                                      iterations of the Brown model, f64 inside, f32 out)
 //   thirdparty/triangulation.py:79-177 iterative_LS_triangulation (Hartley-Sturm, <= 10 iterations, tolerance 3e-5)
 //   sfm/triangulation.py:154-183       triangulate_points_linear / triangulate_nviews (6x6 SVD null vector)
+//   sfm/interpolate_colors.py:14-87, sfm/geometry.py:78-100  interpolate_point_colors: cv2.projectPoints (Brown model, f64,
+//                                      result cast to f32) + bilinear interpolation with clipped neighbours
 #include "common.cuh"
 #include "../../include/icepy4d_b200.h"
 
@@ -185,6 +187,62 @@ __global__ void __launch_bounds__(64) tri_dlt_kernel(const float* __restrict__ x
   for (int j = 0; j < 6; ++j)
     if (j == jmin) { v0 = V[j][0]; v1 = V[j][1]; v2 = V[j][2]; v3 = V[j][3]; }
   X[3 * (size_t)idx + 0] = v0 / v3; X[3 * (size_t)idx + 1] = v1 / v3; X[3 * (size_t)idx + 2] = v2 / v3;
+}
+
+struct CamRt { double R[9]; double t[3]; double K[9]; double d[5]; };
+
+// sfm/interpolate_colors.py:14-87: project every 3-D point with the Brown model (the arithmetic of cv2.projectPoints, f64, result
+// rounded to f32 like `project_points` does), then bilinear interpolation of image / 255 with the reference's clipped-neighbour
+// weights (x1, y1 are clipped BEFORE the weights are formed, interpolate_colors.py:63-80).  One thread per point.
+__global__ void __launch_bounds__(256) project_colors_kernel(const double* __restrict__ X, int n, CamRt c,
+                                                             const unsigned char* __restrict__ img, int H, int W, int C,
+                                                             int swap_rb, double* __restrict__ col, float* __restrict__ proj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double Xw = X[3 * (size_t)i], Yw = X[3 * (size_t)i + 1], Zw = X[3 * (size_t)i + 2];
+  double x = Xw * c.R[0] + Yw * c.R[1] + Zw * c.R[2] + c.t[0];
+  double y = Xw * c.R[3] + Yw * c.R[4] + Zw * c.R[5] + c.t[1];
+  double z = Xw * c.R[6] + Yw * c.R[7] + Zw * c.R[8] + c.t[2];
+  z = z != 0.0 ? 1.0 / z : 1.0;
+  x *= z; y *= z;
+  const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+  const double a1 = 2.0 * x * y, a2 = r2 + 2.0 * x * x, a3 = r2 + 2.0 * y * y;
+  const double cdist = 1.0 + c.d[0] * r2 + c.d[1] * r4 + c.d[4] * r6;
+  const double xd = x * cdist + c.d[2] * a1 + c.d[3] * a2;
+  const double yd = y * cdist + c.d[2] * a3 + c.d[3] * a1;
+  const float uf = (float)(xd * c.K[0] + c.K[2]), vf = (float)(yd * c.K[4] + c.K[5]);
+  if (proj) { proj[2 * (size_t)i] = uf; proj[2 * (size_t)i + 1] = vf; }
+  const double u = (double)uf, v = (double)vf;
+  int x0 = (int)floor(u), y0 = (int)floor(v);
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = min(max(x0, 0), W - 1); x1 = min(max(x1, 0), W - 1);
+  y0 = min(max(y0, 0), H - 1); y1 = min(max(y1, 0), H - 1);
+  const double wa = ((double)x1 - u) * ((double)y1 - v), wb = ((double)x1 - u) * (v - (double)y0);
+  const double wc = (u - (double)x0) * ((double)y1 - v), wd = (u - (double)x0) * (v - (double)y0);
+  for (int ch = 0; ch < C; ++ch) {
+    const int sc = (swap_rb && C == 3) ? 2 - ch : ch;                   // cv2.cvtColor(image, COLOR_BGR2RGB)
+    const double Ia = (double)((float)img[((size_t)y0 * W + x0) * C + sc] / 255.0f);
+    const double Ib = (double)((float)img[((size_t)y1 * W + x0) * C + sc] / 255.0f);
+    const double Ic = (double)((float)img[((size_t)y0 * W + x1) * C + sc] / 255.0f);
+    const double Id = (double)((float)img[((size_t)y1 * W + x1) * C + sc] / 255.0f);
+    col[(size_t)i * C + ch] = wa * Ia + wb * Ib + wc * Ic + wd * Id;
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_interpolate_point_colors(
+    const double* X, int n, const double* R_host, const double* t_host, const double* K_host, const double* dist_host, int n_dist,
+    const unsigned char* image, int H, int W, int C, int convert_bgr2rgb, double* colors, float* projections, void* stream) {
+  I4D_CHECK_ARG(X && R_host && t_host && K_host && image && colors && n >= 0, "null pointer");
+  I4D_CHECK_ARG(H > 0 && W > 0 && C >= 1 && C <= 4, "image must be H x W x C with 1 <= C <= 4");
+  I4D_CHECK_ARG(n_dist >= 0 && n_dist <= 5, "only the k1,k2,p1,p2[,k3] Brown model is supported");
+  if (n == 0) return I4D_OK;
+  CamRt c;
+  for (int i = 0; i < 9; ++i) { c.R[i] = R_host[i]; c.K[i] = K_host[i]; }
+  for (int i = 0; i < 3; ++i) c.t[i] = t_host[i];
+  for (int i = 0; i < 5; ++i) c.d[i] = (dist_host && i < n_dist) ? dist_host[i] : 0.0;
+  project_colors_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(X, n, c, image, H, W, C, convert_bgr2rgb, colors, projections);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int i4d_undistort_points(const float* pts, int n, const double* K_host, const double* dist_host,

@@ -299,6 +299,27 @@ def undistort_points(pts: torch.Tensor, K: np.ndarray, dist: np.ndarray) -> torc
     return out
 
 
+def interpolate_point_colors(points3d: torch.Tensor, image_u8: torch.Tensor, R, t, K, dist, convert_bgr2rgb: bool = True,
+                             want_projections: bool = False):
+    """points3d [n,3] f64 and image [H,W,C] u8 on the device -> colors [n,C] f64 (and projections [n,2] f32)."""
+    assert points3d.is_cuda and points3d.dtype == torch.float64 and points3d.is_contiguous() and points3d.shape[1] == 3
+    assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous() and image_u8.dim() == 3
+    Rh = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(9))
+    th = np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(3))
+    Kh = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    dh = np.ascontiguousarray(np.asarray(dist, dtype=np.float64).reshape(-1))
+    if dh.size > 5 and np.any(dh[5:] != 0):
+        raise ValueError("only the 5-parameter Brown model (k1,k2,p1,p2,k3) is supported")
+    dh = np.ascontiguousarray(dh[:5])
+    n = points3d.shape[0]
+    H, W, C = image_u8.shape
+    col = torch.empty((n, C), device=points3d.device, dtype=torch.float64)
+    proj = torch.empty((n, 2), device=points3d.device, dtype=torch.float32) if want_projections else None
+    N.call("i4d_interpolate_point_colors", points3d, n, Rh, th, Kh, dh, int(dh.size), image_u8, H, W, C, int(bool(convert_bgr2rgb)),
+           col, proj, _st())
+    return (col, proj) if want_projections else col
+
+
 def triangulate_iterative_ls(u1: torch.Tensor, u2: torch.Tensor, P1: np.ndarray, P2: np.ndarray, tol: float = 3e-5):
     _chk(u1), _chk(u2)
     n = u1.shape[0]

@@ -42,7 +42,19 @@ class Triangulate:
             self.points3d = X.cpu().numpy()
             if compute_colors:
                 assert image is not None and type(image) == np.ndarray, "Invalid input image for interpolating point colors"
-                raise NotImplementedError("colour interpolation is downstream of the B200 hot path (SURVEY.md §8f rank 4)")
+                self.interpolate_colors_from_image(image, self.cameras[cam_id], _points_dev=X)
         elif approach == "linear_triangulation":
             self.points3d = ops.triangulate_dlt(u0, u1, P0, P1).cpu().numpy()
         return self.points3d
+
+    def interpolate_colors_from_image(self, image: np.ndarray, camera, convert_BRG2RGB: bool = True, _points_dev=None):
+        """sfm/triangulation.py:133-148 + sfm/interpolate_colors.py:14-51: project the triangulated points into `image` with the
+        camera's Brown model and interpolate the colours bilinearly (values in [0, 1], Nx(channels) f64)."""
+        assert self.points3d is not None, "points 3D are not available, Triangulate homologous points first."
+        assert image.ndim == 3, "invalid input image. Image has not 3 channel"
+        X = _points_dev if _points_dev is not None else torch.as_tensor(np.ascontiguousarray(self.points3d, dtype=np.float64)).cuda()
+        img = torch.as_tensor(np.ascontiguousarray(image, dtype=np.uint8)).cuda()
+        self.colors = ops.interpolate_point_colors(X.contiguous(), img, camera.R, camera.t, camera.K, camera.dist,
+                                                   convert_bgr2rgb=convert_BRG2RGB).cpu().numpy()
+        logging.info("Point colors interpolated")
+        return self.colors

@@ -156,6 +156,14 @@ int i4d_triangulate_iterative_ls(const float* u1, const float* u2, int n, const 
 int i4d_triangulate_dlt(const float* x1, const float* x2, int n, const double* P1_host, const double* P2_host,
                         double* X, void* stream);
 
+/* sfm/interpolate_colors.py:14-87 + sfm/geometry.py:78-100 — colours of 3-D points from an oriented image: Brown-model
+ * projection (cv2.projectPoints arithmetic, f64, rounded to f32) and bilinear interpolation of image / 255 with the
+ * reference's clipped-neighbour weights.  X [n,3] f64 and image [H,W,C] u8 on the device; R [9], t [3], K [9], dist on the
+ * host.  colors [n,C] f64; projections [n,2] f32 (nullable). */
+int i4d_interpolate_point_colors(const double* X, int n, const double* R_host, const double* t_host, const double* K_host,
+                                 const double* dist_host, int n_dist, const unsigned char* image, int H, int W, int C,
+                                 int convert_bgr2rgb, double* colors, float* projections, void* stream);
+
 /* matching/geometric_verification.py:43-102 and sfm/two_view_geometry.py:127-197 — robust fundamental matrix.
  * Batched-hypothesis RANSAC (8-point samples drawn from `seed`, consensus with a truncated quadratic of cut-off
  * 3.64*sigma_max on the Sampson error) + sigma-consensus IRLS polish (`polish_iters` weighted 8-point solves),

@@ -122,3 +122,36 @@ def estimate_pose(kpts0: np.ndarray, kpts1: np.ndarray, K0: np.ndarray, K1: np.n
         if n > best:
             best, ret = n, (R, t[:, 0], mask.ravel() > 0)
     return ret
+
+
+def project_points(points3d: np.ndarray, R: np.ndarray, t: np.ndarray, K: np.ndarray, dist: np.ndarray) -> np.ndarray:
+    """sfm/geometry.py:78-100 restated: cv2.Rodrigues + cv2.projectPoints, result cast to float32."""
+    rvec, _ = cv2.Rodrigues(np.asarray(R, dtype=np.float64))
+    m, _ = cv2.projectPoints(np.expand_dims(np.asarray(points3d, dtype=np.float64), 1), rvec, np.asarray(t, dtype=np.float64),
+                             np.asarray(K, dtype=np.float64), np.asarray(dist, dtype=np.float64))
+    return m[:, 0, :].astype("float32")
+
+
+def bilinear_interpolate(im: np.ndarray, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """sfm/interpolate_colors.py:54-87 restated (neighbours are clipped before the weights are formed)."""
+    x, y = np.asarray(x), np.asarray(y)
+    x0 = np.floor(x).astype(int); x1 = x0 + 1
+    y0 = np.floor(y).astype(int); y1 = y0 + 1
+    x0 = np.clip(x0, 0, im.shape[1] - 1); x1 = np.clip(x1, 0, im.shape[1] - 1)
+    y0 = np.clip(y0, 0, im.shape[0] - 1); y1 = np.clip(y1, 0, im.shape[0] - 1)
+    Ia, Ib, Ic, Id = im[y0, x0], im[y1, x0], im[y0, x1], im[y1, x1]
+    wa = (x1 - x) * (y1 - y); wb = (x1 - x) * (y - y0); wc = (x - x0) * (y1 - y); wd = (x - x0) * (y - y0)
+    return wa * Ia + wb * Ib + wc * Ic + wd * Id
+
+
+def interpolate_point_colors(points3d, image, R, t, K, dist, convert_BRG2RGB=True) -> np.ndarray:
+    """sfm/interpolate_colors.py:14-51 restated."""
+    assert image.ndim == 3
+    if convert_BRG2RGB:
+        image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+    proj = project_points(points3d, R, t, K, dist)
+    image = image.astype(np.float32) / 255.0
+    col = np.zeros((len(points3d), image.shape[2]))
+    for ch in range(image.shape[2]):
+        col[:, ch] = bilinear_interpolate(image[:, :, ch], proj[:, 0], proj[:, 1])
+    return col

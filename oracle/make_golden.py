@@ -193,6 +193,25 @@ def golden_pose():
     print("pose: inliers", int(inl.sum()), "of", len(inl), "true", int(sc["inlier"].sum()), "rotation error deg", float(ang))
 
 
+def golden_colors():
+    """sfm/interpolate_colors.py:14-51 run from the reference itself (its Camera class is not needed: a SimpleCamera has the
+    R, t, K, dist attributes project_points reads)."""
+    ref_shims.install_shims()
+    from icepy4d.sfm.interpolate_colors import interpolate_point_colors
+
+    sc = synthetic.two_view_scene(n=1500, seed=13, outlier_frac=0.0)
+    cam = sc["cams"][1]
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (4008, 6012, 3), dtype=np.uint8)
+    X = sc["X"].copy()
+    X[:40] *= 3.0                                  # some points project outside the image: exercises the clipped weights
+    col = interpolate_point_colors(X, img, cam, convert_BRG2RGB=True)
+    # keep the fixture small: only the image rows/cols the points touch are needed -> store the image seed instead
+    np.savez_compressed(os.path.join(OUT, "colors.npz"), X=X, R=cam.R, t=cam.t, K=cam.K, dist=cam.dist, img_seed=5,
+                        img_shape=np.array(img.shape), colors=col)
+    print("colors: mean", col.mean(0))
+
+
 if __name__ == "__main__":
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -201,6 +220,7 @@ if __name__ == "__main__":
     golden_tiler_quality()
     golden_geometry()
     golden_pose()
+    golden_colors()
     golden_superpoint_superglue()
     golden_lightglue()
     golden_matchers()
