@@ -216,7 +216,8 @@ def run_ours(args):
         pipe.run_device(*dev[s % pool])
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                       # one nvidia-smi poller per box (eight of them perturb an 8-GPU run through the driver lock)
+        sampler.start()
     n0 = _native.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -227,7 +228,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _native.LAUNCHES - n0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     n_matches = int(last["mkpts0"].shape[0])
 
     # ---- end to end through the public API: pinned host images -> host arrays ----
