@@ -285,7 +285,7 @@ def main():
     # bf16 = the tcgen05 tensor-core matcher (bf16 operands, f32 accumulation; match IoU vs the f32 reference >= 0.999,
     # tests/test_gpu_tc.py); f32 = the SIMT f32 matcher kept as the on-device cross-check
     ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
-    ap.add_argument("--conv-precision", dest="conv_precision", default="bf16x3", choices=["bf16x3", "f32", "tf32", "f16", "bf16"])
+    ap.add_argument("--conv-precision", dest="conv_precision", default="f16x3", choices=["bf16x3", "f16x3", "f32", "tf32", "f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,6 +21,7 @@
 //
 // Reference behaviour replaced: conv1b..convDb of thirdparty/SuperGlue/models/superpoint.py:154-168,193-196 (and the
 // LightGlue copy, lightglue/superpoint.py:155-170,189-192), which run as f32 cuDNN/MKL convolutions there.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/icepy4d_b200.h"
@@ -36,7 +37,27 @@ struct ConvTcParams {
   __nv_bfloat16* y_hi; __nv_bfloat16* y_lo; int ld16;
   float* y32; int ld32; int planar;
   int cout;
+  int fmt;          // 16-bit operand format of the split planes and weights: 0 = IEEE half (f16x3), 1 = bfloat16 (bf16x3)
 };
+
+// v -> (hi, lo) pair of 16-bit values, packed two by two: hi = round16(v), lo = round16(v - hi).  bf16x3 carries 16 mantissa
+// bits, f16x3 22 (exact f32 products of the three partial MMAs either way); halves are clamped to the finite f16 range.
+__device__ __forceinline__ void cv_split2(float a, float b, int fmt, uint32_t& hi, uint32_t& lo) {
+  if (fmt) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
 
 template <int N_T, int T> struct ConvCfg {
   static constexpr int ACC_COLS = 2 * N_T;                       // [x_hi*w_hi + x_lo*w_hi | x_hi*w_lo]
@@ -121,8 +142,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 2) {
     // ---- MMA issuer: one elected lane; descriptors advance by adding (bytes >> 4) to a precomputed low word ----
     if (tc::elect_one()) {
-      constexpr uint32_t idesc_cat = tc::make_idesc(128, 2 * N_T, 0, 0, 1);
-      constexpr uint32_t idesc_hi = tc::make_idesc(128, N_T, 0, 0, 1);
+      const uint32_t idesc_cat = tc::make_idesc(128, 2 * N_T, 0, 0, p.fmt);
+      const uint32_t idesc_hi = tc::make_idesc(128, N_T, 0, 0, p.fmt);
       constexpr uint32_t b_hiword = tc::desc_hi_sw128(1024);
       const uint32_t a_hiword = tc::desc_hi_sw128((uint32_t)bw * 128);
       const uint32_t a_lo0 = tc::desc_lo_sw128(tc::smem_u32(a_base)), b_lo0 = tc::desc_lo_sw128(tc::smem_u32(b_base));
@@ -218,13 +239,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
           if (gx < Wo && gy < Ho) {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(z[j], z[j + 1]);
-              const float2 hf = __bfloat1622float2(h);
-              const __nv_bfloat162 l = __floats2bfloat162_rn(z[j] - hf.x, z[j + 1] - hf.y);
-              hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-            }
+            for (int j = 0; j < 8; j += 2) cv_split2(z[j], z[j + 1], p.fmt, hi[j >> 1], lo[j >> 1]);
             const size_t o = ((size_t)gy * Wo + gx) * p.ld16 + ch0 + (odd ? 16 : 0) + (up ? 8 : 0);
             *reinterpret_cast<uint4*>(p.y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(p.y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -236,13 +251,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
         if (p.y_hi) {
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f[j], f[j + 1]);
-            const float2 hf = __bfloat1622float2(h);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(f[j] - hf.x, f[j + 1] - hf.y);
-            hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-          }
+          for (int j = 0; j < 32; j += 2) cv_split2(f[j], f[j + 1], p.fmt, hi[j >> 1], lo[j >> 1]);
           uint4* oh = reinterpret_cast<uint4*>(p.y_hi + pix * p.ld16 + ch0);
           uint4* ol = reinterpret_cast<uint4*>(p.y_lo + pix * p.ld16 + ch0);
 #pragma unroll
@@ -308,10 +317,11 @@ extern "C" __attribute__((visibility("default"))) int i4d_conv_tile_cout(int cou
 
 extern "C" __attribute__((visibility("default"))) int i4d_conv_bf16x3_tc(
     const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_packed, const float* bias, int cout_pad, int cout,
-    int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32, int y32_planar, void* stream) {
+    int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32, int y32_planar, int operand_format, void* stream) {
   I4D_CHECK_ARG(x_hi && x_lo && w_packed && bias, "null pointer");
   I4D_CHECK_ARG(H > 0 && W > 0 && Cin > 0 && Cin % 64 == 0, "Cin must be a positive multiple of 64");
   I4D_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
+  I4D_CHECK_ARG(operand_format == 0 || operand_format == 1, "operand_format: 0 = f16 split planes, 1 = bf16 split planes");
   I4D_CHECK_ARG(cout_pad > 0 && cout_pad % 64 == 0 && cout_pad <= 512 && cout > 0 && cout <= cout_pad, "bad output channel counts");
   I4D_CHECK_ARG((y_hi != nullptr) == (y_lo != nullptr) && (y_hi || y32), "need split planes and/or an f32 output");
   I4D_CHECK_ARG(!pool || (!y32 && H >= 2 && W >= 2), "the fused 2x2 max-pool writes split planes only");
@@ -323,7 +333,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_conv_bf16x3_tc(
   ConvTcParams p{};
   p.H = H; p.W = W; p.KC = Cin / 64; p.taps = taps; p.NT = cout_pad / n_t; p.halo = halo; p.relu = relu; p.pool = pool;
   p.bias = bias; p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
-  p.ld16 = cout_pad; p.y32 = y32; p.ld32 = ld32; p.planar = y32_planar; p.cout = cout;
+  p.ld16 = cout_pad; p.y32 = y32; p.ld32 = ld32; p.planar = y32_planar; p.cout = cout; p.fmt = operand_format;
   CUtensorMap tmHi, tmLo, tmW;
   const uint32_t bw = 8 * T + 2 * halo, bh = CV_TILE_H + 2 * halo;
   if (int rc = i4d_make_tmap_hwc_bf16(&tmHi, x_hi, (uint64_t)H, (uint64_t)W, (uint64_t)Cin, bh, bw)) return rc;

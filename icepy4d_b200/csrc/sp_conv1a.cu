@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sp_conv1a_kernel(const float* __restrict_
 // fetched once (18 LDS.128 from a [tap][channel] table) and reused for the 4 pixels, so the kernel is bound by its 16-byte
 // stores (8 lanes = the 128 contiguous bytes of one pixel per plane) instead of by shared-memory weight reads.
 __global__ void __launch_bounds__(256) sp_conv1a_split_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ wgt,
-                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int fmt) {
   __shared__ __align__(16) float w_s[9 * 64];
   __shared__ __align__(16) float b_s[64];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) w_s[(i % 9) * 64 + i / 9] = wgt[i];      // [ch][tap] -> [tap][ch]
@@ -118,11 +118,19 @@ __global__ void __launch_bounds__(256) sp_conv1a_split_kernel(const float* __res
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
       const float a = fmaxf(acc[px][c], 0.f), b = fmaxf(acc[px][c + 1], 0.f);
-      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-      const float2 hf = __bfloat1622float2(h);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-      hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+      if (fmt) {                                                     // bf16 (hi, lo)
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+      } else {                                                       // IEEE half (hi, lo)
+        const __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(fminf(a, 65504.f) - hf.x, fminf(b, 65504.f) - hf.y);
+        hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+      }
     }
     __nv_bfloat16* o = out + ((size_t)y * W + x0 + px) * 64 + cg * 8;
     *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -182,7 +190,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_conv1a_relu(const f
                                                                         const float* bias, void* out_nhwc, int out_dtype,
                                                                         void* stream) {
   I4D_CHECK_ARG(image && weight && bias && out_nhwc && H > 0 && W > 0, "null pointer or empty image");
-  I4D_CHECK_ARG(out_dtype >= 0 && out_dtype <= 3, "out_dtype: 0 = f32, 1 = f16, 2 = bf16, 3 = split bf16 planes");
+  I4D_CHECK_ARG(out_dtype >= 0 && out_dtype <= 4, "out_dtype: 0 = f32, 1 = f16, 2 = bf16, 3 = split bf16 planes, 4 = split f16 planes");
   const long long threads = (long long)H * W * 4;
   const int grid = i4d_cdiv(threads, 256);
   cudaStream_t st = (cudaStream_t)stream;
@@ -191,7 +199,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_conv1a_relu(const f
   else if (out_dtype == 2) sp_conv1a_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
   else {
     const long long t8 = (long long)H * ((W + 3) >> 2) * 8;
-    sp_conv1a_split_kernel<<<i4d_cdiv(t8, 256), 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+    sp_conv1a_split_kernel<<<i4d_cdiv(t8, 256), 256, 0, st>>>(image, H, W, weight, bias, reinterpret_cast<__nv_bfloat16*>(out_nhwc), out_dtype == 3 ? 1 : 0);
   }
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;

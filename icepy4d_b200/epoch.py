@@ -83,7 +83,7 @@ def gather_results(local: Dict[int, np.ndarray], world_size: int, group=None) ->
 
 
 def make_cfg2_pipeline(max_keypoints: int = 8192, sinkhorn_iterations: int = 100, precision: str = "f32",
-                       conv_precision: str = "bf16x3", grid=(2, 3), cameras=None) -> StereoEpochPipeline:
+                       conv_precision: str = "f16x3", grid=(2, 3), cameras=None) -> StereoEpochPipeline:
     """BASELINE.json configs[1]: full-res 6000x4000 stereo pair, 2x3 tile grid, SuperPoint + SuperGlue (outdoor
     architecture, 100 Sinkhorn iterations), 8192 keypoints per tile, seeded structured random weights."""
     from . import synthetic, weights
@@ -98,7 +98,7 @@ def make_cfg2_pipeline(max_keypoints: int = 8192, sinkhorn_iterations: int = 100
                                geometric_verification=GeometricVerification.MAGSAC)
 
 
-def make_cfg5_pipeline(max_keypoints: int = 16384, precision: str = "f32", conv_precision: str = "bf16x3", grid=(3, 4),
+def make_cfg5_pipeline(max_keypoints: int = 16384, precision: str = "f32", conv_precision: str = "f16x3", grid=(3, 4),
                        cameras=None) -> StereoEpochPipeline:
     """BASELINE.json configs[4]: 16384 kp/tile LightGlue, 3x4 tiles, dual-softmax + mutual-NN (static depth/width)."""
     from . import synthetic, weights

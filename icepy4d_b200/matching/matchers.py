@@ -481,7 +481,7 @@ class SuperGlueMatcher(ImageMatcherBase):
         self.superpoint = SuperPointB200(sp_state, self._device, nms_radius=cfg["superpoint"]["nms_radius"],
                                          keypoint_threshold=cfg["superpoint"]["keypoint_threshold"],
                                          max_keypoints=cfg["superpoint"]["max_keypoints"],
-                                         conv_precision=opt.get("conv_precision", "bf16x3"))
+                                         conv_precision=opt.get("conv_precision", "f16x3"))
         from .superglue import SuperGlueB200
         self.superglue = SuperGlueB200(sg_state, self._device, sinkhorn_iterations=cfg["superglue"]["sinkhorn_iterations"],
                                        match_threshold=cfg["superglue"]["match_threshold"],
@@ -538,7 +538,7 @@ class LightGlueMatcher(ImageMatcherBase):
     def _extractor(self, k: int) -> SuperPointB200:
         if k not in self._sp_cache:   # LG-flavour SuperPoint: radius 4, threshold 0.0005 (LightGlue/lightglue/superpoint.py:97-103)
             self._sp_cache[k] = SuperPointB200(self._sp_state, self._device, nms_radius=4, keypoint_threshold=0.0005,
-                                               max_keypoints=k, conv_precision=self._opt.get("conv_precision", "bf16x3"))
+                                               max_keypoints=k, conv_precision=self._opt.get("conv_precision", "f16x3"))
         return self._sp_cache[k]
 
     def _detect(self, tile, **config):

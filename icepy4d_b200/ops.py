@@ -56,20 +56,22 @@ def maxpool2x2_cl(x: torch.Tensor) -> torch.Tensor:
     return out.permute(0, 3, 1, 2)
 
 
-def sp_conv1a_relu_split(image: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """image [1,1,H,W] f32 -> relu(conv1a) as split bf16 planes [2,H,W,64] (hi, lo)."""
+def sp_conv1a_relu_split(image: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """image [1,1,H,W] f32 -> relu(conv1a) as split 16-bit planes [2,H,W,64] (hi, lo), bfloat16 or float16."""
     _chk(image, name="image")
     H, W = image.shape[-2:]
-    out = torch.empty((2, H, W, 64), device=image.device, dtype=torch.bfloat16)
-    N.call("i4d_sp_conv1a_relu", image, H, W, _chk(weight.reshape(64, 9), name="weight"), _chk(bias, name="bias"), out, 3, _st())
+    out = torch.empty((2, H, W, 64), device=image.device, dtype=dtype)
+    N.call("i4d_sp_conv1a_relu", image, H, W, _chk(weight.reshape(64, 9), name="weight"), _chk(bias, name="bias"), out,
+           3 if dtype == torch.bfloat16 else 4, _st())
     return out
 
 
 class PackedConv:
     """Weights of one convolution in the layout i4d_conv_bf16x3_tc reads (see include/icepy4d_b200.h)."""
 
-    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, device):
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, device, dtype=torch.bfloat16):
         cout, cin, k, k2 = weight.shape
+        self.dtype = dtype
         assert k == k2 and k in (1, 3) and cin % 64 == 0
         self.cout, self.cin, self.ksize = cout, cin, k
         self.cout_pad = 64 if cout <= 64 else -(-cout // 128) * 128
@@ -77,8 +79,8 @@ class PackedConv:
         nt, kc, taps = self.cout_pad // n_t, cin // 64, k * k
         wp = torch.zeros((self.cout_pad, cin, k, k), dtype=torch.float32)
         wp[:cout] = weight.detach().float().cpu()
-        hi = wp.to(torch.bfloat16)
-        lo = (wp - hi.float()).to(torch.bfloat16)
+        hi = wp.to(dtype)
+        lo = (wp - hi.float()).to(dtype)
         t = torch.stack([hi, lo]).reshape(2, nt, n_t, kc, 64, taps)          # [part, nt, r, kc, k, tap]
         self.w = t.permute(1, 5, 3, 0, 2, 4).contiguous().reshape(-1, 64).to(device)   # [nt, tap, kc, part, r, k]
         b = torch.zeros(self.cout_pad, dtype=torch.float32)
@@ -89,13 +91,13 @@ class PackedConv:
 def conv_bf16x3(x: torch.Tensor, pk: PackedConv, relu: bool = True, pool: bool = False, out: str = "split") -> torch.Tensor:
     """x: split bf16 planes [2,H,W,Cin].  out = "split" -> [2,Ho,Wo,cout] bf16 planes (2x2 max-pool fused when pool),
     "nhwc" -> f32 [H,W,cout], "planar" -> f32 [cout,H,W]."""
-    _chk(x, torch.bfloat16, "x")
+    _chk(x, pk.dtype, "x")
     assert x.dim() == 4 and x.shape[0] == 2 and x.shape[3] == pk.cin
     H, W = int(x.shape[1]), int(x.shape[2])
     y16 = y32 = None
     if out == "split":
         Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-        y16 = torch.empty((2, Ho, Wo, pk.cout_pad), device=x.device, dtype=torch.bfloat16)
+        y16 = torch.empty((2, Ho, Wo, pk.cout_pad), device=x.device, dtype=pk.dtype)
     elif out == "nhwc":
         y32 = torch.empty((H, W, pk.cout), device=x.device, dtype=torch.float32)
     elif out == "planar":
@@ -103,7 +105,8 @@ def conv_bf16x3(x: torch.Tensor, pk: PackedConv, relu: bool = True, pool: bool =
     else:
         raise ValueError(out)
     N.call("i4d_conv_bf16x3_tc", x[0], x[1], H, W, pk.cin, pk.w, pk.b, pk.cout_pad, pk.cout, pk.ksize, int(relu), int(pool),
-           y16[0] if y16 is not None else None, y16[1] if y16 is not None else None, y32, pk.cout, int(out == "planar"), _st())
+           y16[0] if y16 is not None else None, y16[1] if y16 is not None else None, y32, pk.cout, int(out == "planar"),
+           1 if pk.dtype == torch.bfloat16 else 0, _st())
     return y16 if y16 is not None else y32
 
 

@@ -31,7 +31,7 @@ int i4d_device_sm_count(void);
 /* ---- SuperPoint first layer ---------------------------------------------------------------------------- */
 /* superpoint.py:154 — relu(conv1a(image)): 1 -> 64 channels, 3x3, pad 1.  image [H,W] f32, weight [64,9] (= [64,1,3,3]),
  * bias [64]; out [H,W,64] channels-last, out_dtype 0 = f32, 1 = f16, 2 = bf16, 3 = split bf16: out is [2][H,W,64], plane 0
- * = bf16(v), plane 1 = bf16(v - plane 0), the operand format of i4d_conv_bf16x3_tc. */
+ * = bf16(v), plane 1 = bf16(v - plane 0), the operand format of i4d_conv_bf16x3_tc; out_dtype 4: the same with IEEE halves. */
 int i4d_sp_conv1a_relu(const float* image, int H, int W, const float* weight, const float* bias, void* out_nhwc,
                        int out_dtype, void* stream);
 
@@ -50,11 +50,13 @@ int i4d_maxpool2x2_nhwc(const void* in, int H, int W, int C, void* out, int elem
  *   bias       : f32 [cout_pad]
  *   outputs    : y_hi / y_lo bf16 planes [Ho][Wo][cout_pad] (requires cout == cout_pad; with pool = 1 the 2x2/stride-2
  *                max-pool of superpoint.py:156,159,162 is fused: Ho = H/2, Wo = W/2) and/or y32 f32, either channels-last
- *                [H][W][ld32] or planar [cout][H][W] (y32_planar = 1, the layout i4d_sp_score_map reads) */
+ *                [H][W][ld32] or planar [cout][H][W] (y32_planar = 1, the layout i4d_sp_score_map reads)
+ *   operand_format : 1 = bfloat16 pairs as described ("bf16x3", 16 mantissa bits per value); 0 = IEEE-half pairs ("f16x3",
+ *                22 mantissa bits, values clamped to +-65504): same three products, same speed, f32-grade results */
 int i4d_conv_tile_cout(int cout_pad);
 int i4d_conv_bf16x3_tc(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_packed, const float* bias,
                        int cout_pad, int cout, int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32,
-                       int y32_planar, void* stream);
+                       int y32_planar, int operand_format, void* stream);
 
 /* ---- SuperPoint post-processing ----------------------------------------------------------------------- */
 /* thirdparty/SuperGlue/models/superpoint.py:169-172 — softmax over 65 channels, drop dustbin, 8x8 pixel shuffle.

@@ -26,7 +26,7 @@ which = sys.argv[1:] or ["cfg1", "cfg3", "cfg5"]
 if "cfg1" in which:
     i0, i1 = synthetic.stereo_pair(4000, 6000, seed=1003, shift=(32, 16), channels=3)
     m = LightGlueMatcher({"features": "superpoint", "superpoint_state": weights.make_superpoint_state(1),
-                          "lightglue_state": weights.make_lightglue_state(3), "precision": "bf16", "conv_precision": "bf16x3"})
+                          "lightglue_state": weights.make_lightglue_state(3), "precision": "bf16", "conv_precision": "f16x3"})
     f = lambda: m.match(i0, i1, quality=Quality.LOW, tile_selection=TileSelection.GRID, grid=[1, 1], overlap=0, max_keypoints=2048,
                         geometric_verification=GeometricVerification.MAGSAC)
     t0 = time.perf_counter(); f(); torch.cuda.synchronize()
@@ -51,7 +51,7 @@ if "cfg3" in which:
     ms = ev(dlt, reps=10)
     print(f"cfg3 undistort x2 + DLT (6x6 Jacobi SVD), {q0.shape[0]} points: {ms * 1e3:.1f} us ({q0.shape[0] / ms / 1e3:.1f} M points/s)")
 if "cfg5" in which:
-    pipe = make_cfg5_pipeline(16384, precision="bf16", conv_precision="bf16x3", grid=(3, 4))
+    pipe = make_cfg5_pipeline(16384, precision="bf16", conv_precision="f16x3", grid=(3, 4))
     i0, i1 = synthetic.stereo_pair(4000, 6000, seed=1005, shift=(16, 8), channels=3)
     d0, d1 = torch.from_numpy(i0).cuda(), torch.from_numpy(i1).cuda()
     ms = ev(lambda: pipe.run_device(d0, d1), reps=2)

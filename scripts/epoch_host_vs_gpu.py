@@ -6,7 +6,7 @@ import torch
 from icepy4d_b200 import synthetic, _native
 from icepy4d_b200.epoch import make_cfg2_pipeline
 
-pipe = make_cfg2_pipeline(8192, 100, precision="bf16", conv_precision="bf16x3")
+pipe = make_cfg2_pipeline(8192, 100, precision="bf16", conv_precision="f16x3")
 i0, i1 = synthetic.stereo_pair(4000, 6000, seed=1000, shift=(16, 24), channels=3)
 d0, d1 = torch.from_numpy(i0).cuda(), torch.from_numpy(i1).cuda()
 for _ in range(3):

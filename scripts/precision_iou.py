@@ -9,7 +9,7 @@ def pairs(a, b): return {(float(p[0]), float(p[1]), float(q[0]), float(q[1])) fo
 def kset(a): return {(float(p[0]), float(p[1])) for p in a}
 ref = pairs(g["sg_mkpts0"], g["sg_mkpts1"]); refk = kset(g["sg_mkpts0"])
 refl = pairs(g["lg_mkpts0"], g["lg_mkpts1"])
-for conv in ("bf16x3", "f32", "tf32", "f16", "bf16"):
+for conv in (tuple(sys.argv[1].split(",")) if len(sys.argv) > 1 else ("bf16x3", "f16x3", "f32", "tf32", "f16", "bf16")):
     for prec in ("f32", "bf16"):
         m = SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": 512, "match_threshold": 0.2,
                               "force_cpu": False, "sinkhorn_iterations": 20, "superpoint_state": weights.make_superpoint_state(1),

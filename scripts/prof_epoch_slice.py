@@ -6,7 +6,7 @@ import torch
 from icepy4d_b200 import synthetic
 from icepy4d_b200.epoch import make_cfg2_pipeline
 from icepy4d_b200.matching import GeometricVerification, Quality, TileSelection
-pipe = make_cfg2_pipeline(8192, 100, precision="bf16", conv_precision="bf16x3", grid=(1, 1))
+pipe = make_cfg2_pipeline(8192, 100, precision="bf16", conv_precision="f16x3", grid=(1, 1))
 i0, i1 = synthetic.stereo_pair(1999, 1999, seed=1000, shift=(16, 24), channels=3)
 d0, d1 = torch.from_numpy(i0).cuda(), torch.from_numpy(i1).cuda()
 out = pipe.run_device(d0, d1)            # warm-up (cuDNN autotune, allocator), not profiled

@@ -18,9 +18,9 @@ def ops():
     return ops
 
 
-def _split(x):
-    hi = x.to(torch.bfloat16)
-    return torch.stack([hi, (x - hi.float()).to(torch.bfloat16)])
+def _split(x, dtype=torch.bfloat16):
+    hi = x.to(dtype)
+    return torch.stack([hi, (x - hi.float()).to(dtype)])
 
 
 def _join(p):
@@ -31,13 +31,14 @@ def _join(p):
     (16, 16, 64, 64, 3, False), (37, 53, 64, 64, 3, False), (38, 54, 64, 64, 3, True), (37, 53, 64, 64, 3, True),
     (33, 20, 64, 128, 3, False), (21, 40, 128, 128, 3, True), (17, 9, 128, 256, 3, False), (130, 70, 64, 64, 3, False),
     (19, 23, 256, 256, 1, False), (19, 23, 256, 65, 1, False)])
-def test_conv_bf16x3(ops, H, W, cin, cout, k, pool):
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_bf16x3(ops, H, W, cin, cout, k, pool, dtype):
     gen = torch.Generator().manual_seed(H * W + cin + cout)
     x = torch.relu(torch.randn(H, W, cin, generator=gen)) * 2.0
     w = torch.randn(cout, cin, k, k, generator=gen) / (cin * k * k) ** 0.5
     b = torch.randn(cout, generator=gen) * 0.1
-    pk = ops.PackedConv(w, b, "cuda")
-    xs = _split(x).cuda()
+    pk = ops.PackedConv(w, b, "cuda", dtype)
+    xs = _split(x, dtype).cuda()
     xq = _join(xs).cpu()                                    # what the kernel actually sees (16 mantissa bits)
     ref = F.conv2d(xq.permute(2, 0, 1)[None].double(), w.double(), b.double(), padding=k // 2)[0]     # [cout,H,W]
     scale = float(ref.abs().max())
@@ -63,12 +64,15 @@ def test_conv1a_split(ops):
     img = torch.rand(1, 1, 45, 67, generator=gen)
     w = torch.randn(64, 1, 3, 3, generator=gen) * 0.3
     b = torch.randn(64, generator=gen) * 0.1
-    y = ops.sp_conv1a_relu_split(img.cuda(), w.cuda(), b.cuda())
     ref = torch.relu(F.conv2d(img.double(), w.double(), b.double(), padding=1))[0].permute(1, 2, 0)
-    assert float((_join(y).cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    for dtype, tol in ((torch.bfloat16, 2e-5), (torch.float16, 2e-6)):
+        y = ops.sp_conv1a_relu_split(img.cuda(), w.cuda(), b.cuda(), dtype)
+        assert y.dtype == dtype
+        assert float((_join(y).cpu().double() - ref).abs().max()) < tol * float(ref.abs().max())
 
 
-def test_superpoint_backbone_bf16x3_vs_f32():
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 2e-4), ("f16x3", 1e-4)])   # f16x3 is at the f32 summation-order noise of the cuDNN reference
+def test_superpoint_backbone_bf16x3_vs_f32(mode, tol):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     from icepy4d_b200.matching.superpoint import SuperPointB200
@@ -77,12 +81,12 @@ def test_superpoint_backbone_bf16x3_vs_f32():
     img, _ = synthetic.stereo_pair(240, 328, seed=3, shift=(4, 2), channels=1)
     x = torch.from_numpy(img.astype(np.float32) / 255.0)[None, None].cuda()
     ref = SuperPointB200(st, conv_precision="f32", keypoint_threshold=1e-4, max_keypoints=512)
-    tcm = SuperPointB200(st, conv_precision="bf16x3", keypoint_threshold=1e-4, max_keypoints=512)
+    tcm = SuperPointB200(st, conv_precision=mode, keypoint_threshold=1e-4, max_keypoints=512)
     l0, d0 = ref.backbone(x)
     l1, d1 = tcm.backbone(x)
     assert l0.shape == l1.shape and d0.shape == d1.shape
-    assert float((l0 - l1).abs().max()) < 2e-4 * float(l0.abs().max())
-    assert float((d0 - d1).abs().max()) < 2e-4 * float(d0.abs().max())
+    assert float((l0 - l1).abs().max()) < tol * float(l0.abs().max())
+    assert float((d0 - d1).abs().max()) < tol * float(d0.abs().max())
     f0, f1 = ref.detect(x), tcm.detect(x)
     from icepy4d_b200.matching.superpoint import sync_counts
     sync_counts(f0, f1)
