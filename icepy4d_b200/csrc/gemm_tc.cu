@@ -4,7 +4,7 @@
 // Persistent, warp-specialised: one CTA per SM walks 128 x 128 output tiles (n fastest, so neighbouring CTAs share A rows in L2).
 //   warp 0      TMA producer: A and W tiles of 128 x 64 bf16 (one 128-byte swizzle row per matrix row) through a 4-stage
 //               mbarrier ring; it runs ahead across tile boundaries
-//   warp 1      MMA issuer (one elected lane): tcgen05.mma M128 N128 K16, four per stage, into one of TWO TMEM accumulators,
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma M128 N128 K16, four per stage, into one of FOUR TMEM accumulators,
 //               so the main loop of tile i+1 overlaps the epilogue of tile i
 //   warps 2..9  epilogue (two warpgroups, each takes every other 32-column chunk), thread = output row: tcgen05.ld 32 columns at a time -> alpha, bias (staged in shared memory), ReLU,
 //               + residual (R chunk brought in by TMA) -> results staged in 128B-swizzled shared memory and written with
@@ -30,6 +30,8 @@
 #define GT_THREADS 320
 #define GT_STAGE_BYTES ((GT_BM + GT_BN) * GT_BK * 2)          // 32 KB
 #define GT_CHUNK_BYTES (GT_BM * 128)                            // 16 KB box: 128 rows x 128 B (32 f32 or 64 bf16 columns)
+#define GT_NACC 4                                               // TMEM accumulators (4 x 128 columns = all of TMEM): the MMA warp runs
+                                                                // up to four tiles ahead of the epilogue, which hides the hand-off latencies
 #define GT_NBOX 8                                               // staging pool shared by the R loads and the C32 / C16 stores
 #define GT_OFF_POOL (GT_STAGES * GT_STAGE_BYTES)
 #define GT_OFF_BIAS (GT_OFF_POOL + GT_NBOX * GT_CHUNK_BYTES)    // 2 x 128 f32
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmC16, GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[GT_STAGES], empty_bar[GT_STAGES], acc_full[2], acc_empty[2], r_full[2];
+  __shared__ __align__(8) uint64_t full_bar[GT_STAGES], empty_bar[GT_STAGES], acc_full[GT_NACC], acc_empty[GT_NACC], r_full[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,10 +79,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (p.has_c32) tc::prefetch_tmap(&tmC32);
     if (p.has_c16) tc::prefetch_tmap(&tmC16);
     for (int s = 0; s < GT_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 8); tc::mbar_init(&r_full[b], 1); }
+    for (int b = 0; b < GT_NACC; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) tc::mbar_init(&r_full[b], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 2 * GT_BN);
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, GT_NACC * GT_BN);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -111,8 +114,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t d0 = tc::desc_lo_sw128(tc::smem_u32(smem));
       uint32_t kc = 0, i = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-        const uint32_t b = i & 1;
-        tc::mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
+        const uint32_t b = i % GT_NACC;
+        tc::mbar_wait(&acc_empty[b], ((i / GT_NACC) & 1) ^ 1);      // the epilogue has drained this accumulator
         tc::tcgen05_fence_after();
         const uint32_t acc = tmem_d + b * GT_BN;
         for (int kb = 0; kb < kblocks; ++kb, ++kc) {
@@ -157,27 +160,35 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::tma_load_2d(sR + (gc & 1) * GT_CHUNK_BYTES, &tmR, &r_full[gc & 1], n0 + (int)c * 32, m0);
     };
     if (lead32 && p.has_r) { issue_r(0); issue_r(1); }
+    // bias of a tile is fetched one tile ahead (an exposed L2 round trip + barrier per tile was the longest link of the
+    // epilogue's dependency chain) and parked in the double-buffered shared-memory row at the end of the previous tile
+    auto bias_of = [&](int tile) -> float {
+      if (tile >= n_tiles || e >= GT_BN || !p.bias) return 0.f;
+      return __ldg(p.bias + min((tile % tiles_n) * GT_BN + e, p.N - 1));
+    };
+    if (e < GT_BN) sBias[e] = bias_of(blockIdx.x);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
-      const uint32_t b = i & 1;
-      float* bs = sBias + b * GT_BN;
-      if (e < GT_BN) bs[e] = p.bias ? __ldg(p.bias + min(n0 + e, p.N - 1)) : 0.f;
-      gt_epi_bar();                                                  // bias staged (its previous user, tile i-2, is long done)
-      tc::mbar_wait(&acc_full[b], (i >> 1) & 1);
+      const uint32_t b = i % GT_NACC, bb2 = i & 1;
+      float* bs = sBias + bb2 * GT_BN;
+      const float bias_next = bias_of(t + (int)gridDim.x);          // in flight during this tile
+      gt_epi_bar();                                                  // bias row of this tile visible (written a tile ago)
+      tc::mbar_wait(&acc_full[b], (i / GT_NACC) & 1);
       tc::tcgen05_fence_after();
-#pragma unroll 1
+      // both of my chunks leave TMEM together (two loads in flight), and the accumulator goes back to the MMA warp at once
+      uint32_t vv[2][32];
+      tc::tmem_ld32(tmem_d + lane_off + b * GT_BN + wg * 32, vv[0]);
+      tc::tmem_ld32(tmem_d + lane_off + b * GT_BN + (2 + wg) * 32, vv[1]);
+      tc::tmem_ld_wait();
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+#pragma unroll
       for (int st = 0; st < 2; ++st) {
         const int c = 2 * st + wg;                                   // my chunk of this step
         const uint32_t S = 2 * i + st;                               // global step index
         const uint32_t g = 2 * S + wg;                               // global chunk index
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_d + lane_off + b * GT_BN + c * 32, v);
-        tc::tmem_ld_wait();
-        if (st == 1) {                                               // accumulator drained: hand it back to the MMA warp
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
-        }
+        const uint32_t (&v)[32] = vv[st];
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -241,12 +252,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+      if (e < GT_BN) sBias[(bb2 ^ 1) * GT_BN + e] = bias_next;         // its previous reader (tile i-1) finished a tile ago
     }
     if (lead32 || lead16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_d, 2 * GT_BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_d, GT_NACC * GT_BN);
 }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----------------------
