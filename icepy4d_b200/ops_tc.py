@@ -3,6 +3,7 @@ layer schedules built on them.  f32 master copy of the residual stream, bf16 act
 accumulation everywhere (TMEM)."""
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -77,22 +78,22 @@ class SuperGlueTensorCore:
                                 "w2": h(L["w2"]), "b2": L["b2"]})
         self.wf, self.bf = h(w.wf), w.bf
         self._buf = {}
+        self._graphs = {}
 
     def _buffers(self, nt):
         if self._buf.get("nt") != nt:
-            d = self.dev
-            self._buf = {"nt": nt, "x32": torch.empty((nt, 256), device=d), "xm": torch.empty((nt, 512), device=d, dtype=BF16),
-                         "qkv": torch.empty((nt, 768), device=d, dtype=BF16), "att": torch.empty((nt, 256), device=d, dtype=BF16),
-                         "hid": torch.empty((nt, 512), device=d, dtype=BF16), "md": torch.empty((nt, 256), device=d, dtype=BF16)}
+            self._buf = self._alloc(nt)
         return self._buf
 
-    def gnn_and_scores(self, d0: torch.Tensor, d1: torch.Tensor, collect=None) -> torch.Tensor:
-        n0, n1 = d0.shape[0], d1.shape[0]
-        nt = n0 + n1
-        b = self._buffers(nt)
-        x32, xm, qkv, att, hid, md = b["x32"], b["xm"], b["qkv"], b["att"], b["hid"], b["md"]
-        x32[:n0] = d0
-        x32[n0:] = d1
+    def _alloc(self, nt):
+        d = self.dev
+        return {"nt": nt, "x32": torch.empty((nt, 256), device=d), "xm": torch.empty((nt, 512), device=d, dtype=BF16),
+                "qkv": torch.empty((nt, 768), device=d, dtype=BF16), "att": torch.empty((nt, 256), device=d, dtype=BF16),
+                "hid": torch.empty((nt, 512), device=d, dtype=BF16), "md": torch.empty((nt, 256), device=d, dtype=BF16)}
+
+    def _schedule(self, b, n0: int, n1: int, scores: torch.Tensor, collect=None) -> torch.Tensor:
+        """The 18-layer GNN + final projection + score GEMM on buffers `b`; b["x32"] already holds the encoded descriptors."""
+        x32, xm, qkv, hid, md = b["x32"], b["xm"], b["qkv"], b["hid"], b["md"]
         to_bf16(x32, xm[:, :256])
         self_p = [(0, n0, 0, n0), (n0, n1, n0, n1)]
         cross_p = [(0, n0, n0, n1), (n0, n1, 0, n0)]
@@ -104,9 +105,59 @@ class SuperGlueTensorCore:
             if collect is not None:
                 collect.append((x32[:n0].clone(), x32[n0:].clone()))
         gemm_tc(xm[:, :256], self.wf, self.bf, out16=md)
-        scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
         gemm_tc(md[:n0], md[n0:], out32=scores, alpha=1.0 / 16.0)
         return scores
+
+    def gnn_and_scores(self, d0: torch.Tensor, d1: torch.Tensor, collect=None) -> torch.Tensor:
+        n0, n1 = d0.shape[0], d1.shape[0]
+        nt = n0 + n1
+        if collect is None and self.use_graphs and min(n0, n1) >= 1024:
+            out = self._graphed(d0, d1)
+            if out is not None:
+                return out
+        b = self._buffers(nt)
+        b["x32"][:n0] = d0
+        b["x32"][n0:] = d1
+        scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
+        return self._schedule(b, n0, n1, scores, collect)
+
+    # -- CUDA-graph replay of the schedule (75 launches per tile pair): one graph per (n0, n1), static buffers, the caller's
+    #    descriptors are copied in front of the replay.  The returned score matrix is the graph's own buffer: it is consumed (by
+    #    the assignment kernels, same stream) before the next replay overwrites it.  Any failure disables graphs for good.
+    use_graphs = os.environ.get("I4D_NO_GRAPHS", "0") != "1"
+    MAX_GRAPHS = 3
+
+    def _graphed(self, d0: torch.Tensor, d1: torch.Tensor):
+        n0, n1 = d0.shape[0], d1.shape[0]
+        key = (n0, n1, torch.cuda.current_stream().cuda_stream)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                return None
+            self._graphs[key] = "seen"           # first call of a shape runs eagerly (it also warms every kernel up)
+            return None
+        try:
+            if ent == "seen":
+                b = self._alloc(n0 + n1)
+                scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
+                launches0 = N.LAUNCHES
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._schedule(b, n0, n1, scores)
+                ent = self._graphs[key] = {"g": g, "b": b, "scores": scores, "launches": N.LAUNCHES - launches0}
+                N.LAUNCHES = launches0           # capture launched nothing
+            b = ent["b"]
+            b["x32"][:n0] = d0
+            b["x32"][n0:] = d1
+            ent["g"].replay()
+            N.LAUNCHES += ent["launches"]
+            return ent["scores"]
+        except Exception as err:                 # noqa: BLE001 - eager execution is always available
+            import logging
+            logging.getLogger(__name__).warning(f"CUDA-graph capture of the SuperGlue schedule failed ({err}); running eagerly")
+            type(self).use_graphs = False
+            self._graphs.clear()
+            return None
 
 
 class LightGlueTensorCore:
