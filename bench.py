@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the per-epoch stereo hot path (BASELINE.json: "stereo epochs/sec (6000x4000 tiled SP+LG)").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg5|cfg1]
 
-One step = one stereo epoch of BASELINE.json configs[1]: a synthetic 6000x4000 pair, 2x3 GRID tiles (1999x1999),
-SuperPoint (8192 kp/tile) + SuperGlue (outdoor arch, 100 Sinkhorn iterations), tile merge, F-matrix verification,
-triangulation.  Epochs are independent: rank r of N processes its own epochs (weak scaling, no data-path collective).
+One step = one stereo epoch of the named BASELINE.json config on a synthetic 6000x4000 pair:
+  cfg2 (default, configs[1], the config the metric is quoted on): 2x3 GRID tiles (1999x1999), SuperPoint (8192 kp/tile) +
+       SuperGlue (outdoor arch, 100 Sinkhorn iterations), tile merge, MAGSAC++ F verification, iterative-LS triangulation;
+  cfg5 (configs[4]): 3x4 GRID tiles (1499x1329), SuperPoint (16384 kp/tile) + LightGlue (static depth/width), dual-softmax +
+       mutual NN, verification, triangulation;
+  cfg1 (configs[0]): Quality.LOW (1500x1000), LightGlue 2048 kp, one tile.
+Epochs are independent: `shard_epochs` gives rank r of N its epochs (weak scaling, no data-path collective); after the timed
+region the per-epoch results are exchanged once with `gather_results` (NCCL) and that time is reported separately.
 
-Output: ONE JSON line (rank 0).  `value` = epochs/s with the u8 images already resident in HBM; `e2e` = the same through
-the public plugin API (`SuperGlueMatcher.match` + `Triangulate.triangulate_two_views`) from pinned host images to host
-arrays; `roofline` = the dominant kernel timed live with CUDA events; `cpu_baseline` = the CPU oracle (a port of the
-reference's algorithm, oracle/*.py) on this box's host cores over a bounded sample, extrapolated to one epoch.
-`--impl reference` times that CPU path alone.
+Output: ONE JSON line (rank 0).  `value` = epochs/s with the u8 images already resident in HBM; `e2e` = the same through the
+public plugin API (`*Matcher.match` + `Triangulate.triangulate_two_views`) from pinned host images to host arrays;
+`roofline` = the dominant HBM-bound kernel and `roofline_tensor` = the attention kernel, both timed live with CUDA events;
+`cpu_baseline` = the reference's own CPU implementation (oracle/_ref, staged by oracle/stage_ref.py; the CPU port in oracle/ if
+that is absent) on this box's host cores over a bounded sample.  `--impl reference` times that CPU path alone.
 """
 from __future__ import annotations
 
@@ -29,13 +34,30 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "stereo epochs/sec (6000x4000, 2x3 tiles, SuperPoint+SuperGlue 8192 kp/tile, 100 Sinkhorn iters)"
 UNIT = "epochs/s"
 H, W = 4000, 6000
-GRID = (2, 3)
-KP = 8192
+CONFIGS = {
+    "cfg2": {"metric": "stereo epochs/sec (6000x4000, 2x3 tiles, SuperPoint+SuperGlue 8192 kp/tile, 100 Sinkhorn iters)",
+             "workload": "cfg2: 6000x4000 stereo pair, 2x3 GRID tiles (1999x1999), SuperPoint+SuperGlue outdoor arch, 8192 kp/tile, "
+                         "100 Sinkhorn iters, MAGSAC++ F verification, iterative-LS triangulation",
+             "grid": (2, 3), "kp": 8192, "pairs": 6, "tile": (2000, 2000), "matcher": "superglue"},
+    "cfg5": {"metric": "stereo epochs/sec (6000x4000, 3x4 tiles, SuperPoint+LightGlue 16384 kp/tile, dual-softmax)",
+             "workload": "cfg5: 6000x4000 stereo pair, 3x4 GRID tiles (1499x1329), SuperPoint+LightGlue (static depth/width), "
+                         "16384 kp/tile, dual-softmax + mutual NN, MAGSAC++ F verification, iterative-LS triangulation",
+             "grid": (3, 4), "kp": 16384, "pairs": 12, "tile": (1330, 1500), "matcher": "lightglue"},
+    "cfg1": {"metric": "stereo epochs/sec (6000x4000 at Quality.LOW = 1500x1000, SuperPoint+LightGlue 2048 kp)",
+             "workload": "cfg1: 6000x4000 stereo pair, Quality.LOW (2x pyrDown -> 1500x1000), one tile, SuperPoint+LightGlue 2048 kp, "
+                         "MAGSAC++ F verification, iterative-LS triangulation",
+             "grid": (1, 1), "kp": 2048, "pairs": 1, "tile": (1000, 1500), "matcher": "lightglue"},
+}
 SINKHORN_ITERS = 100
-N_TILE_IMAGES, N_PAIRS = 12, 6
+
+
+def _config_block(cfg_name: str):
+    """The `config` object both arms print (identical for `--impl ours` and `--impl reference`)."""
+    c = CONFIGS[cfg_name]
+    return {"workload": c["workload"], "weights": "seeded structured random init (icepy4d_b200/weights.py)",
+            "l2": "inputs_larger_than_l2 (2 x 72 MB images; 268 MB / 1.07 GB score matrices)"}
 
 
 def _peaks():
@@ -92,33 +114,98 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- CPU oracle timing
-def cpu_sample(threads: int):
-    """Bounded sample of one cfg2 epoch on the host: 1 of the 12 SuperPoint tile images at full size (1999x1999,
-    8192 kp) + 1 SuperGlue tile pair at 2048 kp with 100 Sinkhorn iterations (1/16 of the N^2 work of an 8192 pair).
-    Returns (estimated seconds per epoch, description)."""
-    from icepy4d_b200 import synthetic, weights
-    from oracle import sg_oracle, sp_oracle
+# ----------------------------------------------------------------------------------------------- CPU reference timing
+def _reference_matcher(cfg_name: str):
+    """The UNMODIFIED reference matcher class (staged under oracle/_ref or mounted at /root/reference) with the seeded weights,
+    on CPU.  Returns (callable(image0, image1, **kw) -> n_matches, description) or None when no reference tree is available."""
+    from oracle import ref_shims
+
+    if not ref_shims.reference_available():
+        return None
+    from icepy4d_b200 import weights
+
+    ref_shims.install_shims()
+    import icepy4d.matching.matchers as M
+    from icepy4d.matching import GeometricVerification, Quality, TileSelection
+
+    c = CONFIGS[cfg_name]
+    sp_sd = weights.make_superpoint_state(1)
+    if c["matcher"] == "superglue":
+        with ref_shims.no_checkpoint_loading():
+            m = M.SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": c["kp"], "match_threshold": 0.2,
+                                    "force_cpu": True, "sinkhorn_iterations": SINKHORN_ITERS})
+        m.matcher.superpoint.load_state_dict(sp_sd)
+        m.matcher.superglue.load_state_dict(weights.make_superglue_state(2))
+
+        def run(i0, i1):
+            m.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.GRID, grid=[1, 1], overlap=0,
+                    geometric_verification=GeometricVerification.MAGSAC)
+            return len(m.mkpts0)
+        return run, "icepy4d.matching.SuperGlueMatcher.match (reference source, CPU)"
+    lg_sd = weights.make_lightglue_state(3)
+    import icepy4d.thirdparty.LightGlue.lightglue as LGpkg
+    # LightGlueMatcher re-instantiates both networks (and reloads checkpoints that do not exist here) on every call
+    # (matchers.py:1256-1258): the constructors are pointed at the seeded weights; everything else is the reference's code
+    LGpkg.SuperPoint = lambda **kw: ref_shims.build_reference_superpoint_lg(sp_sd, **kw)
+    LGpkg.LightGlue = lambda features="superpoint", **kw: ref_shims.build_reference_lightglue(lg_sd, **kw)
+    lm = M.LightGlueMatcher({"features": "superpoint", "force_cpu": True})
+
+    def run_lg(i0, i1, kp):
+        lm.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.GRID, grid=[1, 1], overlap=0, max_keypoints=kp,
+                 geometric_verification=GeometricVerification.MAGSAC)
+        return len(lm.mkpts0)
+    return run_lg, "icepy4d.matching.LightGlueMatcher.match (reference source, CPU)"
+
+
+def cpu_sample(cfg_name: str, threads: int):
+    """Bounded sample of one epoch on the host cores, through the reference's own plugin call: ONE tile pair of the config
+    (`match(tile0, tile1, GRID, grid=[1,1])` on a crop of the epoch's images: with grid [1,1] the reference's tiler yields exactly
+    the (DX-1)x(DY-1) tile the config's grid yields), times the number of tile pairs.  cfg5's 16384-kp pair does not fit a
+    bounded sample (minutes, > 20 GB on the CPU path): it is timed at 4096 kp and scaled by the N^2 attention/assignment work.
+    Returns (seconds per epoch [extrapolated], seconds actually timed, kind, description)."""
+    from icepy4d_b200 import synthetic
 
     torch.set_num_threads(threads)
-    sp_sd, sg_sd = weights.make_superpoint_state(1), weights.make_superglue_state(2)
-    i0, i1 = synthetic.stereo_pair(1999, 1999, seed=1000, shift=(16, 24), channels=1)
-    t = torch.tensor(i0 / 255.0, dtype=torch.float)[None, None]
-    with torch.inference_mode():
+    c = CONFIGS[cfg_name]
+    th, tw = c["tile"]
+    i0, i1 = synthetic.stereo_pair(th, tw, seed=1000, shift=(16, 24), channels=3)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        ref = _reference_matcher(cfg_name)
+    kp, scale = c["kp"], 1.0
+    if cfg_name == "cfg5":
+        kp, scale = 4096, (c["kp"] / 4096.0) ** 2
+    if ref is not None:
+        import contextlib
+        run, what = ref
         t0 = time.perf_counter()
-        f0 = sp_oracle.superpoint_sg(t, sp_sd, 3, 1e-4, KP)
-        t_sp = time.perf_counter() - t0
-        ns = 2048
-        k, s, d = f0["keypoints"][:ns], f0["scores"][:ns], f0["descriptors"][:, :ns]
+        with contextlib.redirect_stdout(sys.stderr):        # the reference prints progress lines; stdout carries the JSON line only
+            n = run(i0, i1) if c["matcher"] == "superglue" else run(i0, i1, kp)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+    else:                                   # the CPU port in oracle/ (same algorithm, restated; used only if oracle/_ref is missing)
+        from icepy4d_b200 import weights
+        from oracle import lg_oracle, sg_oracle, sp_oracle
+        sp_sd = weights.make_superpoint_state(1)
+        g = lambda im: torch.tensor(im[: th - 1, : tw - 1, 0] / 255.0, dtype=torch.float)[None, None]
         t0 = time.perf_counter()
-        sg_oracle.superglue(k, s, d, k.flip(0), s.flip(0), d.flip(1), (1999, 1999), (1999, 1999), sg_sd, iters=SINKHORN_ITERS, thr=0.2)
-        t_sg = time.perf_counter() - t0
-    scale = (KP / ns) ** 2
-    est = N_TILE_IMAGES * t_sp + N_PAIRS * t_sg * scale
-    desc = (f"1/{N_TILE_IMAGES} SuperPoint tile images (1999x1999, {t_sp:.2f} s) + 1 SuperGlue pair at {ns} kp, {SINKHORN_ITERS} "
-            f"Sinkhorn iters ({t_sg:.2f} s, x{scale:.0f} for the N^2 work at {KP} kp); epoch = 12 SP + 6 SG, extrapolated; "
-            "geometry stages (<1 % of CPU time) not included")
-    return est, desc
+        with torch.inference_mode():
+            if c["matcher"] == "superglue":
+                f0, f1 = sp_oracle.superpoint_sg(g(i0), sp_sd, 3, 1e-4, kp), sp_oracle.superpoint_sg(g(i1), sp_sd, 3, 1e-4, kp)
+                out = sg_oracle.superglue(f0["keypoints"], f0["scores"], f0["descriptors"], f1["keypoints"], f1["scores"], f1["descriptors"],
+                                          (th - 1, tw - 1), (th - 1, tw - 1), weights.make_superglue_state(2), iters=SINKHORN_ITERS, thr=0.2)
+            else:
+                f0, f1 = sp_oracle.superpoint_lg(g(i0), sp_sd, k=kp), sp_oracle.superpoint_lg(g(i1), sp_sd, k=kp)
+                out = lg_oracle.lightglue(f0["keypoints"], f0["descriptors"], (tw - 1.0, th - 1.0), f1["keypoints"], f1["descriptors"],
+                                          (tw - 1.0, th - 1.0), weights.make_lightglue_state(3), depth_conf=-1, width_conf=-1)
+        n = int((out["matches0"] > -1).sum())
+        dt = time.perf_counter() - t0
+        kind, what = "port", "oracle/{sp,sg,lg}_oracle.py (CPU port; oracle/_ref not staged)"
+    est = c["pairs"] * dt * scale
+    desc = (f"{what}: 1 of {c['pairs']} tile pairs ({tw - 1}x{th - 1}, {kp} kp/tile, {n} verified matches) in {dt:.1f} s on {threads} threads"
+            + (f", x{scale:.0f} for the N^2 work at {c['kp']} kp" if scale != 1.0 else "")
+            + f", x{c['pairs']} tile pairs = one epoch (extrapolated; triangulation, < 1 % of the CPU time, not included)")
+    return est, dt, kind, desc
 
 
 def run_reference(args):
@@ -126,67 +213,116 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(args.warmup and 1):
-        pass  # the CPU sample needs no warm-up beyond thread-pool start; keep the run bounded
-    ts = []
-    desc = ""
-    for _ in range(max(1, min(args.steps, 3))):
-        est, desc = cpu_sample(threads)
-        ts.append(est)
-    sec = float(np.median(ts))
+    # one sample costs tens of seconds of all host cores: the run stays within minutes by timing min(steps, 2) samples, no warm-up
+    n_samples = max(1, min(args.steps, 2 if args.config == "cfg1" else 1))
+    ests, dts, kind, desc = [], [], "port", ""
+    for _ in range(n_samples):
+        est, dt, kind, desc = cpu_sample(args.config, threads)
+        ests.append(est); dts.append(dt)
+    sec = float(np.median(ests))
     v = 1.0 / sec
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    c = CONFIGS[args.config]
+    line = {"impl": "reference", "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 6000x4000 stereo pair, 2x3 GRID tiles, SuperPoint+SuperGlue 8192 kp/tile, 100 Sinkhorn iters",
-                       "note": "CPU oracle (port of the reference algorithm; the Python reference cannot travel to the GPU box)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "dtype": "f32", "data": "synthetic", "config": _config_block(args.config),
+            "samples_timed": n_samples, "seconds_timed": float(sum(dts)), "extrapolated": True,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def _dominant_kernel_roofline(precision: str, peaks):
-    """Times the fused persistent Sinkhorn kernel (the HBM-bound kernel the 100-iteration optimal transport lives in: 600
-    iterations over 8192x8192 f32 score matrices per epoch) with CUDA events on the launch stream.
-    Algorithmic bytes per iteration = 2 * M * N * 4 (one read of the matrix per LSE pass, two passes per
-    iteration).  The kernel fuses both passes over one staged read and walks its row bands boustrophedon so that part of
-    every pass is served by L2: its measured DRAM traffic (ncu, profiles/r1_ncu_sinkhorn_v11.txt) is 193 MB per iteration
-    (0.72 * M * N * 4) and `frac` can exceed 1 against the copy-bandwidth peak."""
-    from icepy4d_b200 import ops
-
-    M = N = KP
-    S = torch.randn(M, N, device="cuda") * 3
-    ws = ops.AssignWorkspace(M, N, S.device)
-    iters = SINKHORN_ITERS
-    for _ in range(3):
-        ops.sinkhorn(S, 1.0, iters, ws)
+def _event_time(fn, warm=3, reps=5):
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
     e0.record()
     for _ in range(reps):
-        ops.sinkhorn(S, 1.0, iters, ws)
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms_launch = e0.elapsed_time(e1) / reps
-    bytes_launch = 2.0 * M * N * 4 * iters
-    gbs = bytes_launch / (ms_launch * 1e-3) / 1e9
+    return e0.elapsed_time(e1) / reps
+
+
+# ncu `--set full` captures of the final kernels (profiles/r2_ncu_*.txt): DRAM bytes per launch unit
+SINKHORN_TRAFFIC_PER_ITER = {"read": 193.1e6, "write": 6.6e6, "source": "profiles/r1_ncu_sinkhorn_v11.txt"}
+DUALSOFTMAX_TRAFFIC = None
+
+
+def _roofline_hbm(cfg_name: str, peaks):
+    """The dominant HBM-bound kernel of the config, timed live with CUDA events on the launch stream.
+    cfg2: the fused persistent Sinkhorn (600 iterations over 8192x8192 f32 per epoch).  SURVEY.md §8d counts 2*M*N*4 bytes per
+    iteration (one read per LSE pass); the kernel makes ONE staged read per iteration and serves part of it from L2, so `achieved`
+    / `frac` are quoted on the bytes it really moves (ncu dram__bytes) and the §8d figure is kept as `algorithmic_2pass`.
+    cfg5 / cfg1: the dual-softmax + mutual-NN assignment over the MxN similarity matrix (§8d: 2 reads of sim)."""
+    from icepy4d_b200 import ops
+
+    c = CONFIGS[cfg_name]
+    M = N = c["kp"]
+    S = torch.randn(M, N, device="cuda") * 3
+    ws = ops.AssignWorkspace(M, N, S.device)
+    if c["matcher"] == "superglue":
+        iters = SINKHORN_ITERS
+        ms = _event_time(lambda: ops.sinkhorn(S, 1.0, iters, ws))
+        alg2 = 2.0 * M * N * 4 * iters
+        one_read = 1.0 * M * N * 4 * iters
+        tr = SINKHORN_TRAFFIC_PER_ITER
+        traffic = (tr["read"] + tr["write"]) * iters if (M, N) == (8192, 8192) else None
+        moved = traffic if traffic is not None else one_read
+        gbs = moved / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                "traffic": traffic, "kernel": f"sinkhorn_fused_kernel ({iters} iterations, {M}x{N} f32, one launch)",
+                "ms_per_launch": ms, "us_per_iteration": ms * 1e3 / iters, "peak_source": peaks["source"],
+                "bytes_basis": f"DRAM bytes the launch moves: ncu dram__bytes_read + dram__bytes_write per iteration x {iters} ({tr['source']})",
+                "one_read_floor_bytes": one_read, "frac_one_read": one_read / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "algorithmic_2pass": {"bytes_per_launch": alg2, "GB/s": alg2 / (ms * 1e-3) / 1e9,
+                                      "frac": alg2 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                      "note": "SURVEY.md §8d model (2 reads of the matrix per iteration); the fused kernel reads it once"}}
+    z0 = torch.randn(M, device="cuda")
+    z1 = torch.randn(N, device="cuda")
+    ms = _event_time(lambda: ops.lg_assign(S, z0, z1, 0.1, ws))
+    alg = 2.0 * M * N * 4
+    gbs = alg / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": (193.1e6 + 6.6e6) * iters,
-            "kernel": "sinkhorn_fused_kernel (100 iterations, 8192x8192 f32, one launch)", "ms_per_launch": ms_launch,
-            "us_per_iteration": ms_launch * 1e3 / iters, "peak_source": peaks["source"],
-            "algorithmic_bytes_per_launch": bytes_launch,
-            "frac_of_actual_traffic": ((193.1e6 + 6.6e6) * iters / (ms_launch * 1e-3) / 1e9) / peaks["hbm_gbs"],
-            "note": "traffic = ncu dram__bytes_read 193.1 MB + dram__bytes_write 6.6 MB per iteration (profiles/r1_ncu_sinkhorn_v11.txt): "
-                    "one staged read of the matrix per iteration, 23 % of it served by L2 (boustrophedon bands)"}
+            "traffic": DUALSOFTMAX_TRAFFIC, "kernel": f"i4d_lg_assign (dual softmax + mutual NN, {M}x{N} f32 similarity)",
+            "ms_per_launch": ms, "peak_source": peaks["source"],
+            "bytes_basis": "SURVEY.md §8d: 2 reads of the similarity matrix (row/column statistics, then row/column argmax)"}
+
+
+def _roofline_tensor(cfg_name: str, peaks):
+    """attn_tc_kernel (tcgen05 flash attention, head_dim 64, 4 heads) on the config's layer shape, timed live with CUDA events."""
+    from icepy4d_b200 import ops_tc
+
+    c = CONFIGS[cfg_name]
+    n = c["kp"]
+    qkv = (torch.randn(2 * n, 768, device="cuda") * 0.5).to(torch.bfloat16)
+    out = torch.empty(2 * n, 256, device="cuda", dtype=torch.bfloat16)
+    probs = [(0, n, 0, n), (n, n, n, n)]
+    ms = _event_time(lambda: ops_tc.attention_tc(qkv, probs, out, 0, 256, 512), warm=3, reps=10)
+    flops = 2 * 4.0 * n * n * 64 * 4
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+            "traffic": None, "kernel": f"attn_tc_kernel (2 images x 4 heads x {n}x{n}, head_dim 64, bf16 operands, f32 accumulate)",
+            "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": peaks["source"]}
+
+
+def _make_pipeline(cfg_name: str, args):
+    from icepy4d_b200 import epoch
+
+    c = CONFIGS[cfg_name]
+    if cfg_name == "cfg2":
+        return epoch.make_cfg2_pipeline(c["kp"], SINKHORN_ITERS, precision=args.precision, conv_precision=args.conv_precision, grid=c["grid"])
+    if cfg_name == "cfg5":
+        return epoch.make_cfg5_pipeline(c["kp"], precision=args.precision, conv_precision=args.conv_precision, grid=c["grid"])
+    return epoch.make_cfg1_pipeline(c["kp"], precision=args.precision, conv_precision=args.conv_precision)
 
 
 def run_ours(args):
     import torch.distributed as dist
 
     from icepy4d_b200 import _native, synthetic
-    from icepy4d_b200.epoch import make_cfg2_pipeline
+    from icepy4d_b200.epoch import gather_results_device, shard_epochs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,9 +331,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = _peaks()
-    pipe = make_cfg2_pipeline(KP, SINKHORN_ITERS, precision=args.precision, conv_precision=args.conv_precision, grid=GRID)
+    cfg = CONFIGS[args.config]
+    pipe = _make_pipeline(args.config, args)
 
-    # synthetic epochs: seeds 1000 + e, a small pool cycled over the steps (each rank its own epochs)
+    # the job: world * steps epochs, epoch e = synthetic pair with seed 1000 + e; rank r owns shard_epochs(...) (round-robin).
+    # Images come from a small pool cycled over the rank's epochs (generating 72 MB of blurred noise per epoch on the host
+    # would dominate the run); every rank has its own pool.
+    my_epochs = shard_epochs(world * args.steps, rank, world)
+    assert len(my_epochs) == args.steps
     pool = 2
     host = []
     for e in range(pool):
@@ -221,15 +362,28 @@ def run_ours(args):
     n0 = _native.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    last = None
-    for s in range(args.steps):
-        last = pipe.run_device(*dev[s % pool])
+    results = {}
+    for s, epoch_id in enumerate(my_epochs):
+        results[epoch_id] = pipe.run_device(*dev[s % pool])["points3d"]
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _native.LAUNCHES - n0
     clocks = sampler.stop() if rank == 0 else None
-    n_matches = int(last["mkpts0"].shape[0])
+    n_matches = int(results[my_epochs[-1]].shape[0])
+
+    # ---- the single end-of-run exchange: every rank receives every epoch's 3-D points over NCCL ----
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    allres = gather_results_device(results, world)
+    g1.record()
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
+    gathered_epochs = len(allres)
+    gathered_bytes = int(sum(t.numel() * t.element_size() for t in allres.values()))
+    assert gathered_epochs == world * args.steps, (gathered_epochs, world, args.steps)
+    del allres, results
 
     # ---- end to end through the public API: pinned host images -> host arrays ----
     e2e_steps = max(1, min(args.steps, 5))
@@ -243,34 +397,34 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
 
-    t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms, gather_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     value = world * args.steps / (ms * 1e-3)
     e2e_value = world * e2e_steps / (e2e_ms * 1e-3)
-    roof = _dominant_kernel_roofline(args.precision, peaks)
+    roof = _roofline_hbm(args.config, peaks)
+    roof_t = _roofline_tensor(args.config, peaks)
     threads = os.cpu_count() or 1
-    cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
+    cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "skipped (N > 1 or --no-cpu-baseline)"}
     if world == 1 and not args.no_cpu_baseline:
-        est, desc = cpu_sample(threads)
-        cpu = {"value": 1.0 / est, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        est, dt, kind, desc = cpu_sample(args.config, threads)
+        cpu = {"value": 1.0 / est, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc, "seconds_timed": dt}
+    line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "f32" else "bf16 operands / f32 accumulate (matcher), f32 elsewhere",
-            "data": "synthetic",
-            "config": {"workload": "cfg2: 6000x4000 stereo pair, 2x3 GRID tiles (1999x1999), SuperPoint+SuperGlue outdoor arch, "
-                                   "8192 kp/tile, 100 Sinkhorn iters, MAGSAC-style F verification, iterative-LS triangulation",
-                       "precision": args.precision, "conv_precision": args.conv_precision, "weights": "seeded structured random init",
-                       "l2": "inputs_larger_than_l2 (2 x 72 MB images, 268 MB score matrices)", "matches_last_epoch": n_matches,
-                       "parallelism": f"epochs sharded over {world} GPU(s), no data-path collective"},
+            "dtype": "f32" if args.precision == "f32" else "bf16 operands / f32 accumulate (matcher), split-f16 x3 / f32 accumulate (backbone), f32 elsewhere",
+            "data": "synthetic", "config": _config_block(args.config),
+            "details": {"precision": args.precision, "conv_precision": args.conv_precision, "verified_matches_last_epoch": n_matches,
+                        "parallelism": f"{world * args.steps} epochs sharded round-robin over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * H * W * 3, "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "gather": {"ms": gather_ms, "epochs": gathered_epochs, "bytes": gathered_bytes,
+                       "what": "gather_results_device: one count exchange + one padded all_gather of every epoch's 3-D points (NCCL), outside the timed region"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_tensor": roof_t, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -282,8 +436,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # bf16 = the tcgen05 tensor-core matcher (bf16 operands, f32 accumulation; match IoU vs the f32 reference >= 0.999,
-    # tests/test_gpu_tc.py); f32 = the SIMT f32 matcher kept as the on-device cross-check
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    # bf16 = the tcgen05 tensor-core matcher (bf16 operands, f32 accumulation; tests/test_gpu_defaults.py); f32 = the SIMT f32
+    # matcher kept as the on-device cross-check
     ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--conv-precision", dest="conv_precision", default="f16x3", choices=["bf16x3", "f16x3", "f32", "tf32", "f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -90,9 +90,9 @@ def call(name: str, *args):
     """Call an int-returning entry point; pointers may be tensors/arrays; raises NativeError on failure."""
     l = lib()
     fn = getattr(l, name)
-    conv = [(_ptr(a) if t is ctypes.c_void_p else a) for a, t in zip(args, fn.argtypes)]
-    if len(conv) != len(fn.argtypes):
+    if len(args) != len(fn.argtypes):
         raise TypeError(f"{name}: expected {len(fn.argtypes)} arguments, got {len(args)}")
+    conv = [(_ptr(a) if t is ctypes.c_void_p else a) for a, t in zip(args, fn.argtypes)]
     rc = fn(*conv)
     if fn.restype is ctypes.c_int and rc != 0:
         raise NativeError(f"{name} failed ({rc}): {last_error()}")
@@ -122,7 +122,7 @@ def _count(name: str, args) -> int:
         return (1 if fused else 5 * iters) + (5 if name == "i4d_sg_assign" else 0)
     if name == "i4d_fundamental_ransac":
         rounds = min(24, -(-int(args[5]) // 4096))
-        return 1 + 5 * rounds + 1 + 2 * int(args[8]) + 1
+        return 1 + 5 * rounds + 1 + 2 * int(args[8]) + 2
     return 1
 
 

@@ -958,7 +958,7 @@ static int g_sinkhorn_fast = 1;   // 1 = a-priori stabilisers after the first tw
 static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
                                  cudaStream_t st) {
   if (!sinkhorn_fused_ok(M, N) || iters <= 0) return 1;
-  static int coop = -1, sms = 0;
+  static int coop = -1, sms = 0;   // B200 boxes are homogeneous: queried once
   if (coop < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -967,11 +967,10 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   }
   if (!coop || sms <= 0 || sms > 256) return 1;
   const size_t smem = (size_t)SK_STAGES * SK_ROWS * N * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     if (cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SK_STAGES * SK_ROWS * SK_MAXN * (int)sizeof(float)) != cudaSuccess) { cudaGetLastError(); return 1; }
-    attr_set = true;
   }
   int G = sms;
   int rpc = (M + G - 1) / G;

@@ -470,9 +470,12 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   // share of exponentials on the FMA pipe: none by default (measured: no gain, the kernel is latency-bound around the MUFU pipe,
   // DESIGN.md); I4D_FA_POLY=25 selects the 25 % build for experiments
   static int variant = -1;
+  static bool attr_seen[64] = {};
   if (variant < 0) {
     const char* e = getenv("I4D_FA_POLY");
     variant = (e && atoi(e) == 25) ? 1 : 0;
+  }
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }

@@ -41,6 +41,17 @@ void i4d_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must set it on each one (the benign race between two
+// host threads of one process only repeats an idempotent call).  Returns true the first time it is called on the current device
+// for the given call-site flag array.
+static inline bool i4d_first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 static inline int i4d_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_max(float v) {

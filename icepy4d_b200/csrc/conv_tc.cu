@@ -299,10 +299,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 template <int N_T, int T>
 static int launch_conv(const CUtensorMap& tmHi, const CUtensorMap& tmLo, const CUtensorMap& tmW, ConvTcParams p, cudaStream_t st) {
   using C = ConvCfg<N_T, T>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(conv_tc_kernel<N_T, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
   }
   p.tiles_x = i4d_cdiv(p.W, 8 * T);
   p.tiles_y = i4d_cdiv(p.H, CV_TILE_H);

@@ -190,10 +190,9 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_f32(const fl
   I4D_CHECK_ARG((ldo & 3) == 0, "ldo must be a multiple of 4 floats");
   if (Nq == 0) return I4D_OK;
   size_t smem = (size_t)(2 * AD * (AT + 4) + AT * (AD + 4) + AT * (AT + 4)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   dim3 grid(i4d_cdiv(Nq, AT), heads);
   attn_f32_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, Nq, Nk, scale);

@@ -340,10 +340,9 @@ extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
   if (R) { if (int rc = make_tmap_2d_f32(&tmR, R, (uint64_t)M, (uint64_t)N, (uint64_t)ldr, GT_BM, 32)) return rc; }
   if (C32) { if (int rc = make_tmap_2d_f32(&tmC32, C32, (uint64_t)M, (uint64_t)N, (uint64_t)ldc32, GT_BM, 32)) return rc; }
   if (C16) { if (int rc = i4d_make_tmap_2d_bf16(&tmC16, C16, (uint64_t)M, (uint64_t)N, (uint64_t)ldc16, GT_BM, 64)) return rc; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
-    attr_set = true;
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("I4D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }

@@ -1,7 +1,17 @@
 // Fundamental-matrix robust estimation on sm_100a: batched-hypothesis RANSAC (8-point minimal solves, one thread
-// per hypothesis; one warp per hypothesis for consensus scoring) followed by a sigma-consensus (MAGSAC++-style)
-// iteratively re-weighted least-squares polish over all correspondences, all on the device without host syncs.
-// f64 throughout the solvers, -fmad=false.
+// per hypothesis; one warp per hypothesis for consensus scoring) with the MAGSAC++ marginalised (sigma-consensus++)
+// quality function, followed by the MAGSAC++ iteratively re-weighted least-squares polisher over all correspondences run
+// to its fixed point, all on the device without host syncs.  f64 throughout the solvers, -fmad=false.
+//
+// MAGSAC++ (Barath et al., CVPR 2020) as OpenCV's USAC implements it (opencv/modules/calib3d/src/usac/quality.cpp,
+// not vendored in the reference: OpenCV is an unpinned wheel dependency, 4.13.0 in the build container): residuals are
+// squared Sampson errors, noise scale marginalised over sigma in (0, sigma_max], DoF n = 4, k = 3.64 (0.99 quantile of chi_4):
+//   weight(r^2) = Gamma((n-1)/2, r^2/(2 sigma_max^2)) - Gamma((n-1)/2, k^2/2)                          for r < k sigma_max, else 0
+//   loss(r^2)   = 2^((n+1)/2)/sigma_max * [ sigma_max^2/2 * gamma((n+1)/2, x) + r^2/4 * weight(r^2) ],  x = r^2/(2 sigma_max^2)
+//   quality     = sum over r < k sigma_max of (1 - loss / loss(k sigma_max))
+// The incomplete gamma functions OpenCV tabulates have closed forms for n = 4 (erfc / exp), evaluated directly here.
+// sigma_max is not an argument of cv2.findFundamentalMat: scripts/magsac_probe.py fits the cut-off k*sigma_max = 4.5 px to
+// the models OpenCV 4.13 returns (their one-step IRLS displacement is minimal there for every threshold tried).
 //
 // Reference behaviour replaced (paths into /root/reference/src/icepy4d):
 //   matching/geometric_verification.py:43-102   pydegensac.findFundamentalMatrix | cv2.findFundamentalMat(USAC_MAGSAC, 0.5, 0.999, 100000)
@@ -23,9 +33,14 @@ struct RansacState {
   int done;                     // termination flag (confidence reached)
   int hyp_tested;
   int topk[RS_TOPK];
-  double cov[45];               // weighted 9x9 moment matrix (upper triangle) for the polish
   double polishF[9];
+  double final_score[2];        // quality of {bestF, polishF} under the selection rule of the polish mode
+  int converged;                // polisher reached its fixed point: the remaining polish launches are no-ops
+  int polish_done;              // polish iterations executed
+  int failed;                   // no model with >= 8 inliers: mask = all ones, F = NaN (the reference's degrade path)
+  int use_polished;
 };
+#define RS_POLISH_GRID_MAX 320
 
 __device__ __forceinline__ unsigned int rs_hash(unsigned int a, unsigned int b, unsigned int c) {
   unsigned int x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
@@ -47,6 +62,44 @@ __device__ __forceinline__ float sampson_sq_f(const float* F, float x0, float y0
   float e = x1 * a0 + y1 * a1 + a2;
   float den = a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
   return den > 0.f ? e * e / den : 3e38f;
+}
+
+// ---- MAGSAC++ quality / weight (n = 4 degrees of freedom) ----------------------------------------------------
+// Gamma(3/2, x) = sqrt(pi)/2 erfc(sqrt x) + sqrt(x) exp(-x);  Gamma(5/2, x) = 3/2 Gamma(3/2, x) + x^(3/2) exp(-x)
+__device__ __forceinline__ double upper_gamma_1p5(double x) {
+  double sx = sqrt(x);
+  return 0.886226925452758 * erfc(sx) + sx * exp(-x);
+}
+struct MagsacConst {
+  double inv_2s2;      // 1 / (2 sigma_max^2)
+  double cut2;         // (k sigma_max)^2
+  double g_off;        // Gamma(3/2, k^2/2)
+  double half_s2;      // sigma_max^2 / 2
+  double inv_max_loss; // 1 / [ sigma_max^2/2 * gamma(5/2, k^2/2) ]   (the common factor 2^(5/2)/sigma_max cancels)
+};
+__host__ __device__ inline MagsacConst magsac_const(double sigma_max, double kq) {
+  MagsacConst c;
+  c.inv_2s2 = 1.0 / (2.0 * sigma_max * sigma_max);
+  c.cut2 = kq * kq * sigma_max * sigma_max;
+  const double xk = kq * kq * 0.5, sxk = sqrt(xk);
+  c.g_off = 0.886226925452758 * erfc(sxk) + sxk * exp(-xk);
+  c.half_s2 = 0.5 * sigma_max * sigma_max;
+  const double up25 = 1.5 * c.g_off + xk * sxk * exp(-xk);
+  c.inv_max_loss = 1.0 / (c.half_s2 * (1.329340388179137 - up25));
+  return c;
+}
+// 1 - loss/max_loss for a squared residual below the cut-off
+__device__ __forceinline__ double magsac_gain(const MagsacConst& c, double e) {
+  const double x = e * c.inv_2s2, sx = sqrt(x), ex = exp(-x);
+  const double up15 = 0.886226925452758 * erfc(sx) + sx * ex;
+  const double lo25 = 1.329340388179137 - (1.5 * up15 + x * sx * ex);
+  return 1.0 - (c.half_s2 * lo25 + 0.25 * e * (up15 - c.g_off)) * c.inv_max_loss;
+}
+__device__ __forceinline__ float magsac_gain_f(float inv_2s2, float g_off, float half_s2, float inv_max_loss, float e) {
+  const float x = e * inv_2s2, sx = sqrtf(x), ex = __expf(-x);
+  const float up15 = 0.8862269f * erfcf(sx) + sx * ex;
+  const float lo25 = 1.3293404f - (1.5f * up15 + x * sx * ex);
+  return 1.f - (half_s2 * lo25 + 0.25f * e * (up15 - g_off)) * inv_max_loss;
 }
 
 // ---- normalisation statistics (single CTA; N up to a few 100k) ------------------------------------------
@@ -89,6 +142,7 @@ __global__ void __launch_bounds__(1024) rs_norm_kernel(const float* __restrict__
   }
   if (threadIdx.x == 0) {
     st->best_score = -1.0; st->best_inliers = 0; st->done = 0; st->hyp_tested = 0;
+    st->converged = 0; st->polish_done = 0; st->failed = 0; st->use_polished = 0;
     for (int i = 0; i < 9; ++i) st->bestF[i] = 0.0;
   }
 }
@@ -224,10 +278,10 @@ __global__ void __launch_bounds__(128) rs_hypotheses_kernel(const float* __restr
   hyp_ok[h] = ok ? 1 : 0;
 }
 
-// truncated-quadratic consensus score (MSAC form) with cut-off c2 = (k * sigma_max)^2 on the Sampson error
+// MAGSAC++ quality of every hypothesis on a strided subsample (f32: this pass only ranks hypotheses for the full scoring)
 __global__ void __launch_bounds__(256) rs_prescore_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                                           int n, const float* __restrict__ hypF,
-                                                          const int* __restrict__ hyp_ok, float c2,
+                                                          const int* __restrict__ hyp_ok, MagsacConst mc,
                                                           const RansacState* st, float* __restrict__ score) {
   int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (h >= RS_BATCH) return;
@@ -237,12 +291,14 @@ __global__ void __launch_bounds__(256) rs_prescore_kernel(const float* __restric
   for (int i = 0; i < 9; ++i) F[i] = __ldg(hypF + h * 9 + i);
   const int sub = min(n, RS_SUB);
   const long long stride = n / sub;
+  const float c2 = (float)mc.cut2, i2s = (float)mc.inv_2s2, goff = (float)mc.g_off, hs2 = (float)mc.half_s2,
+              iml = (float)mc.inv_max_loss;
   float acc = 0.f;
   for (int i = lane; i < sub; i += 32) {
     long long p = (long long)i * stride;
     float2 a = __ldg(reinterpret_cast<const float2*>(x0) + p), b = __ldg(reinterpret_cast<const float2*>(x1) + p);
     float e = sampson_sq_f(F, a.x, a.y, b.x, b.y);
-    acc += fmaxf(0.f, 1.f - e / c2);
+    if (e < c2) acc += fmaxf(0.f, magsac_gain_f(i2s, goff, hs2, iml, e));
   }
   acc = warp_sum(acc);
   if (lane == 0) score[h] = acc;
@@ -273,7 +329,7 @@ __global__ void __launch_bounds__(1024) rs_topk_kernel(const float* __restrict__
 
 // full scoring of the RS_TOPK candidates on all points: one CTA per candidate
 __global__ void __launch_bounds__(512) rs_fullscore_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int n,
-                                                           const float* __restrict__ hypF, double c2, double thr2,
+                                                           const float* __restrict__ hypF, MagsacConst mc, double thr2,
                                                            const RansacState* st, double* __restrict__ cand_score,
                                                            int* __restrict__ cand_inl) {
   __shared__ double rs[16];
@@ -288,7 +344,7 @@ __global__ void __launch_bounds__(512) rs_fullscore_kernel(const float* __restri
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float2 a = __ldg(reinterpret_cast<const float2*>(x0) + i), b = __ldg(reinterpret_cast<const float2*>(x1) + i);
     double e = sampson_sq(F, a.x, a.y, b.x, b.y);
-    if (e < c2) acc += 1.0 - e / c2;
+    if (e < mc.cut2) acc += magsac_gain(mc, e);
     inl += e < thr2;
   }
   for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); inl += __shfl_xor_sync(0xffffffffu, inl, o); }
@@ -324,32 +380,34 @@ __global__ void rs_update_kernel(const float* __restrict__ hypF, const double* _
   if (enough || st->hyp_tested >= max_hyp) st->done = 1;
 }
 
-// ---- sigma-consensus IRLS polish ------------------------------------------------------------------------
-// weight(r) = Gamma(3/2, r^2 / (2 s^2)) - Gamma(3/2, k^2 / 2) for r < k s (MAGSAC++ with 4 degrees of freedom),
-// Gamma(3/2, x) = sqrt(pi)/2 erfc(sqrt x) + sqrt(x) exp(-x)
-__device__ __forceinline__ double upper_gamma_1p5(double x) {
-  double sx = sqrt(x);
-  return 0.886226925452758 * erfc(sx) + sx * exp(-x);
-}
-
+// ---- polisher -----------------------------------------------------------------------------------------------
+// mode 0 (MAGSAC):     MAGSAC++ weights (see the header), iterated to the fixed point of the re-weighted normalised 8-point fit.
+// mode 1 (LO-RANSAC):  unit weights on the inliers at the caller's threshold (the final least squares on inliers of
+//                      pydegensac's LO-RANSAC, matching/geometric_verification.py:66-76), iterated until the set is stable.
+// Per-CTA partial moment matrices go to a workspace and are summed in a fixed order (no atomics: bit-reproducible).
 __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
-                                                              int n, double sigma_max, double kq, RansacState* st,
-                                                              int use_best) {
+                                                              int n, MagsacConst mc, double thr2, int mode,
+                                                              const RansacState* st, double* __restrict__ partial) {
   __shared__ double red[8][45];
-  const double* Fc = use_best ? st->bestF : st->polishF;
+  if (st->converged || st->failed) return;
   double F[9];
-  for (int i = 0; i < 9; ++i) F[i] = Fc[i];
+  for (int i = 0; i < 9; ++i) F[i] = st->polishF[i];
   const double s0 = st->T0[0], cx0 = st->T0[1], cy0 = st->T0[2], s1 = st->T1[0], cx1 = st->T1[1], cy1 = st->T1[2];
-  const double cut2 = kq * kq * sigma_max * sigma_max, g_off = upper_gamma_1p5(kq * kq * 0.5);
   double acc[45];
 #pragma unroll
   for (int i = 0; i < 45; ++i) acc[i] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float2 a = __ldg(reinterpret_cast<const float2*>(x0) + i), b = __ldg(reinterpret_cast<const float2*>(x1) + i);
     double e = sampson_sq(F, a.x, a.y, b.x, b.y);
-    if (e >= cut2) continue;
-    double w = upper_gamma_1p5(e / (2.0 * sigma_max * sigma_max)) - g_off;
-    if (w <= 0) continue;
+    double w;
+    if (mode == 0) {
+      if (e >= mc.cut2) continue;
+      w = upper_gamma_1p5(e * mc.inv_2s2) - mc.g_off;
+      if (w <= 0) continue;
+    } else {
+      if (e >= thr2) continue;
+      w = 1.0;
+    }
     double ax = s0 * ((double)a.x - cx0), ay = s0 * ((double)a.y - cy0);
     double bx = s1 * ((double)b.x - cx1), by = s1 * ((double)b.y - cy1);
     double v[9] = {bx * ax, bx * ay, bx, by * ax, by * ay, by, ax, ay, 1.0};
@@ -369,26 +427,33 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
   if (threadIdx.x < 45) {
     double t = 0;
     for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    atomicAdd(&st->cov[threadIdx.x], t);
+    partial[(size_t)blockIdx.x * 45 + threadIdx.x] = t;
   }
 }
 
-// Smallest eigenvector of the 9x9 moment matrix, rank-2 projection, denormalisation.
+// Smallest eigenvector of the 9x9 moment matrix, rank-2 projection, denormalisation, convergence test.
 // The matrix is symmetric positive semi-definite with one eigenvalue far below the rest (the epipolar constraint), so inverse
-// iteration on C + eps*I (one Cholesky factorisation, two triangular solves per step, f64) converges in a handful of steps —
-// ~10 us on one thread where the cyclic Jacobi sweep this replaces took ~100 us per polish iteration (20 per verification).
-__global__ void __launch_bounds__(32) rs_polish_solve_kernel(RansacState* st) {
+// iteration on C + eps*I (one Cholesky factorisation, two triangular solves per step, f64) converges in a handful of steps.
+__global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, const double* __restrict__ partial, int n_partial,
+                                                             double tol) {
+  __shared__ double cov[45];
+  if (st->converged || st->failed) return;
+  if (threadIdx.x < 45) {
+    double t = 0;
+    for (int b = 0; b < n_partial; ++b) t += partial[(size_t)b * 45 + threadIdx.x];
+    cov[threadIdx.x] = t;
+  }
+  __syncthreads();
   if (threadIdx.x != 0) return;
   double L[9][9];
   double tr = 0;
   {
     int t = 0;
     for (int p = 0; p < 9; ++p)
-      for (int q = p; q < 9; ++q) { L[q][p] = st->cov[t]; L[p][q] = st->cov[t]; ++t; }
-    for (int i = 0; i < 45; ++i) st->cov[i] = 0.0;
+      for (int q = p; q < 9; ++q) { L[q][p] = cov[t]; L[p][q] = cov[t]; ++t; }
     for (int p = 0; p < 9; ++p) tr += L[p][p];
   }
-  if (!(tr > 0)) return;              // no support: keep the previous model
+  if (!(tr > 0)) { st->converged = 1; return; }   // no support: keep the previous model
   const double eps = 1e-13 * tr;
   // Cholesky of C + eps I (lower triangle, in place)
   for (int j = 0; j < 9; ++j) {
@@ -436,13 +501,48 @@ __global__ void __launch_bounds__(32) rs_polish_solve_kernel(RansacState* st) {
   rs_denormalise(Fn, st->T0, st->T1, F);
   bool ok = true;
   for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
-  if (ok) for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
+  if (!ok) { st->converged = 1; return; }
+  // fixed point reached?  (unit Frobenius norm on both sides, sign-aligned)
+  double dp = 0, dm = 0;
+  for (int i = 0; i < 9; ++i) {
+    dp = fmax(dp, fabs(F[i] - st->polishF[i]));
+    dm = fmax(dm, fabs(F[i] + st->polishF[i]));
+  }
+  for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
+  st->polish_done += 1;
+  if (fmin(dp, dm) < tol) st->converged = 1;
 }
 
-__global__ void rs_copy_best_kernel(RansacState* st) {
+__global__ void rs_begin_polish_kernel(RansacState* st) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 9; ++i) st->polishF[i] = st->bestF[i];
-    for (int i = 0; i < 45; ++i) st->cov[i] = 0.0;
+    if (st->best_inliers < 8) st->failed = 1;
+  }
+}
+
+// Quality of {bestF, polishF} on all points under the selection rule of the mode (MAGSAC++ quality / inlier count at the
+// threshold): the polished model is kept only if it is at least as good as the RANSAC winner it started from.
+__global__ void __launch_bounds__(512) rs_final_score_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int n,
+                                                             MagsacConst mc, double thr2, int mode, RansacState* st) {
+  __shared__ double rs[16];
+  if (st->failed) return;
+  const double* Fc = blockIdx.x == 0 ? st->bestF : st->polishF;
+  double F[9];
+  for (int i = 0; i < 9; ++i) F[i] = Fc[i];
+  double acc = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float2 a = __ldg(reinterpret_cast<const float2*>(x0) + i), b = __ldg(reinterpret_cast<const float2*>(x1) + i);
+    double e = sampson_sq(F, a.x, a.y, b.x, b.y);
+    if (mode == 0) { if (e < mc.cut2) acc += magsac_gain(mc, e); }
+    else acc += e < thr2 ? 1.0 : 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) rs[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 16; ++w) t += rs[w];
+    st->final_score[blockIdx.x] = t;
   }
 }
 
@@ -450,17 +550,19 @@ __global__ void __launch_bounds__(256) rs_mask_kernel(const float* __restrict__ 
                                                       double thr2, const RansacState* st, unsigned char* __restrict__ mask,
                                                       int* __restrict__ n_inl, double* __restrict__ F_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool failed = st->failed != 0;
+  const double* Fc = (st->final_score[1] >= st->final_score[0]) ? st->polishF : st->bestF;
   double F[9];
-  for (int k = 0; k < 9; ++k) F[k] = st->polishF[k];
+  for (int k = 0; k < 9; ++k) F[k] = Fc[k];
   if (i == 0) {
-    // scale like OpenCV (F[2][2] = 1) when possible
+    // scale like OpenCV (F[2][2] = 1) when possible; NaN marks "no model" (the caller returns F = None, all-inlier mask)
     double s = fabs(F[8]) > 1e-300 ? 1.0 / F[8] : 1.0;
-    for (int k = 0; k < 9; ++k) F_out[k] = F[k] * s;
+    for (int k = 0; k < 9; ++k) F_out[k] = failed ? __longlong_as_double(0x7ff8000000000000LL) : F[k] * s;
   }
   int inl = 0;
   if (i < n) {
     float2 a = __ldg(reinterpret_cast<const float2*>(x0) + i), b = __ldg(reinterpret_cast<const float2*>(x1) + i);
-    inl = sampson_sq(F, a.x, a.y, b.x, b.y) < thr2;
+    inl = failed ? 1 : (sampson_sq(F, a.x, a.y, b.x, b.y) < thr2);
     mask[i] = (unsigned char)inl;
   }
   unsigned int bal = __ballot_sync(0xffffffffu, inl);
@@ -469,16 +571,17 @@ __global__ void __launch_bounds__(256) rs_mask_kernel(const float* __restrict__ 
 
 extern "C" __attribute__((visibility("default"))) size_t i4d_fundamental_workspace_bytes(void) {
   return sizeof(RansacState) + (size_t)RS_BATCH * (9 * sizeof(float) + sizeof(int) + sizeof(float)) +
-         RS_TOPK * (sizeof(double) + sizeof(int)) + 256;
+         RS_TOPK * (sizeof(double) + sizeof(int)) + (size_t)RS_POLISH_GRID_MAX * 45 * sizeof(double) + 512;
 }
 
 extern "C" __attribute__((visibility("default"))) int i4d_fundamental_ransac(
     const float* x0, const float* x1, int n, double threshold, double confidence, int max_iters, unsigned int seed,
-    double sigma_max, int polish_iters, double* F_out, unsigned char* mask, int* n_inliers, void* workspace,
+    double sigma_max, int polish_iters, int polish_mode, double* F_out, unsigned char* mask, int* n_inliers, void* workspace,
     size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(x0 && x1 && F_out && mask && n_inliers && workspace, "null pointer");
   I4D_CHECK_ARG(n >= 8, "need at least 8 correspondences");
   I4D_CHECK_ARG(threshold > 0 && confidence > 0 && confidence < 1 && max_iters > 0 && sigma_max > 0, "bad parameters");
+  I4D_CHECK_ARG(polish_mode == 0 || polish_mode == 1, "polish_mode must be 0 (MAGSAC++) or 1 (LO-RANSAC)");
   if (workspace_bytes < i4d_fundamental_workspace_bytes()) {
     i4d_set_error("i4d_fundamental_ransac: workspace too small");
     return I4D_ERR_WORKSPACE;
@@ -490,9 +593,12 @@ extern "C" __attribute__((visibility("default"))) int i4d_fundamental_ransac(
   int* hyp_ok = reinterpret_cast<int*>(w); w += (size_t)RS_BATCH * sizeof(int);
   float* score = reinterpret_cast<float*>(w); w += (size_t)RS_BATCH * sizeof(float);
   double* cand_score = reinterpret_cast<double*>(w); w += RS_TOPK * sizeof(double);
-  int* cand_inl = reinterpret_cast<int*>(w);
+  int* cand_inl = reinterpret_cast<int*>(w); w += RS_TOPK * sizeof(int);
+  w = reinterpret_cast<char*>(((uintptr_t)w + 15) & ~(uintptr_t)15);
+  double* partial = reinterpret_cast<double*>(w);
   const double kq = 3.64;  // 0.99 quantile of the chi distribution with 4 degrees of freedom
-  const double c2 = kq * kq * sigma_max * sigma_max, thr2 = threshold * threshold;
+  const MagsacConst mc = magsac_const(sigma_max, kq);
+  const double thr2 = threshold * threshold;
   I4D_CUDA_CALL(cudaMemsetAsync(n_inliers, 0, sizeof(int), st));
   rs_norm_kernel<<<1, 1024, 0, st>>>(x0, x1, n, state);
   int rounds = i4d_cdiv(max_iters, RS_BATCH);
@@ -500,18 +606,20 @@ extern "C" __attribute__((visibility("default"))) int i4d_fundamental_ransac(
   const int max_hyp = rounds * RS_BATCH;
   for (int r = 0; r < rounds; ++r) {
     rs_hypotheses_kernel<<<RS_BATCH / 128, 128, 0, st>>>(x0, x1, n, seed, r, state, hypF, hyp_ok);
-    rs_prescore_kernel<<<RS_BATCH * 32 / 256, 256, 0, st>>>(x0, x1, n, hypF, hyp_ok, (float)c2, state, score);
+    rs_prescore_kernel<<<RS_BATCH * 32 / 256, 256, 0, st>>>(x0, x1, n, hypF, hyp_ok, mc, state, score);
     rs_topk_kernel<<<1, 1024, 0, st>>>(score, state);
-    rs_fullscore_kernel<<<RS_TOPK, 512, 0, st>>>(x0, x1, n, hypF, c2, thr2, state, cand_score, cand_inl);
+    rs_fullscore_kernel<<<RS_TOPK, 512, 0, st>>>(x0, x1, n, hypF, mc, thr2, state, cand_score, cand_inl);
     rs_update_kernel<<<1, 32, 0, st>>>(hypF, cand_score, cand_inl, n, confidence, max_hyp, state);
   }
-  rs_copy_best_kernel<<<1, 32, 0, st>>>(state);
+  rs_begin_polish_kernel<<<1, 32, 0, st>>>(state);
   int grid = 2 * i4d_num_sms();
+  if (grid > RS_POLISH_GRID_MAX) grid = RS_POLISH_GRID_MAX;
   if (grid > i4d_cdiv(n, 256)) grid = i4d_cdiv(n, 256);
   for (int it = 0; it < polish_iters; ++it) {
-    rs_polish_accum_kernel<<<grid, 256, 0, st>>>(x0, x1, n, sigma_max, kq, state, 0);
-    rs_polish_solve_kernel<<<1, 32, 0, st>>>(state);
+    rs_polish_accum_kernel<<<grid, 256, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state, partial);
+    rs_polish_solve_kernel<<<1, 64, 0, st>>>(state, partial, grid, 1e-13);
   }
+  rs_final_score_kernel<<<2, 512, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state);
   rs_mask_kernel<<<i4d_cdiv(n, 256), 256, 0, st>>>(x0, x1, n, thr2, state, mask, n_inliers, F_out);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;

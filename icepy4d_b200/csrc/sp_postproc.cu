@@ -586,14 +586,13 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_nms_candidates(cons
   I4D_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int), st));
   const int D = NMS_T + 10 * nms_radius, Dp = D | 1;
   const size_t smem = (size_t)D * Dp * (3 * sizeof(float) + 2) + (nms_radius == 0 ? 16 + NMS_T * NMS_T * 8 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_nms_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_nms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_nms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_nms_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_nms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   dim3 grid(i4d_cdiv(W, NMS_T), i4d_cdiv(H, NMS_T));
   switch (nms_radius) {
@@ -613,11 +612,10 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_select_topk(const u
   I4D_CHECK_ARG(cand_keys && cand_count && kpts && scores && n_out && spill, "null pointer");
   I4D_CHECK_ARG(out_cap > 0 && cand_cap > 0 && W > 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(sp_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SEL_MAX_SMEM_KEYS * 8));
-    attr_set = true;
   }
   if (k >= 1 && k <= SEL_MAX_SMEM_KEYS) {
     // multi-CTA radix select; scratch: `spill` holds [TopkState | selected keys (k) | ties (rest)]

@@ -39,6 +39,8 @@ class StereoEpochPipeline:
 
     # -- device-resident: inputs already in HBM, results stay in HBM (kernel-only throughput) --
     def run_device(self, dev0: torch.Tensor, dev1: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if self.quality != Quality.HIGH:                     # matchers.py:583-610 on the device (bit-exact pyrDown / pyrUp)
+            dev0, dev1 = self.matcher._resize_images_device(self.quality, dev0, dev1)
         mk0, mk1, s0, s1, conf, d0, d1, F = self.matcher.match_device(dev0, dev1, self.quality, self.tile_selection,
                                                                       **self.match_config)
         out = {"mkpts0": mk0, "mkpts1": mk1, "scores0": s0, "F": F}
@@ -80,6 +82,64 @@ def gather_results(local: Dict[int, np.ndarray], world_size: int, group=None) ->
     for part in bucket:
         out.update(part)
     return out
+
+
+def gather_results_device(local: Dict[int, torch.Tensor], world_size: int, group=None) -> Dict[int, torch.Tensor]:
+    """The same single end-of-run exchange for device-resident results, without pickling: {epoch: [n_e, C] tensor} per rank ->
+    the union on every rank.  Two collectives in total: the (epoch id, row count) tables, then ONE all_gather of the rank's
+    results concatenated and padded to the longest rank (NCCL over NVLink on GPUs; gloo on CPU tensors).  Ranks may hold
+    different numbers of epochs and rows; C and dtype must agree."""
+    import torch.distributed as dist
+
+    if world_size == 1 or not dist.is_initialized():
+        return dict(local)
+    keys = sorted(local)
+    ref = local[keys[0]] if keys else None
+    dev = ref.device if ref is not None else torch.device("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    # table exchange: [n_epochs, (epoch, rows)...] padded to the largest table
+    n_max = torch.tensor([len(keys)], dtype=torch.int64, device=dev)
+    dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
+    n_max = int(n_max.item())
+    meta = torch.full((1 + 2 * n_max + 2,), -1, dtype=torch.int64, device=dev)
+    meta[0] = len(keys)
+    for i, k in enumerate(keys):
+        meta[1 + 2 * i], meta[2 + 2 * i] = int(k), int(local[k].shape[0])
+    cols = int(np.prod(ref.shape[1:])) if ref is not None else 1
+    meta[-2], meta[-1] = cols, sum(int(local[k].shape[0]) for k in keys)
+    metas = [torch.empty_like(meta) for _ in range(world_size)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.cpu() for m in metas]
+    rows_max = max(int(m[-1]) for m in metas)
+    cols = max(int(m[-2]) for m in metas)
+    dtype = ref.dtype if ref is not None else torch.float64
+    flat = torch.zeros((max(rows_max, 1), cols), dtype=dtype, device=dev)
+    if keys:
+        cat = torch.cat([local[k].reshape(local[k].shape[0], cols) for k in keys])
+        flat[: cat.shape[0]] = cat
+    bucket = [torch.empty_like(flat) for _ in range(world_size)]
+    dist.all_gather(bucket, flat, group=group)
+    out: Dict[int, torch.Tensor] = {}
+    for m, buf in zip(metas, bucket):
+        off = 0
+        for i in range(int(m[0])):
+            e, r = int(m[1 + 2 * i]), int(m[2 + 2 * i])
+            out[e] = buf[off:off + r]
+            off += r
+    return out
+
+
+def make_cfg1_pipeline(max_keypoints: int = 2048, precision: str = "f32", conv_precision: str = "f16x3", cameras=None) -> StereoEpochPipeline:
+    """BASELINE.json configs[0]: the notebook's single stereo epoch — SuperPoint + LightGlue, 2048 kp, 6000x4000 downsampled to
+    1500x1000 (Quality.LOW = two pyrDown), one tile (GRID [1,1]; TileSelection.NONE is buggy in the reference, App. D.1)."""
+    from . import synthetic, weights
+
+    m = LightGlueMatcher({"features": "superpoint", "superpoint_state": weights.make_superpoint_state(1),
+                          "lightglue_state": weights.make_lightglue_state(3), "precision": precision,
+                          "conv_precision": conv_precision})
+    if cameras is None:
+        cameras = synthetic.two_view_scene(n=8, seed=0, outlier_frac=0.0)["cams"]
+    return StereoEpochPipeline(m, cameras, Quality.LOW, TileSelection.GRID, grid=[1, 1], overlap=0,
+                               max_keypoints=max_keypoints, geometric_verification=GeometricVerification.MAGSAC)
 
 
 def make_cfg2_pipeline(max_keypoints: int = 8192, sinkhorn_iterations: int = 100, precision: str = "f32",

@@ -2,9 +2,15 @@
 (icepy4d/matching/geometric_verification.py:11-102), computed by the batched-hypothesis CUDA RANSAC.
 
 Reference semantics kept: fewer than 4 matches -> (None, all-True); the MAGSAC branch ignores the caller's
-threshold/confidence/max_iters and uses (0.5 px, 0.999, 100000) (geometric_verification.py:89-91, Appendix D.5);
-failures degrade to an all-inlier mask and are logged, never raised.  PYDEGENSAC honours the caller's parameters
-(px threshold on the Sampson error, like pydegensac's `error_type="sampson"`).
+threshold/confidence/max_iters and uses (0.5 px, 0.999, 100000) (geometric_verification.py:89-91, Appendix D.5) with the
+MAGSAC++ quality function and polisher of cv2.USAC_MAGSAC; failures degrade to an all-inlier mask with F = None and are
+logged, never raised (:96-100).
+
+PYDEGENSAC branch (the reference's default, :66-76): pydegensac is not installed in the reference's own environment here and
+its source is not vendored, so its output cannot be pinned.  What is matched is its documented behaviour: LO-RANSAC on the
+Sampson error with the CALLER's px threshold, confidence and max_iters, the model being the least-squares fit on its own
+inliers (`polish_mode=1`).  Not reproduced: DEGENSAC's plane-degeneracy (H-consistency) test, the LAF check and the symmetric
+error check — the arguments are accepted and ignored.
 """
 from __future__ import annotations
 
@@ -28,10 +34,12 @@ def geometric_verification_device(mkpts0: torch.Tensor, mkpts1: torch.Tensor,
     n = mkpts0.shape[0]
     if n < 8:
         return None, torch.ones(n, dtype=torch.bool, device=mkpts0.device)
+    polish_mode = 1
     if method == GeometricVerification.MAGSAC:
         threshold, confidence, max_iters = MAGSAC_PARAMS
+        polish_mode = 0
     F, mask, _ = ops.fundamental_ransac(mkpts0.contiguous(), mkpts1.contiguous(), threshold, min(confidence, 0.999999),
-                                        max_iters, seed)
+                                        max_iters, seed, polish_mode=polish_mode)
     return F, mask.bool()
 
 
@@ -53,6 +61,9 @@ def geometric_verification(mkpts0: np.ndarray = None, mkpts1: np.ndarray = None,
         if Fd is not None:
             F = Fd.cpu().numpy().reshape(3, 3)
             inl = mask.cpu().numpy()
+            if not np.isfinite(F).all():        # no model with >= 8 inliers: the reference's degrade path (:96-100)
+                logger.error("RANSAC found no model. Unable to perform geometric verification.")
+                return None, np.ones(len(mkpts0), dtype=bool)
             logger.info(f"B200 RANSAC found {inl.sum()} inliers ({inl.sum() * 100 / len(mkpts0):.2f}%)")
     except Exception as err:  # same degrade-don't-raise convention as the reference (:96-100)
         logger.error(f"{err}. Unable to perform geometric verification.")

@@ -182,6 +182,8 @@ class ImageMatcherBase(ImageMatcherABC):
         finally:
             self._row_events = {}
         self._F = F.cpu().numpy().reshape(3, 3) if F is not None else None
+        if self._F is not None and not np.isfinite(self._F).all():    # no model found: the mask was all ones (degrade path)
+            self._F = None
         self._store_device_results(mk0, mk1, s0, s1, conf, d0, d1)
         if self._save_dir is not None:
             self.save_mkpts_as_txt(self._save_dir)

@@ -344,10 +344,15 @@ def triangulate_dlt(x1: torch.Tensor, x2: torch.Tensor, P1: np.ndarray, P2: np.n
     return X
 
 
+MAGSAC_SIGMA_MAX = 4.5 / 3.64     # cut-off k * sigma_max = 4.5 px: fitted to OpenCV 4.13's USAC_MAGSAC output (scripts/magsac_probe.py)
+
+
 def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.5, confidence: float = 0.999,
-                       max_iters: int = 100000, seed: int = 0, sigma_max: float = 1.0, polish_iters: int = 20,
-                       ws: Optional[torch.Tensor] = None):
-    """x0, x1 [n,2] f32 -> (F [9] f64 device, mask [n] u8 device, n_inliers int32[1] device)."""
+                       max_iters: int = 100000, seed: int = 0, sigma_max: float = MAGSAC_SIGMA_MAX, polish_iters: int = 64,
+                       polish_mode: int = 0, ws: Optional[torch.Tensor] = None):
+    """x0, x1 [n,2] f32 -> (F [9] f64 device, mask [n] u8 device, n_inliers int32[1] device).
+    polish_mode 0 = MAGSAC++ weights (cv2 USAC_MAGSAC), 1 = least squares on the inliers at `threshold` (LO-RANSAC).
+    F is NaN and the mask all ones when no model with >= 8 inliers exists (the reference's degrade path)."""
     _chk(x0, name="x0"), _chk(x1, name="x1")
     n = x0.shape[0]
     dev = x0.device
@@ -358,7 +363,7 @@ def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.
     mask = torch.zeros(n, device=dev, dtype=torch.uint8)
     n_inl = torch.zeros(1, device=dev, dtype=torch.int32)
     N.call("i4d_fundamental_ransac", x0, x1, n, float(threshold), float(confidence), int(max_iters), int(seed) & 0xFFFFFFFF,
-           float(sigma_max), int(polish_iters), F, mask, n_inl, ws, ws.numel(), _st())
+           float(sigma_max), int(polish_iters), int(polish_mode), F, mask, n_inl, ws, ws.numel(), _st())
     return F, mask, n_inl
 
 

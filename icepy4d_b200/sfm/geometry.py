@@ -40,6 +40,6 @@ def estimate_pose(kpts0, kpts1, K0, K1, thresh, conf=0.9999):
         E = (D[:, None] * Fs.view(3, 3) * D[None, :]).reshape(9)
     else:
         raise ValueError("estimate_pose needs at least 8 correspondences on the B200 path")
-    assert bool(torch.isfinite(E).all()), "Unable to estimate Essential matrix"
+    assert bool(torch.isfinite(E).all()) and float(E.abs().max()) > 0, "Unable to estimate Essential matrix"   # geometry.py:74
     _, R, t, mask, n_good = ops.essential_pose(E, xn0, xn1, norm_thresh, 1e9)
     return R.view(3, 3).cpu().numpy(), t.cpu().numpy(), mask.cpu().numpy() > 0

@@ -24,9 +24,10 @@ class RelativeOrientation:
     def estimate_F_matrix(self, threshold: float = 1, confidence: float = 0.9999, max_iters: int = 10000,
                           laf_consistensy_coef: float = -1.0, error_type: str = "sampson",
                           symmetric_error_check: bool = True, enable_degeneracy_check: bool = True):
-        # pydegensac is absent here as it is in the reference's own fallback: the reference then runs MAGSAC with
-        # its hard-coded parameters (two_view_geometry.py:180-187)
-        self.F, self.inlMask = geometric_verification(self.features[0], self.features[1], GeometricVerification.MAGSAC,
+        # two_view_geometry.py:165-175: the pydegensac branch honours the caller's threshold / confidence / max_iters (the
+        # MAGSAC fallback of :180-187, taken when pydegensac is missing, replaces them by 0.5 px / 0.999 / 100000 and then
+        # raises IndexError, Appendix D.6).  The arguments are part of this method's contract, so they take effect here.
+        self.F, self.inlMask = geometric_verification(self.features[0], self.features[1], GeometricVerification.PYDEGENSAC,
                                                       threshold, confidence, max_iters)
         logging.info(f"found {self.inlMask.sum()} inliers ({self.inlMask.sum() * 100 / max(1, len(self.features[0])):.2f}%)")
         self.features[0] = self.features[0][self.inlMask]

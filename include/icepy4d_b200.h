@@ -167,14 +167,20 @@ int i4d_interpolate_point_colors(const double* X, int n, const double* R_host, c
                                  int convert_bgr2rgb, double* colors, float* projections, void* stream);
 
 /* matching/geometric_verification.py:43-102 and sfm/two_view_geometry.py:127-197 — robust fundamental matrix.
- * Batched-hypothesis RANSAC (8-point samples drawn from `seed`, consensus with a truncated quadratic of cut-off
- * 3.64*sigma_max on the Sampson error) + sigma-consensus IRLS polish (`polish_iters` weighted 8-point solves),
- * then inliers = sqrt(Sampson error) < threshold (OpenCV USAC's rule).  x0, x1 [n,2] f32 raw pixel coordinates.
- * Outputs (device): F_out [9] f64 row-major (scaled so F[8] = 1 when possible), mask [n] u8, *n_inliers. */
+ * Batched-hypothesis RANSAC (8-point samples drawn from `seed`) scored with the MAGSAC++ marginalised quality function
+ * (sigma-consensus++, 4 degrees of freedom, k = 3.64, noise scale marginalised up to `sigma_max` on the Sampson error — what
+ * cv2.findFundamentalMat(USAC_MAGSAC) scores with), then a polisher run to its fixed point (at most `polish_iters` weighted
+ * normalised 8-point solves; the polished model is kept only if its quality is not below the RANSAC winner's):
+ *   polish_mode 0 = MAGSAC++ weights  w(r^2) = Gamma(3/2, r^2 / (2 sigma_max^2)) - Gamma(3/2, k^2 / 2)   (the MAGSAC branch,
+ *                   geometric_verification.py:89-92; sigma_max = 4.5 / 3.64 px reproduces OpenCV 4.13, scripts/magsac_probe.py)
+ *   polish_mode 1 = least squares on the inliers at `threshold`, LO-RANSAC's final step (the pydegensac branch, :66-76).
+ * Inliers = sqrt(Sampson error) < threshold (OpenCV USAC's and pydegensac's rule).  x0, x1 [n,2] f32 raw pixel coordinates.
+ * Outputs (device): F_out [9] f64 row-major (scaled so F[8] = 1 when possible), mask [n] u8, *n_inliers.  If no hypothesis
+ * reaches 8 inliers the reference's degrade path applies: F_out = NaN, mask = all ones, *n_inliers = n. */
 size_t i4d_fundamental_workspace_bytes(void);
 int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double threshold, double confidence,
-                           int max_iters, unsigned int seed, double sigma_max, int polish_iters, double* F_out,
-                           unsigned char* mask, int* n_inliers, void* workspace, size_t workspace_bytes,
+                           int max_iters, unsigned int seed, double sigma_max, int polish_iters, int polish_mode,
+                           double* F_out, unsigned char* mask, int* n_inliers, void* workspace, size_t workspace_bytes,
                            void* stream);
 
 /* sfm/geometry.py:31-76 (cv2.findEssentialMat inlier rule + cv2.recoverPose) — relative pose from an essential-matrix

@@ -9,6 +9,13 @@
                         NOTE the reference re-scales A and b *cumulatively* every iteration, :157-160)
   linear_dlt            sfm/triangulation.py:154-183 (6x6 SVD null vector, dehomogenised)
   fundamental_magsac    matching/geometric_verification.py:89-92 -> cv2.findFundamentalMat(USAC_MAGSAC, 0.5, 0.999, 100000)
+  magsac_weights / magsac_quality / magsac_polish
+                        MAGSAC++ (Barath et al. 2020) as OpenCV's USAC applies it to F (opencv/modules/calib3d/src/usac/
+                        quality.cpp; third party, not under /root/reference): sigma-consensus++ weights and marginalised
+                        quality on the squared Sampson error (4 DoF, k = 3.64), and the re-weighted normalised 8-point
+                        polisher iterated to its fixed point.  cv2 does not expose sigma_max; MAGSAC_CUTOFF_PX = 4.5 is
+                        fitted to cv2's own output (tests/test_oracle_vs_golden.py::test_magsac_polisher_pinned_to_opencv,
+                        scripts/magsac_probe.py).
   sampson_error / symmetric epipolar distance: used by tests to compare inlier sets geometrically.
 Pinned against the reference itself by tests/test_oracle_vs_golden.py.
 """
@@ -92,6 +99,71 @@ def linear_dlt(x1: np.ndarray, P1: np.ndarray, x2: np.ndarray, P2: np.ndarray) -
 def fundamental_magsac(m0: np.ndarray, m1: np.ndarray):
     F, inl = cv2.findFundamentalMat(m0, m1, cv2.USAC_MAGSAC, 0.5, 0.999, 100000)
     return F, (inl > 0).squeeze()
+
+
+MAGSAC_K = 3.64                      # 0.99 quantile of the chi distribution with 4 degrees of freedom
+MAGSAC_CUTOFF_PX = 4.5               # k * sigma_max
+
+
+def _upper_gamma_1p5(x):
+    from scipy.special import erfc
+    sx = np.sqrt(x)
+    return 0.886226925452758 * erfc(sx) + sx * np.exp(-x)
+
+
+def magsac_weights(r2: np.ndarray, cutoff: float = MAGSAC_CUTOFF_PX) -> np.ndarray:
+    """w(r^2) = Gamma(3/2, r^2 / (2 s^2)) - Gamma(3/2, k^2 / 2) for r < k s, else 0 (s = cutoff / k)."""
+    s = cutoff / MAGSAC_K
+    w = _upper_gamma_1p5(r2 / (2 * s * s)) - _upper_gamma_1p5(np.float64(MAGSAC_K ** 2 / 2))
+    return np.where(r2 < cutoff * cutoff, np.maximum(w, 0.0), 0.0)
+
+
+def magsac_quality(F: np.ndarray, m0: np.ndarray, m1: np.ndarray, cutoff: float = MAGSAC_CUTOFF_PX) -> float:
+    """sum over r < cutoff of 1 - loss(r^2) / loss(cutoff^2),
+    loss = s^2/2 * gamma(5/2, x) + r^2/4 * (Gamma(3/2, x) - Gamma(3/2, k^2/2)), x = r^2 / (2 s^2)."""
+    s = cutoff / MAGSAC_K
+    r2 = sampson_distance(F, m0, m1) ** 2
+    r2 = r2[r2 < cutoff * cutoff]
+    x = r2 / (2 * s * s)
+    up15 = _upper_gamma_1p5(x)
+    lo25 = 1.329340388179137 - (1.5 * up15 + x * np.sqrt(x) * np.exp(-x))
+    xk = MAGSAC_K ** 2 / 2
+    gk = _upper_gamma_1p5(np.float64(xk))
+    max_loss = s * s / 2 * (1.329340388179137 - (1.5 * gk + xk * np.sqrt(xk) * np.exp(-xk)))
+    return float(np.sum(1.0 - (s * s / 2 * lo25 + r2 / 4 * (up15 - gk)) / max_loss))
+
+
+def weighted_eight_point(m0: np.ndarray, m1: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """Weighted normalised 8-point fit; the similarity normalisation uses ALL correspondences (centroid, mean distance sqrt 2),
+    as the CUDA path does.  Returns F with unit Frobenius norm."""
+    def norm(p):
+        c = p.mean(0)
+        s = np.sqrt(2) / np.sqrt(((p - c) ** 2).sum(1)).mean()
+        return (p - c) * s, np.array([[s, 0, -s * c[0]], [0, s, -s * c[1]], [0, 0, 1]])
+    a, T0 = norm(m0.astype(np.float64))
+    b, T1 = norm(m1.astype(np.float64))
+    A = np.stack([b[:, 0] * a[:, 0], b[:, 0] * a[:, 1], b[:, 0], b[:, 1] * a[:, 0], b[:, 1] * a[:, 1], b[:, 1], a[:, 0], a[:, 1],
+                  np.ones(len(a))], 1)
+    _, V = np.linalg.eigh((A * w[:, None]).T @ A)
+    U, S, Vt = np.linalg.svd(V[:, 0].reshape(3, 3))
+    F = T1.T @ (U @ np.diag([S[0], S[1], 0.0]) @ Vt) @ T0
+    return F / np.linalg.norm(F)
+
+
+def magsac_polish(F0: np.ndarray, m0: np.ndarray, m1: np.ndarray, cutoff: float = MAGSAC_CUTOFF_PX, max_iters: int = 200,
+                  tol: float = 1e-13, hard_threshold: float = None):
+    """Iterates F <- weighted_eight_point(weights(residuals(F))) to its fixed point.  hard_threshold: unit weights on
+    the inliers at that threshold instead (LO-RANSAC's least squares on inliers).  Returns (F unit norm, iterations)."""
+    F = F0 / np.linalg.norm(F0)
+    for it in range(max_iters):
+        r2 = sampson_distance(F, m0, m1) ** 2
+        w = magsac_weights(r2, cutoff) if hard_threshold is None else (r2 < hard_threshold ** 2).astype(np.float64)
+        Fn = weighted_eight_point(m0, m1, w)
+        d = min(np.abs(Fn - F).max(), np.abs(Fn + F).max())
+        F = Fn
+        if d < tol:
+            break
+    return F, it + 1
 
 
 def sampson_distance(F: np.ndarray, m0: np.ndarray, m1: np.ndarray) -> np.ndarray:

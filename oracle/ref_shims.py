@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE — not part of the product.
 
-Import shims that let the *unmodified* reference (`/root/reference/src/icepy4d`) run on CPU in the build
-container.  Used ONLY by `oracle/make_golden.py` and by `-m "not gpu"` tests that are
-skipped when `/root/reference` is absent (it never exists on the GPU box).  Nothing from the reference is
+Import shims that let the *unmodified* reference (`/root/reference/src/icepy4d`, or the copy `oracle/stage_ref.py`
+stages into the git-ignored oracle/_ref/ so that it can travel to the GPU box) run on CPU.
+Used ONLY by `oracle/make_golden.py`, by `bench.py --impl reference` / the cpu_baseline leg, and by `-m "not gpu"`
+tests that are skipped when no reference tree is available.  Nothing from the reference is
 copied: the shims are stubs for third-party modules the container lacks (easydict, matplotlib, kornia,
 exifread, open3d, laspy) and a context manager that neutralises checkpoint loading so seeded weights
 (`icepy4d_b200.weights`) can be installed instead.
@@ -14,7 +15,9 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("ICEPY4D_REFERENCE_SRC", "/root/reference/src")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")      # oracle/stage_ref.py (git-ignored)
+REFERENCE_SRC = os.environ.get("ICEPY4D_REFERENCE_SRC",
+                               "/root/reference/src" if os.path.isdir("/root/reference/src/icepy4d") else _STAGED)
 
 
 def reference_available() -> bool:

@@ -56,10 +56,31 @@ def test_cfg3_200k_verification_and_triangulation():
     assert abs(np.linalg.det(Fh / np.linalg.norm(Fh))) < 1e-10     # rank 2
     assert (mask & ~sc["inlier"]).sum() < 0.002 * mask.sum()       # gross outliers rejected
     assert mask[sc["inlier"]].mean() > 0.45                        # distorted pixels: ~half of the true inliers are within 0.5 px
-    Fr, mr = geom_oracle.fundamental_magsac(sc["pts0"], sc["pts1"])
-    iou = (mask & mr).sum() / (mask | mr).sum()
-    print("cfg3 200k inlier IoU vs cv2 MAGSAC:", iou, mask.sum(), mr.sum())
-    assert iou > 0.85
+    # cv2 USAC_MAGSAC (the reference's runnable branch) on the same points in three orders: it agrees with itself to
+    # 0.98-0.999 on this config (knife-edge inlier rule under a misfitting pinhole model, tests/test_gpu_plugin.py), so the
+    # gates are (a) >= 0.999 against the CPU restatement of the MAGSAC++ polisher started from cv2's model and (b) at least
+    # as close to the cv2 runs as they are to each other.
+    import cv2
+    rng = np.random.default_rng(1)
+    cvm, Fr = [], None
+    for t in range(3):
+        perm = rng.permutation(len(mask)) if t else np.arange(len(mask))
+        Fc, m = cv2.findFundamentalMat(sc["pts0"][perm], sc["pts1"][perm], cv2.USAC_MAGSAC, 0.5, 0.999, 100000)
+        Fr = Fc if Fr is None else Fr
+        mu = np.zeros(len(mask), bool)
+        mu[perm] = m.ravel() > 0
+        cvm.append(mu)
+    iou = lambda a, b: (a & b).sum() / max(1, (a | b).sum())
+    self_iou = [iou(cvm[0], cvm[1]), iou(cvm[0], cvm[2]), iou(cvm[1], cvm[2])]
+    ours = [iou(mask, m) for m in cvm]
+    Fo, _ = geom_oracle.magsac_polish(Fr, sc["pts0"], sc["pts1"])
+    mo = geom_oracle.sampson_distance(Fo, sc["pts0"], sc["pts1"]) < 0.5
+    Fn = Fh / np.linalg.norm(Fh)
+    dF = min(np.abs(Fn - Fo).max(), np.abs(Fn + Fo).max())
+    print(f"cfg3 200k: inlier IoU vs oracle polisher {iou(mask, mo):.4f} (|dF| {dF:.1e}); vs cv2 runs {np.round(ours, 4)}; "
+          f"cv2 vs cv2 {np.round(self_iou, 4)}")
+    assert iou(mask, mo) >= 0.999 and dF < 1e-9
+    assert np.mean(ours) >= np.mean(self_iou) - 0.01 and min(ours) >= min(self_iou) - 0.01
     # triangulation of the true inliers: round trip through the known cameras
     inl = sc["inlier"]
     tri = Triangulate(sc["cams"], [sc["pts0"][inl], sc["pts1"][inl]])

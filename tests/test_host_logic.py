@@ -50,13 +50,17 @@ def test_shard_epochs_partition():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
-    from icepy4d_b200.epoch import gather_results, shard_epochs
+    from icepy4d_b200.epoch import gather_results, gather_results_device, shard_epochs
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         mine = shard_epochs(7, rank, world)
         local = {e: np.full((e + 1, 3), float(e), dtype=np.float64) for e in mine}       # ragged per-epoch results
         allr = gather_results(local, world)
         ok = sorted(allr) == list(range(7)) and all(allr[e].shape == (e + 1, 3) and float(allr[e][0, 0]) == e for e in allr)
+        # the tensor path bench.py uses on GPUs (padded all_gather; here on CPU tensors over gloo), incl. an empty epoch
+        tl = {e: torch.full(((e * 5) % 4, 3), float(e), dtype=torch.float64) for e in mine}
+        tr = gather_results_device(tl, world)
+        ok = ok and sorted(tr) == list(range(7)) and all(tr[e].shape == ((e * 5) % 4, 3) and bool((tr[e] == e).all()) for e in tr)
         t = torch.tensor([len(mine)])
         dist.all_reduce(t)
         out.put((rank, ok and int(t) == 7))
