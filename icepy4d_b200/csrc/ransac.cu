@@ -24,6 +24,7 @@
 #define RS_TOPK 8            // hypotheses re-scored on all points per round
 #define RS_SUB 8192          // points in the pre-scoring subsample
 #define RS_MAX_ROUNDS 24
+#define RS_NPOL 4             // polisher starts (the objective has several local optima on near-degenerate scenes)
 
 struct RansacState {
   double T0[3], T1[3];          // normalisation: x' = s * (x - cx), y' = s * (y - cy)  -> {s, cx, cy}
@@ -33,11 +34,13 @@ struct RansacState {
   int done;                     // termination flag (confidence reached)
   int hyp_tested;
   int topk[RS_TOPK];
-  double polishF[9];
-  double final_score[2];        // quality of {bestF, polishF} under the selection rule of the polish mode
-  int converged;                // polisher reached its fixed point: the remaining polish launches are no-ops
-  int polish_done;              // polish iterations executed
-  int failed;                   // no model with >= 8 inliers: mask = all ones, F = NaN (the reference's degrade path)
+  double topF[RS_NPOL][9];      // the RS_NPOL best fully-scored hypotheses so far (topF[0] == bestF), starts of the polisher
+  double top_score[RS_NPOL];
+  double polishF[RS_NPOL][9];
+  double final_score[RS_NPOL + 1];   // quality of {bestF, polishF[0..]} under the selection rule of the polish mode
+  int converged[RS_NPOL];       // polisher j reached its fixed point: its remaining polish work is skipped
+  int polish_done;              // polish iterations executed (all starts)
+  int failed;                   // no valid model (every minimal sample degenerate): F = NaN, mask = all zeros, like cv2's (None, zeros)
   int use_polished;
 };
 #define RS_POLISH_GRID_MAX 320
@@ -142,7 +145,11 @@ __global__ void __launch_bounds__(1024) rs_norm_kernel(const float* __restrict__
   }
   if (threadIdx.x == 0) {
     st->best_score = -1.0; st->best_inliers = 0; st->done = 0; st->hyp_tested = 0;
-    st->converged = 0; st->polish_done = 0; st->failed = 0; st->use_polished = 0;
+    st->polish_done = 0; st->failed = 0; st->use_polished = 0;
+    for (int j = 0; j < RS_NPOL; ++j) {
+      st->converged[j] = 0; st->top_score[j] = -1.0;
+      for (int i = 0; i < 9; ++i) st->topF[j][i] = 0.0;
+    }
     for (int i = 0; i < 9; ++i) st->bestF[i] = 0.0;
   }
 }
@@ -362,10 +369,22 @@ __global__ void rs_update_kernel(const float* __restrict__ hypF, const double* _
                                  RansacState* st) {
   if (threadIdx.x != 0 || st->done) return;
   for (int k = 0; k < RS_TOPK; ++k) {
-    if (st->topk[k] >= 0 && cand_score[k] > st->best_score) {
+    if (st->topk[k] < 0) continue;
+    if (cand_score[k] > st->best_score) {
       st->best_score = cand_score[k];
       st->best_inliers = cand_inl[k];
       for (int i = 0; i < 9; ++i) st->bestF[i] = (double)hypF[st->topk[k] * 9 + i];
+    }
+    // sorted insertion into the list of polisher starts
+    int pos = RS_NPOL;
+    while (pos > 0 && cand_score[k] > st->top_score[pos - 1]) --pos;
+    if (pos < RS_NPOL) {
+      for (int j = RS_NPOL - 1; j > pos; --j) {
+        st->top_score[j] = st->top_score[j - 1];
+        for (int i = 0; i < 9; ++i) st->topF[j][i] = st->topF[j - 1][i];
+      }
+      st->top_score[pos] = cand_score[k];
+      for (int i = 0; i < 9; ++i) st->topF[pos][i] = (double)hypF[st->topk[k] * 9 + i];
     }
   }
   st->hyp_tested += RS_BATCH;
@@ -389,9 +408,10 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
                                                               int n, MagsacConst mc, double thr2, int mode,
                                                               const RansacState* st, double* __restrict__ partial) {
   __shared__ double red[8][45];
-  if (st->converged || st->failed) return;
+  const int j = blockIdx.y;
+  if (st->converged[j] || st->failed) return;
   double F[9];
-  for (int i = 0; i < 9; ++i) F[i] = st->polishF[i];
+  for (int i = 0; i < 9; ++i) F[i] = st->polishF[j][i];
   const double s0 = st->T0[0], cx0 = st->T0[1], cy0 = st->T0[2], s1 = st->T1[0], cx1 = st->T1[1], cy1 = st->T1[2];
   double acc[45];
 #pragma unroll
@@ -427,7 +447,7 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
   if (threadIdx.x < 45) {
     double t = 0;
     for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    partial[(size_t)blockIdx.x * 45 + threadIdx.x] = t;
+    partial[((size_t)j * gridDim.x + blockIdx.x) * 45 + threadIdx.x] = t;
   }
 }
 
@@ -437,10 +457,11 @@ __global__ void __launch_bounds__(256) rs_polish_accum_kernel(const float* __res
 __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, const double* __restrict__ partial, int n_partial,
                                                              double tol) {
   __shared__ double cov[45];
-  if (st->converged || st->failed) return;
+  const int j = blockIdx.x;
+  if (st->converged[j] || st->failed) return;
   if (threadIdx.x < 45) {
     double t = 0;
-    for (int b = 0; b < n_partial; ++b) t += partial[(size_t)b * 45 + threadIdx.x];
+    for (int b = 0; b < n_partial; ++b) t += partial[((size_t)j * n_partial + b) * 45 + threadIdx.x];
     cov[threadIdx.x] = t;
   }
   __syncthreads();
@@ -453,7 +474,7 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
       for (int q = p; q < 9; ++q) { L[q][p] = cov[t]; L[p][q] = cov[t]; ++t; }
     for (int p = 0; p < 9; ++p) tr += L[p][p];
   }
-  if (!(tr > 0)) { st->converged = 1; return; }   // no support: keep the previous model
+  if (!(tr > 0)) { st->converged[j] = 1; return; }   // no support: keep the previous model
   const double eps = 1e-13 * tr;
   // Cholesky of C + eps I (lower triangle, in place)
   for (int j = 0; j < 9; ++j) {
@@ -501,21 +522,25 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
   rs_denormalise(Fn, st->T0, st->T1, F);
   bool ok = true;
   for (int i = 0; i < 9; ++i) ok &= isfinite(F[i]);
-  if (!ok) { st->converged = 1; return; }
+  if (!ok) { st->converged[j] = 1; return; }
   // fixed point reached?  (unit Frobenius norm on both sides, sign-aligned)
   double dp = 0, dm = 0;
   for (int i = 0; i < 9; ++i) {
-    dp = fmax(dp, fabs(F[i] - st->polishF[i]));
-    dm = fmax(dm, fabs(F[i] + st->polishF[i]));
+    dp = fmax(dp, fabs(F[i] - st->polishF[j][i]));
+    dm = fmax(dm, fabs(F[i] + st->polishF[j][i]));
   }
-  for (int i = 0; i < 9; ++i) st->polishF[i] = F[i];
-  st->polish_done += 1;
-  if (fmin(dp, dm) < tol) st->converged = 1;
+  for (int i = 0; i < 9; ++i) st->polishF[j][i] = F[i];
+  atomicAdd(&st->polish_done, 1);
+  if (fmin(dp, dm) < tol) st->converged[j] = 1;
 }
 
 __global__ void rs_begin_polish_kernel(RansacState* st) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) st->polishF[i] = st->bestF[i];
+    for (int j = 0; j < RS_NPOL; ++j) {
+      const bool have = st->top_score[j] >= 0.0;            // fewer valid hypotheses than starts: duplicate the best, already "converged"
+      for (int i = 0; i < 9; ++i) st->polishF[j][i] = have ? st->topF[j][i] : st->bestF[i];
+      if (!have && j > 0) st->converged[j] = 1;
+    }
     if (st->best_inliers < 8) st->failed = 1;
   }
 }
@@ -526,7 +551,7 @@ __global__ void __launch_bounds__(512) rs_final_score_kernel(const float* __rest
                                                              MagsacConst mc, double thr2, int mode, RansacState* st) {
   __shared__ double rs[16];
   if (st->failed) return;
-  const double* Fc = blockIdx.x == 0 ? st->bestF : st->polishF;
+  const double* Fc = blockIdx.x == 0 ? st->bestF : st->polishF[blockIdx.x - 1];
   double F[9];
   for (int i = 0; i < 9; ++i) F[i] = Fc[i];
   double acc = 0;
@@ -551,18 +576,21 @@ __global__ void __launch_bounds__(256) rs_mask_kernel(const float* __restrict__ 
                                                       int* __restrict__ n_inl, double* __restrict__ F_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool failed = st->failed != 0;
-  const double* Fc = (st->final_score[1] >= st->final_score[0]) ? st->polishF : st->bestF;
+  const double* Fc = st->bestF;           // a polished model replaces the RANSAC winner only if it is at least as good
+  double fs = st->final_score[0];
+  for (int j = 0; j < RS_NPOL; ++j)
+    if (st->final_score[j + 1] >= fs) { fs = st->final_score[j + 1]; Fc = st->polishF[j]; }
   double F[9];
   for (int k = 0; k < 9; ++k) F[k] = Fc[k];
   if (i == 0) {
-    // scale like OpenCV (F[2][2] = 1) when possible; NaN marks "no model" (the caller returns F = None, all-inlier mask)
+    // scale like OpenCV (F[2][2] = 1) when possible; NaN marks "no model" (the caller returns F = None; cv2 returns (None, zeros))
     double s = fabs(F[8]) > 1e-300 ? 1.0 / F[8] : 1.0;
     for (int k = 0; k < 9; ++k) F_out[k] = failed ? __longlong_as_double(0x7ff8000000000000LL) : F[k] * s;
   }
   int inl = 0;
   if (i < n) {
     float2 a = __ldg(reinterpret_cast<const float2*>(x0) + i), b = __ldg(reinterpret_cast<const float2*>(x1) + i);
-    inl = failed ? 1 : (sampson_sq(F, a.x, a.y, b.x, b.y) < thr2);
+    inl = failed ? 0 : (sampson_sq(F, a.x, a.y, b.x, b.y) < thr2);
     mask[i] = (unsigned char)inl;
   }
   unsigned int bal = __ballot_sync(0xffffffffu, inl);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(256) rs_mask_kernel(const float* __restrict__ 
 
 extern "C" __attribute__((visibility("default"))) size_t i4d_fundamental_workspace_bytes(void) {
   return sizeof(RansacState) + (size_t)RS_BATCH * (9 * sizeof(float) + sizeof(int) + sizeof(float)) +
-         RS_TOPK * (sizeof(double) + sizeof(int)) + (size_t)RS_POLISH_GRID_MAX * 45 * sizeof(double) + 512;
+         RS_TOPK * (sizeof(double) + sizeof(int)) + (size_t)RS_NPOL * RS_POLISH_GRID_MAX * 45 * sizeof(double) + 512;
 }
 
 extern "C" __attribute__((visibility("default"))) int i4d_fundamental_ransac(
@@ -612,14 +640,14 @@ extern "C" __attribute__((visibility("default"))) int i4d_fundamental_ransac(
     rs_update_kernel<<<1, 32, 0, st>>>(hypF, cand_score, cand_inl, n, confidence, max_hyp, state);
   }
   rs_begin_polish_kernel<<<1, 32, 0, st>>>(state);
-  int grid = 2 * i4d_num_sms();
+  int grid = i4d_num_sms();                       // x RS_NPOL starts in grid.y
   if (grid > RS_POLISH_GRID_MAX) grid = RS_POLISH_GRID_MAX;
   if (grid > i4d_cdiv(n, 256)) grid = i4d_cdiv(n, 256);
   for (int it = 0; it < polish_iters; ++it) {
-    rs_polish_accum_kernel<<<grid, 256, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state, partial);
-    rs_polish_solve_kernel<<<1, 64, 0, st>>>(state, partial, grid, 1e-13);
+    rs_polish_accum_kernel<<<dim3(grid, RS_NPOL), 256, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state, partial);
+    rs_polish_solve_kernel<<<RS_NPOL, 64, 0, st>>>(state, partial, grid, 1e-13);
   }
-  rs_final_score_kernel<<<2, 512, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state);
+  rs_final_score_kernel<<<RS_NPOL + 1, 512, 0, st>>>(x0, x1, n, mc, thr2, polish_mode, state);
   rs_mask_kernel<<<i4d_cdiv(n, 256), 256, 0, st>>>(x0, x1, n, thr2, state, mask, n_inliers, F_out);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;

@@ -3,8 +3,9 @@
 
 Reference semantics kept: fewer than 4 matches -> (None, all-True); the MAGSAC branch ignores the caller's
 threshold/confidence/max_iters and uses (0.5 px, 0.999, 100000) (geometric_verification.py:89-91, Appendix D.5) with the
-MAGSAC++ quality function and polisher of cv2.USAC_MAGSAC; failures degrade to an all-inlier mask with F = None and are
-logged, never raised (:96-100).
+MAGSAC++ quality function and polisher of cv2.USAC_MAGSAC; exceptions degrade to an all-inlier mask with F = None and are
+logged, never raised (:96-100); degenerate input (no valid model) gives (None, all-False) as cv2 does; 4-7 matches give
+(None, all-True) (cv2 raises below 7 points; its 7-point model for exactly 7 matches is not reproduced).
 
 PYDEGENSAC branch (the reference's default, :66-76): pydegensac is not installed in the reference's own environment here and
 its source is not vendored, so its output cannot be pinned.  What is matched is its documented behaviour: LO-RANSAC on the
@@ -61,9 +62,9 @@ def geometric_verification(mkpts0: np.ndarray = None, mkpts1: np.ndarray = None,
         if Fd is not None:
             F = Fd.cpu().numpy().reshape(3, 3)
             inl = mask.cpu().numpy()
-            if not np.isfinite(F).all():        # no model with >= 8 inliers: the reference's degrade path (:96-100)
-                logger.error("RANSAC found no model. Unable to perform geometric verification.")
-                return None, np.ones(len(mkpts0), dtype=bool)
+            if not np.isfinite(F).all():        # degenerate input: cv2 returns (None, zeros) and the reference passes that on (:89-92)
+                logger.error("RANSAC found no model.")
+                return None, inl
             logger.info(f"B200 RANSAC found {inl.sum()} inliers ({inl.sum() * 100 / len(mkpts0):.2f}%)")
     except Exception as err:  # same degrade-don't-raise convention as the reference (:96-100)
         logger.error(f"{err}. Unable to perform geometric verification.")

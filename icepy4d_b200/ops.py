@@ -352,7 +352,7 @@ def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.
                        polish_mode: int = 0, ws: Optional[torch.Tensor] = None):
     """x0, x1 [n,2] f32 -> (F [9] f64 device, mask [n] u8 device, n_inliers int32[1] device).
     polish_mode 0 = MAGSAC++ weights (cv2 USAC_MAGSAC), 1 = least squares on the inliers at `threshold` (LO-RANSAC).
-    F is NaN and the mask all ones when no model with >= 8 inliers exists (the reference's degrade path)."""
+    F is NaN and the mask all zeros when no valid model exists (degenerate input), like cv2's (None, zeros)."""
     _chk(x0, name="x0"), _chk(x1, name="x1")
     n = x0.shape[0]
     dev = x0.device

@@ -169,14 +169,16 @@ int i4d_interpolate_point_colors(const double* X, int n, const double* R_host, c
 /* matching/geometric_verification.py:43-102 and sfm/two_view_geometry.py:127-197 — robust fundamental matrix.
  * Batched-hypothesis RANSAC (8-point samples drawn from `seed`) scored with the MAGSAC++ marginalised quality function
  * (sigma-consensus++, 4 degrees of freedom, k = 3.64, noise scale marginalised up to `sigma_max` on the Sampson error — what
- * cv2.findFundamentalMat(USAC_MAGSAC) scores with), then a polisher run to its fixed point (at most `polish_iters` weighted
- * normalised 8-point solves; the polished model is kept only if its quality is not below the RANSAC winner's):
+ * cv2.findFundamentalMat(USAC_MAGSAC) scores with), then a polisher run to its fixed point from each of the 4 best hypotheses
+ * (at most `polish_iters` weighted normalised 8-point solves each, batched in the same launches; the best final quality wins and
+ * replaces the RANSAC winner only if it is not worse):
  *   polish_mode 0 = MAGSAC++ weights  w(r^2) = Gamma(3/2, r^2 / (2 sigma_max^2)) - Gamma(3/2, k^2 / 2)   (the MAGSAC branch,
  *                   geometric_verification.py:89-92; sigma_max = 4.5 / 3.64 px reproduces OpenCV 4.13, scripts/magsac_probe.py)
  *   polish_mode 1 = least squares on the inliers at `threshold`, LO-RANSAC's final step (the pydegensac branch, :66-76).
  * Inliers = sqrt(Sampson error) < threshold (OpenCV USAC's and pydegensac's rule).  x0, x1 [n,2] f32 raw pixel coordinates.
- * Outputs (device): F_out [9] f64 row-major (scaled so F[8] = 1 when possible), mask [n] u8, *n_inliers.  If no hypothesis
- * reaches 8 inliers the reference's degrade path applies: F_out = NaN, mask = all ones, *n_inliers = n. */
+ * Outputs (device): F_out [9] f64 row-major (scaled so F[8] = 1 when possible), mask [n] u8, *n_inliers.  If no valid model
+ * exists (every minimal sample degenerate: coincident / collinear points) F_out = NaN, mask = all zeros, *n_inliers = 0 — what
+ * cv2.findFundamentalMat returns in that case (F None, zero mask), which the reference passes on (geometric_verification.py:89-92). */
 size_t i4d_fundamental_workspace_bytes(void);
 int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double threshold, double confidence,
                            int max_iters, unsigned int seed, double sigma_max, int polish_iters, int polish_mode,

@@ -212,11 +212,68 @@ def golden_colors():
     print("colors: mean", col.mean(0))
 
 
+def golden_preselection():
+    """TileSelection.PRESELECTION (matchers.py:513-560) and the `_match_images` / `_match_by_tile` return contracts
+    (matchers.py:892-940, 394-469) run from the reference itself.  The pair is shifted by (208, 104) px so that off-diagonal tile
+    pairs are selected; the per-pair counts of the pre-match are stored so that the test can check the decision margin."""
+    ref_shims.install_shims()
+    import cv2
+    import icepy4d.matching.matchers as M
+    from icepy4d.matching import GeometricVerification, Quality, TileSelection
+
+    sp_sd, sg_sd = weights.make_superpoint_state(1), weights.make_superglue_state(2)
+    i0, i1 = synthetic.stereo_pair(960, 1280, seed=1011, shift=(208, 104), channels=3)
+    with ref_shims.no_checkpoint_loading():
+        m = M.SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": 1024,
+                                "match_threshold": 0.2, "force_cpu": True, "sinkhorn_iterations": 20})
+    m.matcher.superpoint.load_state_dict(sp_sd)
+    m.matcher.superglue.load_state_dict(sg_sd)
+    rec = {}
+    orig = m._tile_selection
+
+    def spy(image0, image1, t0_lims, t1_lims, method=TileSelection.PRESELECTION, **config):
+        pairs = orig(image0, image1, t0_lims, t1_lims, method, **config)
+        rec["pairs"], rec["t0"], rec["t1"] = pairs, t0_lims, t1_lims
+        return pairs
+    m._tile_selection = spy
+    m.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.PRESELECTION, grid=[2, 3], overlap=0,
+            geometric_verification=GeometricVerification.NONE)
+    mk0, mk1 = m.mkpts0.copy(), m.mkpts1.copy()
+    # the pre-match itself (what _tile_selection ran internally), to store the per-pair counts
+    f0, f1, mtc, mconf = m._match_images(cv2.pyrDown(i0), cv2.pyrDown(i1), max_keypoints=4096)
+    vld = mtc > -1
+    kp0, kp1 = f0.keypoints[vld] * 2, f1.keypoints[mtc[vld]] * 2
+    keys0, keys1 = sorted(rec["t0"]), sorted(rec["t1"])
+    counts = np.zeros((len(keys0), len(keys1)), np.int64)
+    inr = lambda p, r: np.all(p > r[:2], axis=1) & np.all(p < r[2:], axis=1)
+    for a in keys0:
+        for b in keys1:
+            counts[a, b] = int(np.sum(inr(kp0, rec["t0"][a]) & inr(kp1, rec["t1"][b])))
+    assert sorted(rec["pairs"]) == sorted((a, b) for a in keys0 for b in keys1 if counts[a, b] > 5)
+    # _match_images / _match_by_tile return contracts on a small pair
+    j0, j1 = synthetic.stereo_pair(240, 320, seed=1012, shift=(16, 8), channels=3)
+    g0, g1, gm, gc = m._match_images(j0, j1)
+    t0, t1, tm, tc = m._match_by_tile(j0, j1, tile_selection=TileSelection.GRID, grid=[1, 2], overlap=20)
+    np.savez_compressed(os.path.join(OUT, "preselection.npz"), image0=i0, image1=i1, pairs=np.array(sorted(rec["pairs"]), np.int64),
+                        counts=counts, mkpts0=mk0, mkpts1=mk1, small0=j0, small1=j1,
+                        mi_kpts0=g0.keypoints, mi_desc0=g0.descriptors, mi_scores0=g0.scores, mi_kpts1=g1.keypoints,
+                        mi_desc1=g1.descriptors, mi_scores1=g1.scores, mi_matches0=gm, mi_mconf=gc,
+                        mt_kpts0=t0.keypoints, mt_kpts1=t1.keypoints, mt_desc0=t0.descriptors, mt_scores0=t0.scores,
+                        mt_matches0=tm, mt_mconf=tc)
+    print("preselection: pairs", sorted(rec["pairs"]), "counts", counts.tolist(), "matches", len(mk0),
+          "| _match_images", g0.keypoints.shape, g0.descriptors.shape, gm.shape, gc.shape, gm.dtype,
+          "| _match_by_tile", t0.keypoints.shape, t0.descriptors.shape, tm.shape, tc.shape)
+
+
 if __name__ == "__main__":
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:                       # regenerate selected fixtures only: python -m oracle.make_golden preselection ...
+        for name in sys.argv[1:]:
+            globals()[f"golden_{name}"]()
+        sys.exit(0)
     golden_tiler_quality()
     golden_geometry()
     golden_pose()
@@ -224,3 +281,4 @@ if __name__ == "__main__":
     golden_superpoint_superglue()
     golden_lightglue()
     golden_matchers()
+    golden_preselection()

@@ -11,7 +11,13 @@
   (3) the fixed point of that polisher (oracle/geom_oracle.py::magsac_polish, which csrc/ransac.cu implements) against the
       cv2 runs of (1): it agrees with them as well as they agree with each other.
 
+  (4) --translation: the matcher golden (tests/golden/matchers.npz) is a pure image translation; a 2-parameter family of
+      rank-2 F fits all its true matches exactly, so the MAGSAC++ objective has several local optima that differ only in
+      which WRONG matches they accept.  RANSAC (8-point samples, best of 300 by MAGSAC++ quality) + polisher from 30 seeds:
+      the optimum most seeds reach has a HIGHER quality than the model cv2 returns and an inlier IoU of 0.95 with it.
+
     python scripts/magsac_probe.py [n ...]            # default 20000 50000
+    python scripts/magsac_probe.py --translation
 """
 import itertools
 import os
@@ -42,7 +48,40 @@ def cv2_runs(p0, p1, k, seed=1):
     return out
 
 
+def translation_landscape():
+    d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "matchers.npz"))
+    p0, p1 = d["sg_mkpts0"], d["sg_mkpts1"]
+    n = len(p0)
+    true = (p0[:, 0] - p1[:, 0] == 16) & (p0[:, 1] - p1[:, 1] == 8)
+    runs = cv2_runs(p0, p1, 5)
+    print(f"matcher golden: {n} matches, {true.sum()} true; cv2 runs keep {[int(m.sum()) for _, m in runs]} "
+          f"(all true matches: {[bool((m & true).sum() == true.sum()) for _, m in runs]}), MAGSAC++ quality of cv2's models "
+          f"{[round(g.magsac_quality(F, p0, p1), 2) for F, _ in runs]}")
+    rng = np.random.default_rng(0)
+    rows = {}
+    for trial in range(30):
+        best, bq = None, -1.0
+        for _ in range(300):
+            idx = rng.choice(n, 8, replace=False)
+            F = g.weighted_eight_point(p0[idx], p1[idx], np.ones(8))
+            if not np.isfinite(F).all():
+                continue
+            q = g.magsac_quality(F, p0, p1)
+            if q > bq:
+                best, bq = F, q
+        Fp, _ = g.magsac_polish(best, p0, p1)
+        mp = g.sampson_distance(Fp, p0, p1) < 0.5
+        key = (round(g.magsac_quality(Fp, p0, p1), 2), int(mp.sum()), round(iou(mp, runs[0][1]), 4), bool((mp & true).sum() == true.sum()))
+        rows[key] = rows.get(key, 0) + 1
+    print("   (quality after polish, inliers, IoU vs cv2, keeps all true matches) -> number of seeds")
+    for k in sorted(rows, reverse=True):
+        print("  ", k, "->", rows[k])
+
+
 def main():
+    if "--translation" in sys.argv:
+        print(f"OpenCV {cv2.__version__}")
+        return translation_landscape()
     sizes = [int(a) for a in sys.argv[1:]] or [20000, 50000]
     print(f"OpenCV {cv2.__version__}")
     print("(2) one-step displacement of cv2's F under the MAGSAC++ polisher, by cut-off [px] (distortion-free, no outliers)")
