@@ -111,3 +111,41 @@ extern "C" __attribute__((visibility("default"))) int i4d_pyr_up_u8(const unsign
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
+
+// ---- PRESELECTION decision (matchers.py:495-499, 541-556) ---------------------------------------------------------------
+// counts[t0 * T1 + t1] = #{ matches i : valid[i], scale * kp0[i] strictly inside lims0[t0] and scale * kp1[i] strictly inside
+// lims1[t1] }.  One thread per match builds the two membership bit sets (<= 64 tiles per image) and adds 1 to every pair in
+// their product (integer atomics: order-independent, bit-reproducible).
+__global__ void __launch_bounds__(256) tile_pair_count_kernel(const float* __restrict__ kp0, const float* __restrict__ kp1,
+                                                              const unsigned char* __restrict__ valid, int n, float scale,
+                                                              const float* __restrict__ lims0, int T0,
+                                                              const float* __restrict__ lims1, int T1, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (valid && !valid[i])) return;
+  const float x0 = kp0[2 * i] * scale, y0 = kp0[2 * i + 1] * scale, x1 = kp1[2 * i] * scale, y1 = kp1[2 * i + 1] * scale;
+  unsigned long long m1 = 0ull;
+  for (int t = 0; t < T1; ++t) {
+    const float* r = lims1 + 4 * t;
+    if (x1 > r[0] && y1 > r[1] && x1 < r[2] && y1 < r[3]) m1 |= 1ull << t;
+  }
+  if (!m1) return;
+  for (int t = 0; t < T0; ++t) {
+    const float* r = lims0 + 4 * t;
+    if (!(x0 > r[0] && y0 > r[1] && x0 < r[2] && y0 < r[3])) continue;
+    for (unsigned long long b = m1; b; b &= b - 1) atomicAdd(counts + t * T1 + (__ffsll((long long)b) - 1), 1);
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_tile_pair_counts(const float* kp0, const float* kp1,
+                                                                          const unsigned char* valid, int n, float scale,
+                                                                          const float* lims0, int T0, const float* lims1, int T1,
+                                                                          int* counts, void* stream) {
+  I4D_CHECK_ARG(counts && lims0 && lims1 && (n == 0 || (kp0 && kp1)), "null pointer");
+  I4D_CHECK_ARG(T0 >= 1 && T0 <= 64 && T1 >= 1 && T1 <= 64, "1..64 tiles per image");
+  I4D_CUDA_CALL(cudaMemsetAsync(counts, 0, (size_t)T0 * T1 * sizeof(int), (cudaStream_t)stream));
+  if (n > 0) {
+    tile_pair_count_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(kp0, kp1, valid, n, scale, lims0, T0, lims1, T1, counts);
+    I4D_CUDA_LAUNCH_CHECK();
+  }
+  return I4D_OK;
+}

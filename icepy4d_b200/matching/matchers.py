@@ -423,20 +423,13 @@ class ImageMatcherBase(ImageMatcherABC):
             for _ in range(n_down):
                 i0, i1 = ops.pyr_down(i0), ops.pyr_down(i1)           # on the device, bit-exact with cv2.pyrDown
             r = self._match_tensors(i0, i1, (0, 0, i0.shape[1], i0.shape[0]), (0, 0, i1.shape[1], i1.shape[0]), max_keypoints=4096)
-            f0, f1, mtc, _ = self._pair_to_numpy(r)
-            vld = mtc > -1
-            kp0 = f0.keypoints[vld] * float(2 ** n_down)
-            kp1 = f1.keypoints[mtc[vld]] * float(2 ** n_down)
-
-            def points_in_rect(points, rect):
-                rect = np.asarray(rect)
-                return np.all(points > rect[:2], axis=1) & np.all(points < rect[2:], axis=1)
-
-            pairs = []
-            for t0, t1 in sorted(product(t0_lims.keys(), t1_lims.keys())):
-                if np.sum(points_in_rect(kp0, t0_lims[t0]) & points_in_rect(kp1, t1_lims[t1])) > min_matches_per_tile:
-                    pairs.append((t0, t1))
-            return pairs
+            # the decision itself (strict rectangle test :495-499, count > min_matches :555) on the device: one small kernel
+            # over the pre-matches, then T0 x T1 integers come back — no keypoint array crosses to the host
+            k0, k1 = sorted(t0_lims.keys()), sorted(t1_lims.keys())
+            counts = ops.tile_pair_counts(r.mk0.contiguous(), r.mk1.contiguous(), r.valid, float(2 ** n_down),
+                                          [t0_lims[k] for k in k0], [t1_lims[k] for k in k1]).cpu().numpy()
+            self._preselection_counts = counts
+            return [(a, b) for ia, a in enumerate(k0) for ib, b in enumerate(k1) if counts[ia, ib] > min_matches_per_tile]
         raise ValueError(f"unsupported tile selection {method}")
 
     # -- numpy-level API kept for compatibility (matchers.py:276-302, 304-469) --

@@ -395,6 +395,19 @@ def tile_to_gray_f32(image_u8: torch.Tensor, x0: int, y0: int, tw: int, th: int,
     return out
 
 
+def tile_pair_counts(kp0: torch.Tensor, kp1: torch.Tensor, valid: Optional[torch.Tensor], scale: float, lims0, lims1) -> torch.Tensor:
+    """PRESELECTION decision on the device: counts [T0,T1] i32 of valid matches strictly inside both tile rectangles
+    (lims = sequences of (xmin, ymin, xmax, ymax), keypoints multiplied by `scale` first)."""
+    _chk(kp0, name="kp0"), _chk(kp1, name="kp1")
+    dev = kp0.device
+    l0 = torch.tensor(np.asarray(lims0, dtype=np.float32).reshape(-1, 4), device=dev)
+    l1 = torch.tensor(np.asarray(lims1, dtype=np.float32).reshape(-1, 4), device=dev)
+    v = None if valid is None else valid.to(torch.uint8).contiguous()
+    counts = torch.empty((l0.shape[0], l1.shape[0]), device=dev, dtype=torch.int32)
+    N.call("i4d_tile_pair_counts", kp0, kp1, v, kp0.shape[0], float(scale), l0, l0.shape[0], l1, l1.shape[0], counts, _st())
+    return counts
+
+
 def pyr_down(image_u8: torch.Tensor) -> torch.Tensor:
     """cv2.pyrDown on a device u8 image [H,W] or [H,W,3] (bit-exact)."""
     assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()

@@ -205,6 +205,13 @@ int i4d_essential_pose(const double* E_in, const float* xn0, const float* xn1, i
 int i4d_tile_to_gray_f32(const unsigned char* image, int H, int W, int C, int x0, int y0, int tw, int th, int mode,
                          float* out, void* stream);
 
+/* matching/matchers.py:495-499,541-556 — the PRESELECTION decision: for every tile pair (t0, t1) the number of pre-matches whose
+ * up-scaled keypoints lie strictly inside both tile rectangles.  kp0 / kp1 [n,2] f32 (row i = one candidate match, kp1 already
+ * gathered through matches0), valid [n] u8 or NULL, scale = 2^n_down, lims0 [T0,4] / lims1 [T1,4] f32 (xmin, ymin, xmax, ymax;
+ * T <= 64) on the device.  counts [T0*T1] i32 (device) is zeroed and filled; the caller keeps pairs with count > min_matches. */
+int i4d_tile_pair_counts(const float* kp0, const float* kp1, const unsigned char* valid, int n, float scale, const float* lims0,
+                         int T0, const float* lims1, int T1, int* counts, void* stream);
+
 /* matching/matchers.py:583-610 (Quality resize) and :526-531 (PRESELECTION pass) — cv2.pyrDown / cv2.pyrUp on 8-bit images,
  * bit-exact with OpenCV's integer arithmetic and border rules.  image [H,W,C] u8 (C = 1 or 3).
  * pyr_down: out [(H+1)/2, (W+1)/2, C];  pyr_up: out [2H, 2W, C]. */

@@ -214,7 +214,7 @@ def golden_colors():
 
 def golden_preselection():
     """TileSelection.PRESELECTION (matchers.py:513-560) and the `_match_images` / `_match_by_tile` return contracts
-    (matchers.py:892-940, 394-469) run from the reference itself.  The pair is shifted by (208, 104) px so that off-diagonal tile
+    (matchers.py:892-940, 394-469) run from the reference itself.  The pair is shifted by (400, 96) px so that off-diagonal tile
     pairs are selected; the per-pair counts of the pre-match are stored so that the test can check the decision margin."""
     ref_shims.install_shims()
     import cv2
@@ -222,9 +222,9 @@ def golden_preselection():
     from icepy4d.matching import GeometricVerification, Quality, TileSelection
 
     sp_sd, sg_sd = weights.make_superpoint_state(1), weights.make_superglue_state(2)
-    i0, i1 = synthetic.stereo_pair(960, 1280, seed=1011, shift=(208, 104), channels=3)
+    i0, i1 = synthetic.stereo_pair(960, 1280, seed=1013, shift=(400, 96), channels=3)
     with ref_shims.no_checkpoint_loading():
-        m = M.SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": 1024,
+        m = M.SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 1e-4, "max_keypoints": 2048,
                                 "match_threshold": 0.2, "force_cpu": True, "sinkhorn_iterations": 20})
     m.matcher.superpoint.load_state_dict(sp_sd)
     m.matcher.superglue.load_state_dict(sg_sd)
@@ -233,7 +233,8 @@ def golden_preselection():
 
     def spy(image0, image1, t0_lims, t1_lims, method=TileSelection.PRESELECTION, **config):
         pairs = orig(image0, image1, t0_lims, t1_lims, method, **config)
-        rec["pairs"], rec["t0"], rec["t1"] = pairs, t0_lims, t1_lims
+        if "pairs" not in rec:
+            rec["pairs"], rec["t0"], rec["t1"] = list(pairs), t0_lims, t1_lims
         return pairs
     m._tile_selection = spy
     m.match(i0, i1, quality=Quality.HIGH, tile_selection=TileSelection.PRESELECTION, grid=[2, 3], overlap=0,
@@ -254,12 +255,14 @@ def golden_preselection():
     j0, j1 = synthetic.stereo_pair(240, 320, seed=1012, shift=(16, 8), channels=3)
     g0, g1, gm, gc = m._match_images(j0, j1)
     t0, t1, tm, tc = m._match_by_tile(j0, j1, tile_selection=TileSelection.GRID, grid=[1, 2], overlap=20)
-    np.savez_compressed(os.path.join(OUT, "preselection.npz"), image0=i0, image1=i1, pairs=np.array(sorted(rec["pairs"]), np.int64),
-                        counts=counts, mkpts0=mk0, mkpts1=mk1, small0=j0, small1=j1,
-                        mi_kpts0=g0.keypoints, mi_desc0=g0.descriptors, mi_scores0=g0.scores, mi_kpts1=g1.keypoints,
-                        mi_desc1=g1.descriptors, mi_scores1=g1.scores, mi_matches0=gm, mi_mconf=gc,
-                        mt_kpts0=t0.keypoints, mt_kpts1=t1.keypoints, mt_desc0=t0.descriptors, mt_scores0=t0.scores,
-                        mt_matches0=tm, mt_mconf=tc)
+    # images are regenerated from their seeds by the test (synthetic.stereo_pair is deterministic); descriptors: first 64 columns
+    np.savez_compressed(os.path.join(OUT, "preselection.npz"), seed=1013, shift=np.array([400, 96]), shape=np.array([960, 1280]),
+                        pairs=np.array(sorted(rec["pairs"]), np.int64), counts=counts, mkpts0=mk0, mkpts1=mk1,
+                        small_seed=1012, small_shift=np.array([16, 8]), small_shape=np.array([240, 320]),
+                        mi_kpts0=g0.keypoints, mi_desc0=g0.descriptors[:, :64], mi_desc_shape=np.array(g0.descriptors.shape),
+                        mi_scores0=g0.scores, mi_kpts1=g1.keypoints, mi_scores1=g1.scores, mi_matches0=gm, mi_mconf=gc,
+                        mt_kpts0=t0.keypoints, mt_kpts1=t1.keypoints, mt_desc0=t0.descriptors[:, :64],
+                        mt_desc_shape=np.array(t0.descriptors.shape), mt_scores0=t0.scores, mt_matches0=tm, mt_mconf=tc)
     print("preselection: pairs", sorted(rec["pairs"]), "counts", counts.tolist(), "matches", len(mk0),
           "| _match_images", g0.keypoints.shape, g0.descriptors.shape, gm.shape, gc.shape, gm.dtype,
           "| _match_by_tile", t0.keypoints.shape, t0.descriptors.shape, tm.shape, tc.shape)
