@@ -35,12 +35,20 @@
 #define FA_BN 128
 #define FA_D 64
 #define FA_KV_STAGES 3
-#define FA_THREADS 576
+#define FA_THREADS 640                          // warpgroup 0: TMA producer, MMA issuer, two idle warps; warpgroups 1-4: softmax
 #define FA_Q_BYTES (FA_BM * FA_D * 2)           // 16 KB
 #define FA_KV_BYTES (FA_BN * FA_D * 2)          // 16 KB each for K and V
+#ifndef FA_P_TMEM
+#define FA_P_TMEM 1                             // 1: P_j goes to tensor memory (A operand of the P V product read from TMEM)
+#endif
+#if FA_P_TMEM
+#define FA_P_BYTES 0
+#else
 #define FA_P_BYTES (FA_BM * FA_BN * 2)          // 32 KB (two 16 KB K-halves), two buffers
-#define FA_SMEM_BYTES (FA_Q_BYTES + 2 * FA_KV_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024)   // Q | K x3 | V x3 | P x2 = 176 KB (+ align)
-#define FA_TMEM_COLS 512                        // S0: [0,128)  S1: [128,256)  O: [256,320)
+#endif
+#define FA_SMEM_BYTES (FA_Q_BYTES + 2 * FA_KV_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024)   // Q | K ring | V ring (| P x2) (+ align)
+#define FA_TMEM_COLS 512                        // S0: [0,128)  S1: [128,256)  O: [256,320)  P0: [320,384)  P1: [384,448) (bf16 pairs)
+#define FA_TMEM_P 320
 #define FA_MAX_PROBLEMS 4
 #define FA_TAU 8.0f                             // lazy-rescale threshold (log2 units)
 // Share of the exponentials evaluated on the FMA pipe instead of MUFU (Cody-Waite range reduction + degree-3 minimax
@@ -90,7 +98,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
@@ -108,7 +116,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
@@ -153,7 +161,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
     item = p.n_whole + split;
   }
   const int qt = item % p.n_qt, h = (item / p.n_qt) % p.heads;
-  AttnProblem pr = p.prob[item / (p.n_qt * p.heads)];
+  AttnProblem pr = p.prob[0];                                     // (a dynamic index would put the parameter array on the stack)
+  {
+    const int z = item / (p.n_qt * p.heads);
+#pragma unroll
+    for (int i = 1; i < FA_MAX_PROBLEMS; ++i)
+      if (z == i) pr = p.prob[i];
+  }
   const int q0 = qt * FA_BM;
   if (q0 >= pr.nq) return;                                        // uniform per CTA (both halves of a split item): safe before any barrier
   if (split >= 0) {                                               // my half of the key blocks
@@ -184,6 +198,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   const uint32_t tmem = tmem_base_s;
   const uint32_t tmem_O = tmem + 256;
 
+  // Register budget by role (setmaxnreg works on whole warpgroups): the launch gives every thread 96 registers (640 threads =
+  // 61440); the four softmax warpgroups grow to 104 (128 * 96 + 512 * 104 = 65536) so that the 64 scores, the packed
+  // probabilities and the running statistics of a row half stay in registers (no local-memory traffic in the loop).
+  if (warp >= 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (tc::elect_one()) {
@@ -241,23 +259,31 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
         tc::mbar_wait(&v_full[s], (j / FA_KV_STAGES) & 1);
         tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);                        // P_j in shared memory, O rescaled if needed
         tc::tcgen05_fence_after();
-        const uint32_t dP = dP0 + (uint32_t)((j & 1) * (FA_P_BYTES >> 4));
         const uint32_t dV = dV0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
+#if FA_P_TMEM
+        const uint32_t tP = tmem + FA_TMEM_P + (uint32_t)(j & 1) * (FA_BN / 2);
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k)      // A: P k-slice = 16 keys = 8 TMEM columns;  B: V rows [16k, 16k+16) x 64 dims
+          tc::umma_f16_ts(tmem_O, tP + (uint32_t)(k * 8), dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (j | k) ? 1u : 0u);
+        (void)dP0;
+#else
+        const uint32_t dP = dP0 + (uint32_t)((j & 1) * (FA_P_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
           // A: P k-slice = 16 keys = 32 B inside the 128-B swizzle row of K-half (k / 4);  B: V rows [16k, 16k+16) x 64 dims
           tc::umma_f16_parts(tmem_O, dP + (uint32_t)(((k >> 2) * (FA_BM * 128) + (k & 3) * 32) >> 4), hi_k,
                              dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (j | k) ? 1u : 0u);
         }
+#endif
         tc::umma_commit(&v_empty[s]);                                       // V stage free
         tc::umma_commit(&pv_done[j & 1]);                                   // O includes block j; P buffer free
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------ softmax: group g (8 warps) owns key blocks j = g, g + 2, ...;
     // TWO threads per query row (TMEM lane), 64 keys each: 16 softmax warps per SM keep the issue slots and the MUFU pipe fed
-    const int sw = warp - 2;                                                // 0..15
+    const int sw = warp - 4;                                                // 0..15
     const int g = sw >> 3;
     const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
     const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
@@ -331,25 +357,44 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       float2 rs2 = make_float2(0.f, 0.f);
       const float2 nm2 = make_float2(-m_new, -m_new);
       const uint32_t prow = prow0 + b * FA_P_BYTES;
+#if FA_P_TMEM
+      uint32_t pk_all[16];
+#endif
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
+#if FA_P_TMEM
+        uint32_t* pk = pk_all + (t & 3) * 4;
+#else
         uint32_t pk[4];
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = t * 8 + e * 2;
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
           const bool poly = (((t & 1) ? (POLY_MASK >> 4) : POLY_MASK) >> e) & 1;      // compile-time after unrolling
-          const float2 ab = poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          const float2 ab = (POLY_MASK & 0x100) ? x                                            // timing experiment: no exponential at all
+                            : poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
           rs2 = __fadd2_rn(rs2, ab);
           __nv_bfloat162 pr2 = __floats2bfloat162_rn(ab.x, ab.y);
           pk[e] = *reinterpret_cast<uint32_t*>(&pr2);
         }
+#if FA_P_TMEM
+        // my 64 keys of row q as bf16 pairs -> TMEM lane q, columns [32 hf, 32 hf + 32) of P[b], 16 columns (32 keys) at a time
+        if ((t & 3) == 3) tmem_st16(tmem + lane_off + FA_TMEM_P + b * (FA_BN / 2) + hf * 32 + (t >> 2) * 16, pk_all);
+#else
         const uint32_t addr = prow + ((((uint32_t)t) ^ rsw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+#endif
       }
       l_part += rs2.x + rs2.y;
+#if FA_P_TMEM
+      (void)prow; (void)rsw;
+      tmem_st_wait();
+      tc::tcgen05_fence_before();
+#else
       tc::tcgen05_fence_before();
       tc::fence_proxy_async_smem();                                         // make P_j visible to the tensor-core proxy
+#endif
       tc::mbar_arrive(&p_full[b]);
     }
     // ---- final: bring all four partial row sums to the final maximum, exchange, normalise O
@@ -378,7 +423,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
         if (g == 0 && hf == 0) { mine[FA_BM * FA_D + q] = m_fin; mine[FA_BM * FA_D + FA_BM + q] = l; }
         __threadfence();
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (threadIdx.x == 64) merge_flag_s = atomicAdd(p.counters + split, 1);
+        if (threadIdx.x == 128) merge_flag_s = atomicAdd(p.counters + split, 1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         store = merge_flag_s != 0;                                          // uniform over the CTA
         if (store) {
@@ -473,15 +518,26 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   static bool attr_seen[64] = {};
   if (variant < 0) {
     const char* e = getenv("I4D_FA_POLY");
-    variant = (e && atoi(e) == 25) ? 1 : 0;
+    const int v = e ? atoi(e) : 0;
+    variant = v == 25 ? 1 : v == 50 ? 2 : v == 75 ? 3 : v == 100 ? 4 : v == -1 ? 5 : 0;
   }
   if (i4d_first_use_on_device(attr_seen)) {
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
     I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }
   const int grid = n_items + rem;
-  if (variant == 1) attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
-  else attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
+  switch (variant) {
+    case 1: attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 2: attn_tc_kernel<0xAA><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 3: attn_tc_kernel<0xEE><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 4: attn_tc_kernel<0xFF><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    case 5: attn_tc_kernel<0x100><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
+    default: attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
+  }
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
