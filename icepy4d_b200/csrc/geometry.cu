@@ -280,3 +280,79 @@ extern "C" __attribute__((visibility("default"))) int i4d_triangulate_dlt(const 
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
+
+// ---- absolute orientation (Helmert): sfm/absolute_orientation.py:141-154 + thirdparty/transformations.py:889-1020 ---------
+// Moments of two corresponding point sets for the closed-form similarity (Horn's quaternion method as the reference's
+// affine_matrix_from_points(shear=False, scale=True, usesvd=False) applies it): centroids, the 3x3 cross-covariance of the
+// centred sets and their sums of squares.  One CTA, two passes, fixed-order tree reductions (bit-reproducible).
+//   out[0..2] = mean(v0), out[3..5] = mean(v1), out[6..14] = sum_i c0_i c1_i^T (row-major: [a][b] = sum c0[a] c1[b]),
+//   out[15] = sum |c0|^2, out[16] = sum |c1|^2
+__global__ void __launch_bounds__(1024) helmert_moments_kernel(const double* __restrict__ v0, const double* __restrict__ v1, int n,
+                                                               double* __restrict__ out) {
+  __shared__ double red[32][11];
+  __shared__ double mean[6];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto block_sum = [&](double (&acc)[11], int cnt) {
+    for (int c = 0; c < cnt; ++c) {
+      double v = acc[c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < cnt) {
+      double t = 0;
+      for (int w = 0; w < 32; ++w) t += red[w][tid];
+      red[0][tid] = t;
+    }
+    __syncthreads();
+  };
+  double acc[11];
+  for (int c = 0; c < 11; ++c) acc[c] = 0.0;
+  for (int i = tid; i < n; i += blockDim.x)
+    for (int c = 0; c < 3; ++c) { acc[c] += v0[3 * i + c]; acc[3 + c] += v1[3 * i + c]; }
+  block_sum(acc, 6);
+  if (tid < 6) { mean[tid] = red[0][tid] / n; out[tid] = mean[tid]; }
+  __syncthreads();
+  for (int c = 0; c < 11; ++c) acc[c] = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    double a[3], b[3];
+    for (int c = 0; c < 3; ++c) { a[c] = v0[3 * i + c] - mean[c]; b[c] = v1[3 * i + c] - mean[3 + c]; }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) acc[3 * r + c] += a[r] * b[c];
+    acc[9] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    acc[10] += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+  }
+  block_sum(acc, 11);
+  if (tid < 11) out[6 + tid] = red[0][tid];
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_helmert_moments(const double* v0, const double* v1, int n, double* out,
+                                                                         void* stream) {
+  I4D_CHECK_ARG(v0 && v1 && out && n >= 1, "null pointer or empty point set");
+  helmert_moments_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v0, v1, n, out);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}
+
+// sfm/absolute_orientation.py:269-272: points_out = T @ [x; 1], dehomogenised.  T row-major 4x4 (host), f64 throughout.
+struct Mat16 { double m[16]; };
+__global__ void __launch_bounds__(256) apply_transform_kernel(const double* __restrict__ X, int n, Mat16 T, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+  double h[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) h[r] = ((T.m[4 * r] * x + T.m[4 * r + 1] * y) + T.m[4 * r + 2] * z) + T.m[4 * r + 3];
+  out[3 * i] = h[0] / h[3]; out[3 * i + 1] = h[1] / h[3]; out[3 * i + 2] = h[2] / h[3];
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_apply_transform(const double* X, int n, const double* T_host, double* out,
+                                                                         void* stream) {
+  I4D_CHECK_ARG(T_host && n >= 0 && (n == 0 || (X && out)), "null pointer");
+  if (n == 0) return I4D_OK;
+  Mat16 T;
+  for (int i = 0; i < 16; ++i) T.m[i] = T_host[i];
+  apply_transform_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(X, n, T, out);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}

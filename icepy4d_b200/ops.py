@@ -385,6 +385,25 @@ def essential_pose(E: torch.Tensor, xn0: torch.Tensor, xn1: torch.Tensor, thresh
     return Eo, R, t, mask, n_good
 
 
+def helmert_moments(v0: torch.Tensor, v1: torch.Tensor) -> torch.Tensor:
+    """v0, v1 [n,3] f64 on the device -> [17] f64 (means, centred cross-covariance, sums of squares) on the device."""
+    assert v0.is_cuda and v1.is_cuda and v0.dtype == torch.float64 and v1.dtype == torch.float64
+    assert v0.shape == v1.shape and v0.dim() == 2 and v0.shape[1] == 3 and v0.shape[0] >= 1
+    out = torch.empty(17, device=v0.device, dtype=torch.float64)
+    N.call("i4d_helmert_moments", v0.contiguous(), v1.contiguous(), v0.shape[0], out, _st())
+    return out
+
+
+def apply_transform(X: torch.Tensor, T: np.ndarray) -> torch.Tensor:
+    """X [n,3] f64 on the device, T 4x4 (host) -> dehomogenise(T [x; 1]) [n,3] f64 on the device."""
+    assert X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.shape[1] == 3
+    Th = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+    X = X.contiguous()
+    out = torch.empty_like(X)
+    N.call("i4d_apply_transform", X, X.shape[0], Th, out, _st())
+    return out
+
+
 def tile_to_gray_f32(image_u8: torch.Tensor, x0: int, y0: int, tw: int, th: int, mode: int) -> torch.Tensor:
     """image [H,W,C] or [H,W] u8 on the device -> [1,1,th,tw] f32 network input."""
     assert image_u8.is_cuda and image_u8.dtype == torch.uint8 and image_u8.is_contiguous()

@@ -166,6 +166,15 @@ int i4d_interpolate_point_colors(const double* X, int n, const double* R_host, c
                                  const double* dist_host, int n_dist, const unsigned char* image, int H, int W, int C,
                                  int convert_bgr2rgb, double* colors, float* projections, void* stream);
 
+/* sfm/absolute_orientation.py:141-154 (Absolute_orientation.estimate_transformation_linear -> thirdparty/transformations.py:
+ * 889-1020 affine_matrix_from_points(shear=False, scale=True, usesvd=False)) — the reductions of the closed-form Helmert /
+ * similarity fit.  v0, v1 [n,3] f64 on the device.  out [17] f64 (device): mean(v0) [3], mean(v1) [3], the cross-covariance of
+ * the centred sets sum c0 c1^T [9, row-major], sum |c0|^2, sum |c1|^2.  The 4x4 quaternion eigenproblem is solved by the host. */
+int i4d_helmert_moments(const double* v0, const double* v1, int n, double* out, void* stream);
+/* sfm/absolute_orientation.py:269-272 (apply_transformation): out = dehomogenise(T [x; 1]), T [16] row-major 4x4 on the host,
+ * X, out [n,3] f64 on the device (out may alias X). */
+int i4d_apply_transform(const double* X, int n, const double* T_host, double* out, void* stream);
+
 /* matching/geometric_verification.py:43-102 and sfm/two_view_geometry.py:127-197 — robust fundamental matrix.
  * Batched-hypothesis RANSAC (8-point samples drawn from `seed`) scored with the MAGSAC++ marginalised quality function
  * (sigma-consensus++, 4 degrees of freedom, k = 3.64, noise scale marginalised up to `sigma_max` on the Sampson error — what

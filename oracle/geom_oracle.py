@@ -16,6 +16,9 @@
                         polisher iterated to its fixed point.  cv2 does not expose sigma_max; MAGSAC_CUTOFF_PX = 4.5 is
                         fitted to cv2's own output (tests/test_oracle_vs_golden.py::test_magsac_polisher_pinned_to_opencv,
                         scripts/magsac_probe.py).
+  helmert_linear / apply_transform
+                        sfm/absolute_orientation.py:141-154,247-287 + thirdparty/transformations.py:889-1020 (Horn's quaternion
+                        method, affine_matrix_from_points with shear=False, usesvd=False)
   sampson_error / symmetric epipolar distance: used by tests to compare inlier sets geometrically.
 Pinned against the reference itself by tests/test_oracle_vs_golden.py.
 """
@@ -194,6 +197,43 @@ def estimate_pose(kpts0: np.ndarray, kpts1: np.ndarray, K0: np.ndarray, K1: np.n
         if n > best:
             best, ret = n, (R, t[:, 0], mask.ravel() > 0)
     return ret
+
+
+def helmert_linear(v0: np.ndarray, v1: np.ndarray, scale: bool = True) -> np.ndarray:
+    """sfm/absolute_orientation.py:141-154 -> thirdparty/transformations.py:889-1020 affine_matrix_from_points(v0.T, v1.T,
+    shear=False, scale=scale, usesvd=False) restated: Horn's quaternion method, scale = ratio of RMS deviations from the centroids.
+    v0, v1 [n,3]; returns the 4x4 matrix with v1 ~ T v0."""
+    import math
+    a = np.array(v0, dtype=np.float64).T.copy()
+    b = np.array(v1, dtype=np.float64).T.copy()
+    t0, t1 = -a.mean(1), -b.mean(1)
+    M0, M1 = np.identity(4), np.identity(4)
+    M0[:3, 3], M1[:3, 3] = t0, t1
+    a += t0.reshape(3, 1)
+    b += t1.reshape(3, 1)
+    xx, yy, zz = np.sum(a * b, axis=1)
+    xy, yz, zx = np.sum(a * np.roll(b, -1, axis=0), axis=1)
+    xz, yx, zy = np.sum(a * np.roll(b, -2, axis=0), axis=1)
+    N = [[xx + yy + zz, 0.0, 0.0, 0.0], [yz - zy, xx - yy - zz, 0.0, 0.0], [zx - xz, xy + yx, yy - xx - zz, 0.0],
+         [xy - yx, zx + xz, yz + zy, zz - xx - yy]]
+    w, V = np.linalg.eigh(N)
+    q = V[:, np.argmax(w)]
+    q = q / np.linalg.norm(q)
+    q = q * math.sqrt(2.0 / np.dot(q, q))
+    o = np.outer(q, q)
+    M = np.array([[1.0 - o[2, 2] - o[3, 3], o[1, 2] - o[3, 0], o[1, 3] + o[2, 0], 0.0],
+                  [o[1, 2] + o[3, 0], 1.0 - o[1, 1] - o[3, 3], o[2, 3] - o[1, 0], 0.0],
+                  [o[1, 3] - o[2, 0], o[2, 3] + o[1, 0], 1.0 - o[1, 1] - o[2, 2], 0.0], [0.0, 0.0, 0.0, 1.0]])
+    if scale:
+        M[:3, :3] *= math.sqrt(np.sum(b * b) / np.sum(a * a))
+    M = np.linalg.inv(M1) @ (M @ M0)
+    return M / M[3, 3]
+
+
+def apply_transform(T: np.ndarray, points3d: np.ndarray) -> np.ndarray:
+    """sfm/absolute_orientation.py:269-272 restated: dehomogenise(T @ [x; 1])."""
+    h = T @ np.concatenate([np.asarray(points3d, dtype=np.float64).T, np.ones((1, len(points3d)))], 0)
+    return (h[:3] / h[3]).T
 
 
 def project_points(points3d: np.ndarray, R: np.ndarray, t: np.ndarray, K: np.ndarray, dist: np.ndarray) -> np.ndarray:

@@ -268,6 +268,35 @@ def golden_preselection():
           "| _match_by_tile", t0.keypoints.shape, t0.descriptors.shape, tm.shape, tc.shape)
 
 
+def golden_helmert():
+    """sfm/absolute_orientation.py:56-287 run from the reference itself: closed-form similarity between two noisy point sets,
+    its Euler / translation parameters, and the transformation applied to a point cloud and to two cameras."""
+    ref_shims.install_shims()
+    from icepy4d.sfm.absolute_orientation import Absolute_orientation
+
+    rng = np.random.default_rng(21)
+    n = 12
+    v0 = rng.uniform(-50, 50, (n, 3))
+    ang = np.array([0.3, -0.2, 1.1])
+    cx, cy, cz = np.cos(ang); sx, sy, sz = np.sin(ang)
+    R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+         @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    v1 = 2.5 * v0 @ R.T + np.array([1000.0, -2000.0, 300.0]) + rng.normal(0, 0.05, (n, 3))
+    cams = synthetic.two_view_scene(n=8, seed=0, outlier_frac=0.0)["cams"]
+    ext0 = [c.extrinsics.copy() for c in cams]
+    ao = Absolute_orientation(tuple(cams), points3d_final=v1.copy(), points3d_orig=v0.copy())
+    T = ao.estimate_transformation_linear()
+    T_noscale = Absolute_orientation((), points3d_final=v1.copy(), points3d_orig=v0.copy()).estimate_transformation_linear(estimate_scale=False)
+    prm = ao.extract_params_from_T()
+    cloud = rng.uniform(-80, 80, (5000, 3))
+    out = ao.apply_transformation(points3d=cloud.copy())
+    ext1 = [c.extrinsics.copy() for c in cams]
+    np.savez_compressed(os.path.join(OUT, "helmert.npz"), v0=v0, v1=v1, T=T, T_noscale=T_noscale,
+                        params=np.array([prm[k] for k in ("rx", "ry", "rz", "tx", "ty", "tz", "m")]), cloud=cloud, cloud_out=out,
+                        ext_before=np.array(ext0), ext_after=np.array(ext1))
+    print("helmert: scale", np.cbrt(np.linalg.det(T[:3, :3])), "params", prm)
+
+
 if __name__ == "__main__":
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -285,3 +314,4 @@ if __name__ == "__main__":
     golden_lightglue()
     golden_matchers()
     golden_preselection()
+    golden_helmert()
