@@ -176,25 +176,29 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   const int cta = blockIdx.x;
   const long long u_begin = fa_range_start(p, cta), u_end = fa_range_start(p, cta + 1);
 
-  auto init_barriers = [&](uint32_t nt) {                          // nt = query tiles with rows = MMA issuers that release K / V stages
+  // Barriers are initialised ONCE; their phases run on across the segments of this CTA (re-initialising a live mbarrier is
+  // undefined).  K / V stages are released by two arrivals: one per tile issuer, or both from tile A's issuer when the item has no
+  // rows for tile B.
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmX);
     tc::mbar_init(&q_full, 1);
     for (int s = 0; s < FA_KV_STAGES; ++s) {
-      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], nt);
-      tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], nt);
+      tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 2);
+      tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
       tc::mbar_init(&s_full[t], 1); tc::mbar_init(&s_empty[t], 256); tc::mbar_init(&p_full[t], 256);
       tc::mbar_init(&pv_done[t], 1);
     }
     tc::fence_barrier_init();
-  };
-  if (threadIdx.x == 0) tc::prefetch_tmap(&tmX);
+  }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, FA_TMEM_COLS);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  uint32_t seg = 0, kv_base = 0, blk_base[2] = {0u, 0u};           // segments / K-V blocks / blocks per tile processed so far
   for (long long u = u_begin; u < u_end;) {
     // ---- this segment: item (z, h, qt), key blocks [kb0, kb1) ----
     int z = 0;
@@ -215,9 +219,6 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
     const int q0 = qt * (2 * FA_BM);
     const bool validB = q0 + FA_BM < pr.nq;                         // tile A always has rows
     const int slot = (u == u_begin) ? 0 : 1;
-    if (threadIdx.x == 0) init_barriers(validB ? 2u : 1u);          // fresh barriers for every segment (phases restart at 0)
-    __syncthreads();
-
     if (warp == 0) {
       // ------------------------------------------------ TMA producer
       if (tc::elect_one()) {
@@ -225,14 +226,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
         tc::tma_load_2d(sQ, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0);
         if (validB) tc::tma_load_2d(sQ + FA_Q_BYTES, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0 + FA_BM);
         auto load_k = [&](int jj) {
-          const int s = jj % FA_KV_STAGES;
-          tc::mbar_wait(&k_empty[s], ((jj / FA_KV_STAGES) & 1) ^ 1);
+          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
+          tc::mbar_wait(&k_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(&k_full[s], FA_KV_BYTES);
           tc::tma_load_2d(sK + s * FA_KV_BYTES, &tmX, &k_full[s], p.k_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
         };
         auto load_v = [&](int jj) {
-          const int s = jj % FA_KV_STAGES;
-          tc::mbar_wait(&v_empty[s], ((jj / FA_KV_STAGES) & 1) ^ 1);
+          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
+          tc::mbar_wait(&v_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(&v_full[s], FA_KV_BYTES);
           tc::tma_load_2d(sV + s * FA_KV_BYTES, &tmX, &v_full[s], p.v_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
         };
@@ -258,39 +259,41 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
         const uint32_t dV0 = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
         const uint32_t tS = tmem + (uint32_t)t * FA_BN;
         const uint32_t tO = tmem + FA_TMEM_O + (uint32_t)t * FA_D, tP = tmem + FA_TMEM_P + (uint32_t)t * (FA_BN / 2);
+        const uint32_t bb = blk_base[t];                                      // this tile's block counter at the segment start
+        const bool twice = !validB;                                           // tile A alone: both stage-release arrivals are mine
         auto issue_qk = [&](int jj) {                                         // S_t = Q_t K_jj^T
-          const int s = jj % FA_KV_STAGES;
-          const uint32_t dK = dK0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
+          const uint32_t s = (kv_base + (uint32_t)jj) % FA_KV_STAGES;
+          const uint32_t dK = dK0 + s * (FA_KV_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tS, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
           tc::umma_commit(&s_full[t]);
-          tc::umma_commit(&k_empty[s]);                                       // (one arrival per issuer)
+          tc::umma_commit(&k_empty[s]);
+          if (twice) tc::umma_commit(&k_empty[s]);
         };
-        tc::mbar_wait(&q_full, 0);
-        tc::mbar_wait(&k_full[0], 0);
+        tc::mbar_wait(&q_full, seg & 1u);
+        tc::mbar_wait(&k_full[kv_base % FA_KV_STAGES], (kv_base / FA_KV_STAGES) & 1u);
         tc::tcgen05_fence_after();
         issue_qk(0);
         for (int jj = 0; jj < nb; ++jj) {
-          const int s = jj % FA_KV_STAGES;
+          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
           if (jj + 1 < nb) {
             // scores of the NEXT block: the buffer is free as soon as the group has block jj in registers
-            tc::mbar_wait(&k_full[(jj + 1) % FA_KV_STAGES], ((jj + 1) / FA_KV_STAGES) & 1);
-            tc::mbar_wait(&s_empty[t], jj & 1);
+            tc::mbar_wait(&k_full[(g + 1) % FA_KV_STAGES], ((g + 1) / FA_KV_STAGES) & 1u);
+            tc::mbar_wait(&s_empty[t], (bb + (uint32_t)jj) & 1u);
             tc::tcgen05_fence_after();
             issue_qk(jj + 1);
           }
-          tc::mbar_wait(&v_full[s], (jj / FA_KV_STAGES) & 1);
-          tc::mbar_wait(&p_full[t], jj & 1);                                   // P_t(jj) in TMEM, O_t rescaled if needed
+          tc::mbar_wait(&v_full[s], (g / FA_KV_STAGES) & 1u);
+          tc::mbar_wait(&p_full[t], (bb + (uint32_t)jj) & 1u);                 // P_t(jj) in TMEM, O_t rescaled if needed
           tc::tcgen05_fence_after();
-          const uint32_t dV = dV0 + (uint32_t)(s * (FA_KV_BYTES >> 4));
+          const uint32_t dV = dV0 + s * (FA_KV_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < FA_BN / 16; ++k)        // A: P k-slice = 16 keys = 8 TMEM columns;  B: V rows [16k, 16k+16) x 64 dims
             tc::umma_f16_ts(tO, tP + (uint32_t)(k * 8), dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (jj | k) ? 1u : 0u);
           tc::umma_commit(&pv_done[t]);                                        // O_t includes block jj; P_t free
           tc::umma_commit(&v_empty[s]);
+          if (twice) tc::umma_commit(&v_empty[s]);
         }
-        // every commit of this segment has arrived before the barriers are re-initialised for the next one
-        tc::mbar_wait(&v_empty[(nb - 1) % FA_KV_STAGES], ((nb - 1) / FA_KV_STAGES) & 1);
       }
       __syncwarp();
     } else if (warp >= 4) {
@@ -310,10 +313,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
       uint32_t ov[32];
       float l = 1.f;
+      const uint32_t bb = blk_base[t];
 
       if (tile_valid) {
         for (int jj = 0; jj < nb; ++jj) {
-          const uint32_t ph = (uint32_t)jj & 1u;
+          const uint32_t ph = (bb + (uint32_t)jj) & 1u;
           tc::mbar_wait(&s_full[t], ph);
           tc::tcgen05_fence_after();
           uint32_t v[64];
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           const bool need = jj > 0 && m_blk > m_run + FA_TAU;
           const float m_new = (jj == 0 || need) ? m_blk : m_run;
           if (jj > 0) {
-            tc::mbar_wait(&pv_done[t], ((uint32_t)(jj - 1)) & 1u);            // PV_t(jj-1) retired: O_t complete, P_t free
+            tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
             if (__any_sync(0xffffffffu, need)) {
               tc::tcgen05_fence_after();
               const float alpha = need ? ex2_approx(m_run - m_new) : 1.f;     // O_t and the row sum are relative to m_run
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
         lsum_s[t][hf][q] = l_part;
         named_bar_sync(pair_bar, 64);
         l = l_part + lsum_s[t][hf ^ 1][q];
-        tc::mbar_wait(&pv_done[t], ((uint32_t)(nb - 1)) & 1u);
+        tc::mbar_wait(&pv_done[t], (bb + (uint32_t)(nb - 1)) & 1u);
         tc::tcgen05_fence_after();
         tmem_ld32x(tO, ov);
         tc::tmem_ld_wait();
@@ -451,7 +455,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       }
     }
     u = item_start + kb1;
-    // ---- next segment: every pipeline of this one has drained (the softmax groups waited for the last PV)
+    ++seg; kv_base += (uint32_t)nb; blk_base[0] += (uint32_t)nb; if (validB) blk_base[1] += (uint32_t)nb;
+    // ---- next segment: the softmax groups have O_t in registers (they waited for the last PV), Q / O / P may be overwritten
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tc {
 
@@ -35,7 +36,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 26)) {
+#ifdef I4D_MBAR_DEBUG
+      printf("mbar_wait timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+#endif
+      __trap();
+    }
   }
 }
 

@@ -83,16 +83,12 @@ class LightGlueB200:
     def _ffn(self, xm: torch.Tensor, L, tag: str):
         """xm [n,512] = [x | message]; x <- x + W2 gelu(LN(W1 [x|m]))   (lightglue.py:144-149,162)"""
         x = xm[:, :256]
-        if self._tc is not None:
-            return self._tc.ffn(xm, L, tag)
         h = ops.gemm_f32(xm, L[f"w1_{tag}"], L[f"b1_{tag}"])
         ops.layernorm_gelu(h, L[f"g_{tag}"], L[f"be_{tag}"])
         ops.gemm_f32(h, L[f"w2_{tag}"], L[f"b2_{tag}"], residual=x, out=x)
 
     def _self_block(self, xm: torch.Tensor, cs: torch.Tensor, L):
         x = xm[:, :256]
-        if self._tc is not None:
-            return self._tc.self_block(xm, cs, L)
         qkv = ops.gemm_f32(x, L["wqkv"], L["bqkv"])
         ops.lg_rotary_(qkv[:, :256], cs)
         ops.lg_rotary_(qkv[:, 256:512], cs)
@@ -102,8 +98,6 @@ class LightGlueB200:
         self._ffn(xm, L, "s")
 
     def _cross_block(self, xm0: torch.Tensor, xm1: torch.Tensor, L):
-        if self._tc is not None:
-            return self._tc.cross_block(xm0, xm1, L)
         p0 = ops.gemm_f32(xm0[:, :256], L["wqkv_x"], L["bqkv_x"])     # [m,512] = [qk | v]
         p1 = ops.gemm_f32(xm1[:, :256], L["wqkv_x"], L["bqkv_x"])
         a0 = torch.empty((xm0.shape[0], 256), device=xm0.device, dtype=torch.float32)
@@ -132,10 +126,22 @@ class LightGlueB200:
                     "scores": torch.zeros(0, device=dev), "prune0": torch.ones(m, device=dev), "prune1": torch.ones(n, device=dev)}
         cs0 = ops.lg_posenc(kpts0.contiguous(), float(size0[0]), float(size0[1]), W.Wr)
         cs1 = ops.lg_posenc(kpts1.contiguous(), float(size1[0]), float(size1[1]), W.Wr)
-        xm0 = torch.empty((m, 512), device=dev, dtype=torch.float32)
-        xm1 = torch.empty((n, 512), device=dev, dtype=torch.float32)
-        xm0[:, :256] = desc0
-        xm1[:, :256] = desc1
+        tc = self._tc
+        if tc is not None:
+            # tensor-core path: both images stacked in one f32 residual stream X [m+n,256] (+ its bf16 shadow inside `tc`)
+            X = torch.empty((m + n, 256), device=dev, dtype=torch.float32)
+            X[:m] = desc0
+            X[m:] = desc1
+            cs = torch.cat([cs0, cs1])
+            tc.refresh_shadow(X)
+            mc, nc = m, n                                                        # current (un-pruned) keypoint counts
+            x0, x1 = X[:mc], X[mc:]
+        else:
+            xm0 = torch.empty((m, 512), device=dev, dtype=torch.float32)
+            xm1 = torch.empty((n, 512), device=dev, dtype=torch.float32)
+            xm0[:, :256] = desc0
+            xm1[:, :256] = desc1
+            x0, x1 = xm0[:, :256], xm1[:, :256]
         do_stop, do_prune = self.depth_confidence > 0, self.width_confidence > 0
         ind0, ind1 = torch.arange(m, device=dev), torch.arange(n, device=dev)
         prune0 = torch.ones(m, dtype=torch.int64, device=dev)
@@ -143,47 +149,70 @@ class LightGlueB200:
         i = 0
         for i in range(nl):
             L = W.layers[i]
-            self._self_block(xm0, cs0, L)
-            self._self_block(xm1, cs1, L)
-            self._cross_block(xm0, xm1, L)
+            if tc is not None:
+                tc.layer(X, cs, mc, nc, L)
+            else:
+                self._self_block(xm0, cs0, L)
+                self._self_block(xm1, cs1, L)
+                self._cross_block(xm0, xm1, L)
             if collect is not None:
-                collect.append((xm0[:, :256].clone(), xm1[:, :256].clone()))
+                collect.append((x0.clone(), x1.clone()))
             if i == nl - 1:
                 continue
             t0 = t1 = None
             if do_stop:   # lightglue.py:491-494,571-579
                 tk = W.token[i]
-                t0 = torch.sigmoid(self._lin1(xm0[:, :256], tk["w"], tk["b"]))
-                t1 = torch.sigmoid(self._lin1(xm1[:, :256], tk["w"], tk["b"]))
+                t0 = torch.sigmoid(self._lin1(x0, tk["w"], tk["b"]))
+                t1 = torch.sigmoid(self._lin1(x1, tk["w"], tk["b"]))
                 unconf = (torch.cat([t0, t1]) < W.conf_thr[i]).float().sum()
                 if float(1.0 - unconf / (m + n)) > self.depth_confidence:      # host read, as in the reference
                     break
             if do_prune:  # lightglue.py:495-510 (CPU semantics: evaluated at every layer)
                 A = W.assign[i]
+                pruned = False
                 for side in (0, 1):
-                    xm, t = (xm0, t0) if side == 0 else (xm1, t1)
-                    keep = torch.sigmoid(self._lin1(xm[:, :256], A["wm"], A["bm"])) > (1 - self.width_confidence)
+                    x, t = (x0, t0) if side == 0 else (x1, t1)
+                    keep = torch.sigmoid(self._lin1(x, A["wm"], A["bm"])) > (1 - self.width_confidence)
                     if t is not None:
                         keep = keep | (t <= W.conf_thr[i])
                     idx = torch.nonzero(keep).squeeze(1)                          # host read (data-dependent size)
-                    if idx.numel() != xm.shape[0]:
+                    if idx.numel() != x.shape[0]:
+                        pruned = True
                         if side == 0:
-                            ind0, xm0, cs0 = ind0[idx], xm0.index_select(0, idx), cs0.index_select(0, idx)
+                            ind0, cs0 = ind0[idx], cs0.index_select(0, idx)
+                            if tc is not None:
+                                x0 = x0.index_select(0, idx)
+                            else:
+                                xm0 = xm0.index_select(0, idx)
+                                x0 = xm0[:, :256]
                         else:
-                            ind1, xm1, cs1 = ind1[idx], xm1.index_select(0, idx), cs1.index_select(0, idx)
+                            ind1, cs1 = ind1[idx], cs1.index_select(0, idx)
+                            if tc is not None:
+                                x1 = x1.index_select(0, idx)
+                            else:
+                                xm1 = xm1.index_select(0, idx)
+                                x1 = xm1[:, :256]
                     if side == 0:
                         prune0[ind0] += 1
                     else:
                         prune1[ind1] += 1
+                if pruned and tc is not None:                                    # re-pack the stacked stream and its shadow
+                    mc, nc = x0.shape[0], x1.shape[0]
+                    X = torch.cat([x0, x1])
+                    cs = torch.cat([cs0, cs1])
+                    x0, x1 = X[:mc], X[mc:]
+                    if mc + nc > 0:
+                        tc.refresh_shadow(X)
+                if x0.shape[0] == 0 or x1.shape[0] == 0:
+                    break
         A = W.assign[i]
-        x0, x1 = xm0[:, :256], xm1[:, :256]
         if x0.shape[0] == 0 or x1.shape[0] == 0:
             a = torch.full((x0.shape[0],), -1, device=dev, dtype=torch.int32)
             b = torch.full((x1.shape[0],), -1, device=dev, dtype=torch.int32)
             c, d = torch.zeros(x0.shape[0], device=dev), torch.zeros(x1.shape[0], device=dev)
         else:
-            if self._tc is not None:
-                sim = self._tc.similarity(x0, x1, A)
+            if tc is not None:
+                sim = tc.similarity(X, x0.shape[0], x1.shape[0], A)
             else:
                 md0, md1 = ops.gemm_f32(x0, A["wf"], A["bf"]), ops.gemm_f32(x1, A["wf"], A["bf"])
                 sim = ops.gemm_f32(md0, md1)

@@ -57,7 +57,23 @@ def to_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1})
+def rotary_cast_bf16(qkv32: torch.Tensor, cs: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
+    """qkv32 [n,768] f32, cs [n,64] -> out16 [n,768] bf16 with the rotary embedding applied to q and k (one pass)."""
+    assert qkv32.dtype == torch.float32 and out16.dtype == BF16 and cs.dtype == torch.float32 and cs.is_contiguous()
+    assert qkv32.shape[1] == 768 and out16.shape == qkv32.shape and cs.shape == (qkv32.shape[0], 64)
+    N.call("i4d_lg_rotary_cast_bf16", qkv32, qkv32.stride(0), cs, qkv32.shape[0], out16, out16.stride(0), _st())
+    return out16
+
+
+def layernorm_gelu_bf16(x32: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out16: torch.Tensor, eps: float = 1e-5):
+    """x32 [n,512] f32 -> GELU(LayerNorm(x32)) as bf16 (one pass)."""
+    assert x32.dtype == torch.float32 and out16.dtype == BF16 and x32.shape == out16.shape and x32.shape[1] == 512
+    N.call("i4d_layernorm_gelu_bf16", x32, x32.stride(0), gamma, beta, x32.shape[0], 512, float(eps), out16, out16.stride(0), _st())
+    return out16
+
+
+N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1, "i4d_lg_rotary_cast_bf16": 1,
+                    "i4d_layernorm_gelu_bf16": 1})
 
 
 class SuperGlueTensorCore:
@@ -161,7 +177,12 @@ class SuperGlueTensorCore:
 
 
 class LightGlueTensorCore:
-    """Self / cross / FFN blocks and the similarity matrix of LightGlue on the tensor-core path (lightglue.py:133-216,268-284)."""
+    """Self / cross / FFN blocks and the similarity matrix of LightGlue on the tensor-core path (lightglue.py:133-216,268-284).
+
+    Both images are STACKED in one [m + n, .] set of buffers, so every GEMM / element-wise pass / attention launch of a layer
+    covers both images (the weights are shared).  Per block the activations make one trip through HBM between two tensor-core
+    kernels: the f32 master copy of the residual stream X [m+n,256] is read and written only by the GEMM epilogues (which also
+    emit its bf16 shadow, the A operand of the next GEMM), rotary + cast and LayerNorm + GELU + cast are single passes."""
 
     def __init__(self, w, device):
         self.dev = torch.device(device)
@@ -172,61 +193,57 @@ class LightGlueTensorCore:
                 self.h[id(L[k])] = h(L[k])
         for A in w.assign:
             self.h[id(A["wf"])] = h(A["wf"])
+        self._buf = {}
 
     def _w(self, t):
         return self.h[id(t)]
 
-    def _x16(self, xm: torch.Tensor) -> torch.Tensor:
-        """bf16 shadow [n,512] of the f32 [x | message] buffer, refreshed for the x half."""
-        x16 = torch.empty(xm.shape, device=xm.device, dtype=BF16)
-        to_bf16(xm[:, :256], x16[:, :256])
-        return x16
+    def buffers(self, nt: int):
+        """Persistent activation buffers for nt = m + n stacked keypoints (re-allocated only when nt grows)."""
+        b = self._buf
+        if b.get("cap", 0) < nt:
+            d = self.dev
+            b = self._buf = {"cap": nt, "x16": torch.empty((nt, 512), device=d, dtype=BF16),
+                             "qkv32": torch.empty((nt, 768), device=d), "qkv16": torch.empty((nt, 768), device=d, dtype=BF16),
+                             "att": torch.empty((nt, 256), device=d, dtype=BF16), "hid32": torch.empty((nt, 512), device=d),
+                             "hid16": torch.empty((nt, 512), device=d, dtype=BF16), "md": torch.empty((nt, 256), device=d, dtype=BF16)}
+        return b
 
-    def ffn(self, xm, L, tag, x16=None):
-        x16 = self._x16(xm) if x16 is None else x16
-        n = xm.shape[0]
-        hid = torch.empty((n, 512), device=xm.device, dtype=torch.float32)
-        gemm_tc(x16, self._w(L[f"w1_{tag}"]), L[f"b1_{tag}"], out32=hid)
-        ops.layernorm_gelu(hid, L[f"g_{tag}"], L[f"be_{tag}"])
-        h16 = torch.empty((n, 512), device=xm.device, dtype=BF16)
-        to_bf16(hid, h16)
-        x = xm[:, :256]
-        gemm_tc(h16, self._w(L[f"w2_{tag}"]), L[f"b2_{tag}"], residual=x, out32=x)
+    def refresh_shadow(self, X: torch.Tensor):
+        """bf16 shadow of the f32 residual stream (first layer, and after a pruning step re-packed X)."""
+        to_bf16(X, self.buffers(X.shape[0])["x16"][: X.shape[0], :256])
 
-    def self_block(self, xm, cs, L):
-        n = xm.shape[0]
-        x16 = self._x16(xm)
-        qkv = torch.empty((n, 768), device=xm.device, dtype=torch.float32)
-        gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv)
-        ops.lg_rotary_(qkv[:, :256], cs)
-        ops.lg_rotary_(qkv[:, 256:512], cs)
-        q16 = torch.empty((n, 768), device=xm.device, dtype=BF16)
-        to_bf16(qkv, q16)
-        att = torch.empty((n, 256), device=xm.device, dtype=BF16)
-        attention_tc(q16, [(0, n, 0, n)], att, 0, 256, 512)
+    def _ffn(self, X, nt, L, tag, b):
+        x16, hid32, hid16 = b["x16"][:nt], b["hid32"][:nt], b["hid16"][:nt]
+        gemm_tc(x16, self._w(L[f"w1_{tag}"]), L[f"b1_{tag}"], out32=hid32)
+        layernorm_gelu_bf16(hid32, L[f"g_{tag}"], L[f"be_{tag}"], hid16)
+        gemm_tc(hid16, self._w(L[f"w2_{tag}"]), L[f"b2_{tag}"], residual=X, out32=X, out16=x16[:, :256])
+
+    def layer(self, X: torch.Tensor, cs: torch.Tensor, m: int, n: int, L):
+        """One LightGlue layer (self block on both images, cross block) on the stacked residual stream X [m+n,256] f32 (updated
+        in place), cs [m+n,64] rotary tables.  The bf16 shadow of X must be current (`refresh_shadow`)."""
+        nt = m + n
+        b = self.buffers(nt)
+        x16, qkv32, qkv16, att = b["x16"][:nt], b["qkv32"][:nt], b["qkv16"][:nt], b["att"][:nt]
+        # ---- self block (lightglue.py:133-163): Wqkv -> rotary(q, k) -> attention -> out_proj -> FFN([x | message]) ----
+        gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv32)
+        rotary_cast_bf16(qkv32, cs, qkv16)
+        attention_tc(qkv16, [(0, m, 0, m), (m, n, m, n)], att, 0, 256, 512)
         gemm_tc(att, self._w(L["wo"]), L["bo"], out16=x16[:, 256:])
-        self.ffn(xm, L, "s", x16)
-
-    def cross_block(self, xm0, xm1, L):
-        m, n = xm0.shape[0], xm1.shape[0]
-        x16 = torch.empty((m + n, 512), device=xm0.device, dtype=BF16)
-        to_bf16(xm0[:, :256], x16[:m, :256])
-        to_bf16(xm1[:, :256], x16[m:, :256])
-        p = torch.empty((m + n, 512), device=xm0.device, dtype=BF16)        # [qk | v] for both images
+        self._ffn(X, nt, L, "s", b)
+        # ---- cross block (lightglue.py:166-216): shared to_qk (q = k) and to_v, both directions in one attention launch ----
+        p = qkv16[:, :512]                                                   # [qk | v]
         gemm_tc(x16[:, :256], self._w(L["wqkv_x"]), L["bqkv_x"], out16=p)
-        att = torch.empty((m + n, 256), device=xm0.device, dtype=BF16)
-        attention_tc(p, [(0, m, m, n), (m, n, 0, m)], att, 0, 0, 256)      # q and k share the `qk` projection
+        attention_tc(qkv16, [(0, m, m, n), (m, n, 0, m)], att, 0, 0, 256)
         gemm_tc(att, self._w(L["wo_x"]), L["bo_x"], out16=x16[:, 256:])
-        self.ffn(xm0, L, "x", x16[:m])
-        self.ffn(xm1, L, "x", x16[m:])
+        self._ffn(X, nt, L, "x", b)
 
-    def similarity(self, x0, x1, A):
-        m, n = x0.shape[0], x1.shape[0]
-        x16 = torch.empty((m + n, 256), device=x0.device, dtype=BF16)
-        to_bf16(x0, x16[:m])
-        to_bf16(x1, x16[m:])
-        md = torch.empty((m + n, 256), device=x0.device, dtype=BF16)
-        gemm_tc(x16, self._w(A["wf"]), A["bf"], out16=md)
-        sim = torch.empty((m, n), device=x0.device, dtype=torch.float32)
+    def similarity(self, X: torch.Tensor, m: int, n: int, A):
+        """sim = final_proj(x0) final_proj(x1)^T (lightglue.py:268-284; the 256^-1/4 scaling is folded into the weights)."""
+        nt = m + n
+        b = self.buffers(nt)
+        md = b["md"][:nt]
+        gemm_tc(b["x16"][:nt, :256], self._w(A["wf"]), A["bf"], out16=md)
+        sim = torch.empty((m, n), device=X.device, dtype=torch.float32)
         gemm_tc(md[:m], md[m:], out32=sim)
         return sim

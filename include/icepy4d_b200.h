@@ -110,10 +110,18 @@ int i4d_sg_kenc_input(const float* kpts, const float* scores, int n, float width
 int i4d_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr,
                      float* C32, int ldc32, void* C16, int ldc16, int M, int N, int K, float alpha, int relu,
                      void* stream);
+/* LightGlue glue of the tensor-core path (lightglue.py:49-57,144-159): fused element-wise passes between the tcgen05 kernels.
+ *   i4d_lg_rotary_cast_bf16: qkv [n,768] f32 (heads contiguous: q | k | v, 4 x 64 each), cs [n,64] (cos[32] | sin[32] per rotary
+ *     pair, from i4d_lg_posenc) -> out [n,768] bf16 with the rotary embedding applied to q and k.
+ *   i4d_layernorm_gelu_bf16: X [n,C] f32 -> GELU(LayerNorm(X) * gamma + beta) as bf16 (C = 512). */
+int i4d_lg_rotary_cast_bf16(const float* qkv, int ldx, const float* cs, int n, void* out, int ldy, void* stream);
+int i4d_layernorm_gelu_bf16(const float* X, int ldx, const float* gamma, const float* beta, int n, int C, float eps, void* out,
+                            int ldy, void* stream);
 /* Flash attention, head_dim 64, on one bf16 buffer X [rows, ld] holding Q, K and V as column blocks
  * (q_col/k_col/v_col + 64*head).  problems_host: n_problems x {q_row0, nq, k_row0, nk} (host ints, 1..4 problems run in
  * one launch: both images of a self/cross layer).  O [rows, ldo] bf16, row-indexed like Q.  `workspace` (nullable,
- * i4d_attention_workspace_bytes()) lets the kernel split the ragged last wave of its one-CTA-per-SM schedule along the keys.
+ * i4d_attention_workspace_bytes()) lets the persistent kernel cut the key blocks of all (problem, head, 256-query tile) items into
+ * equal per-SM ranges and merge the parts of items a range boundary cuts; without it every CTA runs whole items.
  * Replaces superglue.py:87-93 and lightglue.py:108-130 on the throughput path. */
 size_t i4d_attention_workspace_bytes(void);
 int i4d_attention_bf16_tc(const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads,
