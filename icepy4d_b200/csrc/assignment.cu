@@ -10,7 +10,7 @@
 // The (M+1) x (N+1) coupling matrix is never materialised: its dustbin row/column are the constant
 // `bin_score`, so their contribution to every log-sum-exp is added analytically.
 //
-// Building blocks (S is M x N row-major, ld = N):
+// Building blocks (S is M x N row-major with row pitch ld >= N floats; 128-bit loads whenever ld % 4 == 0):
 //   row_reduce : out_i = LSE_j / max_j ( scale * S_ij + coloff_j )      one warp per row, float4 streaming loads
 //   col_reduce : out_j = LSE_i / max_i ( scale * S_ij + rowoff_i )      column strips, partials + combine
 #include "common.cuh"
@@ -54,26 +54,24 @@ struct ArgAcc {  // running (max, first index of max)
 #define ROW_WARPS 8
 
 template <int MODE>
-__global__ void __launch_bounds__(ROW_WARPS * 32) row_reduce_kernel(const float* __restrict__ S, int M, int N,
+__global__ void __launch_bounds__(ROW_WARPS * 32) row_reduce_kernel(const float* __restrict__ S, int M, int N, int ld,
                                                                     float scale, const float* __restrict__ coloff,
                                                                     const float* __restrict__ extra_ptr, float extra_add, float base,
                                                                     float* __restrict__ out_val,
                                                                     int* __restrict__ out_idx) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* r = S + (size_t)row * N;
+  const float* r = S + (size_t)row * ld;
+  const int Nv = (ld & 3) ? 0 : (N & ~3);        // columns covered by 128-bit loads; the rest (tail, or everything) is scalar
   if (MODE == 2) {
     ArgAcc a; a.init();
-    if ((N & 3) == 0) {
-      for (int j = lane * 4; j < N; j += 128) {
-        float4 x = ldg_stream(reinterpret_cast<const float4*>(r + j));
-        float4 o = coloff ? __ldg(reinterpret_cast<const float4*>(coloff + j)) : make_float4(0, 0, 0, 0);
-        a.add(fmaf(scale, x.x, o.x), j); a.add(fmaf(scale, x.y, o.y), j + 1);
-        a.add(fmaf(scale, x.z, o.z), j + 2); a.add(fmaf(scale, x.w, o.w), j + 3);
-      }
-    } else {
-      for (int j = lane; j < N; j += 32) a.add(fmaf(scale, r[j], coloff ? coloff[j] : 0.f), j);
+    for (int j = lane * 4; j < Nv; j += 128) {
+      float4 x = ldg_stream(reinterpret_cast<const float4*>(r + j));
+      float4 o = coloff ? __ldg(reinterpret_cast<const float4*>(coloff + j)) : make_float4(0, 0, 0, 0);
+      a.add(fmaf(scale, x.x, o.x), j); a.add(fmaf(scale, x.y, o.y), j + 1);
+      a.add(fmaf(scale, x.z, o.z), j + 2); a.add(fmaf(scale, x.w, o.w), j + 3);
     }
+    for (int j = Nv + lane; j < N; j += 32) a.add(fmaf(scale, r[j], coloff ? coloff[j] : 0.f), j);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float om = __shfl_xor_sync(0xffffffffu, a.m, o);
@@ -83,15 +81,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) row_reduce_kernel(const float*
     if (lane == 0) { out_val[row] = a.m; out_idx[row] = a.i; }
   } else {
     LseAcc a; a.init();
-    if ((N & 3) == 0) {
-      for (int j = lane * 4; j < N; j += 128) {
-        float4 x = ldg_stream(reinterpret_cast<const float4*>(r + j));
-        float4 o = coloff ? __ldg(reinterpret_cast<const float4*>(coloff + j)) : make_float4(0, 0, 0, 0);
-        a.add4(fmaf(scale, x.x, o.x), fmaf(scale, x.y, o.y), fmaf(scale, x.z, o.z), fmaf(scale, x.w, o.w));
-      }
-    } else {
-      for (int j = lane; j < N; j += 32) a.add1(fmaf(scale, r[j], coloff ? coloff[j] : 0.f));
+    for (int j = lane * 4; j < Nv; j += 128) {
+      float4 x = ldg_stream(reinterpret_cast<const float4*>(r + j));
+      float4 o = coloff ? __ldg(reinterpret_cast<const float4*>(coloff + j)) : make_float4(0, 0, 0, 0);
+      a.add4(fmaf(scale, x.x, o.x), fmaf(scale, x.y, o.y), fmaf(scale, x.z, o.z), fmaf(scale, x.w, o.w));
     }
+    for (int j = Nv + lane; j < N; j += 32) a.add1(fmaf(scale, r[j], coloff ? coloff[j] : 0.f));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float om = __shfl_xor_sync(0xffffffffu, a.m, o);
@@ -113,26 +108,26 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) row_reduce_kernel(const float*
 #define COL_THREADS 128
 
 template <int MODE>  // 0/1: LSE partials, 2: argmax partials
-__global__ void __launch_bounds__(COL_THREADS) col_partial_kernel(const float* __restrict__ S, int M, int N,
+__global__ void __launch_bounds__(COL_THREADS) col_partial_kernel(const float* __restrict__ S, int M, int N, int ld,
                                                                   float scale, const float* __restrict__ rowoff,
                                                                   int rows_per_split, float* __restrict__ pm,
                                                                   float* __restrict__ ps, int* __restrict__ pi) {
   const int j0 = (blockIdx.x * COL_THREADS + threadIdx.x) * 4;
   const int i0 = blockIdx.y * rows_per_split, i1 = min(M, i0 + rows_per_split);
   if (j0 >= N) return;
-  const bool vec = ((N & 3) == 0);
-  const int nv = vec ? 4 : min(4, N - j0);
+  const bool vec = ((ld & 3) == 0);           // 128-bit loads stay inside the row pitch; components >= nv are ignored
+  const int nv = min(4, N - j0);
   if (MODE == 2) {
     ArgAcc a[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) a[c].init();
     for (int i = i0; i < i1; ++i) {
       float o = rowoff ? __ldg(rowoff + i) : 0.f;
-      const float* p = S + (size_t)i * N + j0;
+      const float* p = S + (size_t)i * ld + j0;
       if (vec) {
         float4 x = ldg_stream(reinterpret_cast<const float4*>(p));
         a[0].add(fmaf(scale, x.x, o), i); a[1].add(fmaf(scale, x.y, o), i);
-        a[2].add(fmaf(scale, x.z, o), i); a[3].add(fmaf(scale, x.w, o), i);
+        a[2].add(fmaf(scale, x.z, o), i); a[3].add(fmaf(scale, x.w, o), i);      // columns >= nv: computed, never stored
       } else {
         for (int c = 0; c < nv; ++c) a[c].add(fmaf(scale, p[c], o), i);
       }
@@ -152,7 +147,7 @@ __global__ void __launch_bounds__(COL_THREADS) col_partial_kernel(const float* _
         float4 x[4]; float o[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          x[r] = ldg_stream(reinterpret_cast<const float4*>(S + (size_t)(i + r) * N + j0));
+          x[r] = ldg_stream(reinterpret_cast<const float4*>(S + (size_t)(i + r) * ld + j0));
           o[r] = rowoff ? __ldg(rowoff + i + r) : 0.f;
         }
         a[0].add4(fmaf(scale, x[0].x, o[0]), fmaf(scale, x[1].x, o[1]), fmaf(scale, x[2].x, o[2]), fmaf(scale, x[3].x, o[3]));
@@ -163,7 +158,7 @@ __global__ void __launch_bounds__(COL_THREADS) col_partial_kernel(const float* _
     }
     for (; i < i1; ++i) {
       float o = rowoff ? __ldg(rowoff + i) : 0.f;
-      const float* p = S + (size_t)i * N + j0;
+      const float* p = S + (size_t)i * ld + j0;
       for (int c = 0; c < nv; ++c) a[c].add1(fmaf(scale, p[c], o));
     }
     for (int c = 0; c < nv; ++c) {
@@ -243,20 +238,20 @@ struct AssignWs {
 };
 
 template <int MODE>
-static void launch_row(const float* S, int M, int N, float scale, const float* coloff, const float* extra_ptr,
+static void launch_row(const float* S, int M, int N, int ld, float scale, const float* coloff, const float* extra_ptr,
                        float extra_add, float base, float* out_val, int* out_idx, cudaStream_t st) {
-  row_reduce_kernel<MODE><<<i4d_cdiv(M, ROW_WARPS), ROW_WARPS * 32, 0, st>>>(S, M, N, scale, coloff, extra_ptr,
+  row_reduce_kernel<MODE><<<i4d_cdiv(M, ROW_WARPS), ROW_WARPS * 32, 0, st>>>(S, M, N, ld, scale, coloff, extra_ptr,
                                                                              extra_add, base, out_val, out_idx);
 }
 template <int MODE>
-static void launch_col(const float* S, int M, int N, float scale, const float* rowoff, const float* extra_ptr,
+static void launch_col(const float* S, int M, int N, int ld, float scale, const float* rowoff, const float* extra_ptr,
                        float extra_add, float base, float* out_val, int* out_idx, AssignWs& w, cudaStream_t st) {
   int splits = col_splits_for(M, N);
   int rps = i4d_cdiv(M, splits);
   rps = (rps + 3) & ~3;
   splits = i4d_cdiv(M, rps);
   dim3 grid(i4d_cdiv(N, COL_THREADS * 4), splits);
-  col_partial_kernel<MODE><<<grid, COL_THREADS, 0, st>>>(S, M, N, scale, rowoff, rps, w.pm, w.ps, w.pi);
+  col_partial_kernel<MODE><<<grid, COL_THREADS, 0, st>>>(S, M, N, ld, scale, rowoff, rps, w.pm, w.ps, w.pi);
   col_combine_kernel<MODE><<<i4d_cdiv(N, 256), 256, 0, st>>>(w.pm, w.ps, w.pi, splits, N, extra_ptr, extra_add, base,
                                                              out_val, out_idx);
 }
@@ -273,7 +268,7 @@ static int check_ws(const char* fn, int M, int N, size_t have) {
 // ---- primitives exposed for tests / roofline measurements -------------------------------------------
 extern "C" __attribute__((visibility("default"))) int i4d_row_lse(const float* S, int M, int N, float scale, const float* coloff, float* out, void* stream) {
   I4D_CHECK_ARG(S && out && M > 0 && N > 0, "null pointer or empty matrix");
-  launch_row<1>(S, M, N, scale, coloff, nullptr, 0.f, 0.f, out, nullptr, (cudaStream_t)stream);
+  launch_row<1>(S, M, N, N, scale, coloff, nullptr, 0.f, 0.f, out, nullptr, (cudaStream_t)stream);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
@@ -282,40 +277,40 @@ extern "C" __attribute__((visibility("default"))) int i4d_col_lse(const float* S
   I4D_CHECK_ARG(S && out && workspace && M > 0 && N > 0, "null pointer or empty matrix");
   if (int rc = check_ws("i4d_col_lse", M, N, workspace_bytes)) return rc;
   AssignWs w(workspace, M, N);
-  launch_col<1>(S, M, N, scale, rowoff, nullptr, 0.f, 0.f, out, nullptr, w, (cudaStream_t)stream);
+  launch_col<1>(S, M, N, N, scale, rowoff, nullptr, 0.f, 0.f, out, nullptr, w, (cudaStream_t)stream);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
 
 // ---- Sinkhorn potentials ------------------------------------------------------------------------------
-static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
+static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, int iters, float* u, float* v, AssignWs& w,
                                  cudaStream_t st);
 static int g_sinkhorn_mode = 0;   // 0 = fused when the shape allows, 1 = always the two-pass kernels (tests / comparison)
 
-static void sinkhorn_iterations(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
+static void sinkhorn_iterations(float* S, int M, int N, int ld, float alpha, int iters, float* u, float* v, AssignWs& w,
                                 cudaStream_t st) {
-  if (g_sinkhorn_mode == 0 && sinkhorn_fused_launch(S, M, N, alpha, iters, u, v, w, st) == 0) return;
+  if (g_sinkhorn_mode == 0 && sinkhorn_fused_launch(S, M, N, ld, alpha, iters, u, v, w, st) == 0) return;
   const float norm = -logf((float)M + (float)N);
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
   cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
   cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);
   for (int it = 0; it < iters; ++it) {
     // u_i = log_mu_i - LSE_j(Z_ij + v_j): rows i < M stream S; the dustbin row is a vector LSE
-    launch_row<0>(S, M, N, 1.f, v, v + N, alpha, norm, u, nullptr, st);
+    launch_row<0>(S, M, N, ld, 1.f, v, v + N, alpha, norm, u, nullptr, st);
     vec_lse_kernel<<<1, 1024, 0, st>>>(v, N + 1, alpha, log_mu_last, u + M);
     // v_j = log_nu_j - LSE_i(Z_ij + u_i)
-    launch_col<0>(S, M, N, 1.f, u, u + M, alpha, norm, v, nullptr, w, st);
+    launch_col<0>(S, M, N, ld, 1.f, u, u + M, alpha, norm, v, nullptr, w, st);
     vec_lse_kernel<<<1, 1024, 0, st>>>(u, M + 1, alpha, log_nu_last, v + N);
   }
 }
 
-extern "C" __attribute__((visibility("default"))) int i4d_sinkhorn(const float* scores, int M, int N, float bin_score, int iters, float* u, float* v,
+extern "C" __attribute__((visibility("default"))) int i4d_sinkhorn(float* scores, int M, int N, int ld, float bin_score, int iters, float* u, float* v,
                             void* workspace, size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(scores && u && v && workspace, "null pointer");
-  I4D_CHECK_ARG(M > 0 && N > 0 && iters >= 0, "bad sizes");
+  I4D_CHECK_ARG(M > 0 && N > 0 && ld >= N && iters >= 0, "bad sizes");
   if (int rc = check_ws("i4d_sinkhorn", M, N, workspace_bytes)) return rc;
   AssignWs w(workspace, M, N);
-  sinkhorn_iterations(scores, M, N, bin_score, iters, u, v, w, (cudaStream_t)stream);
+  sinkhorn_iterations(scores, M, N, ld, bin_score, iters, u, v, w, (cudaStream_t)stream);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
@@ -343,19 +338,19 @@ __global__ void mutual_kernel1(const int* __restrict__ idx0, const int* __restri
   m1[j] = (mutual && m0[i] >= 0) ? i : -1;
 }
 
-extern "C" __attribute__((visibility("default"))) int i4d_sg_assign(const float* scores, int M, int N, float bin_score, int iters, float match_threshold,
+extern "C" __attribute__((visibility("default"))) int i4d_sg_assign(float* scores, int M, int N, int ld, float bin_score, int iters, float match_threshold,
                              int* matches0, int* matches1, float* mscores0, float* mscores1, float* u, float* v,
                              void* workspace, size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(scores && matches0 && matches1 && mscores0 && mscores1 && u && v && workspace, "null pointer");
-  I4D_CHECK_ARG(M > 0 && N > 0 && iters >= 0, "bad sizes");
+  I4D_CHECK_ARG(M > 0 && N > 0 && ld >= N && iters >= 0, "bad sizes");
   if (int rc = check_ws("i4d_sg_assign", M, N, workspace_bytes)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   AssignWs w(workspace, M, N);
-  sinkhorn_iterations(scores, M, N, bin_score, iters, u, v, w, st);
+  sinkhorn_iterations(scores, M, N, ld, bin_score, iters, u, v, w, st);
   const float norm = -logf((float)M + (float)N);
   // P_ij = S_ij + u_i + v_j - norm over the core block: row argmax ignores u_i, column argmax ignores v_j
-  launch_row<2>(scores, M, N, 1.f, v, nullptr, 0.f, 0.f, w.val0, w.idx0, st);
-  launch_col<2>(scores, M, N, 1.f, u, nullptr, 0.f, 0.f, w.val1, w.idx1, w, st);
+  launch_row<2>(scores, M, N, ld, 1.f, v, nullptr, 0.f, 0.f, w.val0, w.idx0, st);
+  launch_col<2>(scores, M, N, ld, 1.f, u, nullptr, 0.f, 0.f, w.val1, w.idx1, w, st);
   mutual_kernel0<<<i4d_cdiv(M, 256), 256, 0, st>>>(w.val0, w.idx0, u, -norm, w.idx1, M, match_threshold, matches0,
                                                    mscores0);
   mutual_kernel1<<<i4d_cdiv(N, 256), 256, 0, st>>>(w.idx0, w.idx1, matches0, mscores0, N, matches1, mscores1);
@@ -375,20 +370,20 @@ __global__ void lg_offsets_kernel(const float* __restrict__ z, const float* __re
   if (i < n) off[i] = logsigmoidf_(z[i]) - lse[i];
 }
 
-extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float* sim, int M, int N, const float* z0, const float* z1, float filter_threshold,
+extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float* sim, int M, int N, int ld, const float* z0, const float* z1, float filter_threshold,
                              int* matches0, int* matches1, float* mscores0, float* mscores1, void* workspace,
                              size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(sim && z0 && z1 && matches0 && matches1 && mscores0 && mscores1 && workspace, "null pointer");
-  I4D_CHECK_ARG(M > 0 && N > 0, "bad sizes");
+  I4D_CHECK_ARG(M > 0 && N > 0 && ld >= N, "bad sizes");
   if (int rc = check_ws("i4d_lg_assign", M, N, workspace_bytes)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   AssignWs w(workspace, M, N);
-  launch_row<1>(sim, M, N, 1.f, nullptr, nullptr, 0.f, 0.f, w.rl, nullptr, st);
-  launch_col<1>(sim, M, N, 1.f, nullptr, nullptr, 0.f, 0.f, w.cl, nullptr, w, st);
+  launch_row<1>(sim, M, N, ld, 1.f, nullptr, nullptr, 0.f, 0.f, w.rl, nullptr, st);
+  launch_col<1>(sim, M, N, ld, 1.f, nullptr, nullptr, 0.f, 0.f, w.cl, nullptr, w, st);
   lg_offsets_kernel<<<i4d_cdiv(M, 256), 256, 0, st>>>(z0, w.rl, M, w.rowoff);
   lg_offsets_kernel<<<i4d_cdiv(N, 256), 256, 0, st>>>(z1, w.cl, N, w.coloff);
-  launch_row<2>(sim, M, N, 2.f, w.coloff, nullptr, 0.f, 0.f, w.val0, w.idx0, st);
-  launch_col<2>(sim, M, N, 2.f, w.rowoff, nullptr, 0.f, 0.f, w.val1, w.idx1, w, st);
+  launch_row<2>(sim, M, N, ld, 2.f, w.coloff, nullptr, 0.f, 0.f, w.val0, w.idx0, st);
+  launch_col<2>(sim, M, N, ld, 2.f, w.rowoff, nullptr, 0.f, 0.f, w.val1, w.idx1, w, st);
   mutual_kernel0<<<i4d_cdiv(M, 256), 256, 0, st>>>(w.val0, w.idx0, w.rowoff, 0.f, w.idx1, M, filter_threshold,
                                                    matches0, mscores0);
   mutual_kernel1<<<i4d_cdiv(N, 256), 256, 0, st>>>(w.idx0, w.idx1, matches0, mscores0, N, matches1, mscores1);
@@ -491,7 +486,7 @@ struct SkCtx {
   const float* S; float* stage_buf; uint64_t* full; uint64_t* bpart;
   float (*part_m)[SK_ROWS][SK_WARPS]; float (*part_s)[SK_ROWS][SK_WARPS];
   float* u; const float* v; float* pm; float* ps; int* flag;
-  int M, N, n4, row0, row1, nst, cta, keep_rows;
+  int M, N, NP, ld, n4, row0, row1, nst, cta, keep_rows, pf, tid, warp, lane; uint32_t total;   // NP = 4 * n4: N rounded up to whole float4 groups
   float norm, c_mu, c_nu, extra_row, kfac;
   const float* uold_s;   // previous-iteration u of this CTA's band, pre-scaled by log2(e) (shared memory)
   uint32_t row_bytes;
@@ -526,7 +521,13 @@ __device__ __forceinline__ void sk_issue(const SkCtx& c, uint32_t seq) {
   else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   sk_mbar_expect(&c.full[buf], nr * c.row_bytes);
   for (int k = 0; k < nr; ++k)
-    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.N, c.S + (size_t)(r + k) * c.N, c.row_bytes, &c.full[buf], policy);
+    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.NP, c.S + (size_t)(r + k) * c.ld, c.row_bytes, &c.full[buf], policy);
+  if (c.pf > 0 && seq + (uint32_t)c.pf < c.total) {      // pull a later stage of the band from HBM into L2 ahead of its smem fill
+    const int rp = c.row0 + sk_idx(seq + (uint32_t)c.pf, c.nst) * SK_ROWS;
+    const int np = min(SK_ROWS, c.row1 - rp);
+    for (int k = 0; k < np; ++k)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c.S + (size_t)(rp + k) * c.ld), "r"(c.row_bytes) : "memory");
+  }
 }
 __device__ __forceinline__ void sk_wait_full(const SkCtx& c, SkRing& rg) {
   sk_mbar_wait(&c.full[rg.buf], (rg.full_par >> rg.buf) & 1u);
@@ -540,7 +541,7 @@ template <bool FULL>
 __device__ __forceinline__ void sk_stage_exact(const SkCtx& c, int idx, SkRing& rg, const float (&vl)[SK_GROUPS][4],
                                                L2Acc (&col)[SK_GROUPS][4]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = c.N, n4 = c.n4;
+  const int N = c.NP, n4 = c.n4;
   const int pp = rg.seq & 1;
   const int r_base = c.row0 + idx * SK_ROWS;
   const int nr = FULL ? SK_ROWS : min(SK_ROWS, c.row1 - r_base);
@@ -598,7 +599,7 @@ __device__ __forceinline__ void sk_stage_exact(const SkCtx& c, int idx, SkRing& 
 
 __device__ __forceinline__ void sk_band_exact(const SkCtx& c, SkRing& rg, const float4 (&vraw)[SK_GROUPS]) {
   const int tid = threadIdx.x;
-  const int N = c.N, n4 = c.n4;
+  const int N = c.NP, n4 = c.n4;
   float vl[SK_GROUPS][4];                                          // old v of my columns, log2 domain
   L2Acc col[SK_GROUPS][4];
 #pragma unroll
@@ -634,7 +635,7 @@ __device__ __forceinline__ void sk_band_exact(const SkCtx& c, SkRing& rg, const 
 template <bool FULL>
 __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t seq, uint32_t fq, SkRing& rg,
                                              const float (&e)[SK_ROWS][SK_GROUPS][4], float2 (&cs)[SK_GROUPS][2]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = c.warp, lane = c.lane;
   const uint32_t pp = fq & 1u, slot = fq & 3u;
   const int row = lane >> 4;
   const bool valid = FULL || (c.row0 + idx * SK_ROWS + row < c.row1);
@@ -660,7 +661,7 @@ __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t s
     cs[g][0] = __ffma2_rn(make_float2(e[1][g][0], e[1][g][1]), a1v, cs[g][0]);
     cs[g][1] = __ffma2_rn(make_float2(e[1][g][2], e[1][g][3]), a1v, cs[g][1]);
   }
-  if (warp == (int)(fq & (SK_WARPS - 1))) {                         // duty: off everybody's critical path
+  if (warp == (int)(fq & (SK_WARPS - 1))) {                                               // duty: off everybody's critical path
     if (lane == 0 && seq + SK_STAGES < rg.total) sk_issue(c, seq + SK_STAGES);
     if ((lane & 15) == 0 && valid) {
       if (!(sm > 0.f && sm < INFINITY)) atomicExch(c.flag, 1);
@@ -676,8 +677,8 @@ template <bool FULL, bool HAVE_PREV, bool PREV_FULL>
 __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_prev, SkRing& rg,
                                               const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2],
                                               float (&e_cur)[SK_ROWS][SK_GROUPS][4], const float (&e_prev)[SK_ROWS][SK_GROUPS][4]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = c.N, n4 = c.n4;
+  const int tid = c.tid, warp = c.warp, lane = c.lane;
+  const int N = c.NP, n4 = c.n4;
   // partial sums go to slot fq % 4: a warp may run a stage ahead of another one that has arrived for stage s+1 but not yet read
   // the partials of stage s, so a slot is only rewritten four stages later (behind the wait on stage s+2's barrier)
   const uint32_t pp = rg.fq & 1u, slot = rg.fq & 3u;
@@ -726,7 +727,7 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
 
 __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const float4 (&vraw)[SK_GROUPS]) {
   const int tid = threadIdx.x;
-  const int N = c.N, n4 = c.n4, nst = c.nst;
+  const int N = c.NP, n4 = c.n4, nst = c.nst;
   float2 vl[SK_GROUPS][2];                                         // old v of my columns, log2 domain
   float2 cs[SK_GROUPS][2];                                         // column sums relative to the stabiliser m_j = c_mu - v_j
 #pragma unroll
@@ -751,9 +752,9 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
     else if (f_) sk_stage_fast<true, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                       \
     else sk_stage_fast<false, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                              \
   }
+  int st = 1;
   if (SK_ISFULL(SK_IDX(0))) sk_stage_fast<true, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
   else sk_stage_fast<false, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
-  int st = 1;
 #pragma unroll 1
   for (; st + 1 < nst; st += 2) {
     SK_STAGE(st, eB, eA);
@@ -776,9 +777,9 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
   }
 }
 
-__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, float alpha,
+__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, int ld, float alpha,
                                                                        int iters, float* u, float* v, float* pm, float* ps,
-                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct, int dbg) {
+                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct, int dbg, int pf_stages) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
   __shared__ __align__(8) uint64_t full[SK_STAGES], bpart[2];
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   const float norm = -logf((float)M + (float)N);
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
   const float c_mu = fmaxf(norm, log_mu_last) * LOG2E, c_nu = fmaxf(norm, log_nu_last) * LOG2E;   // log2 of the largest marginals
-  const int n4 = N >> 2;
+  const int n4 = (N + 3) >> 2, NP = n4 * 4;      // columns [N, NP) hold -1e30 (filled by the launcher): they add 0 to every sum
 
   if (tid == 0) {
     for (int s = 0; s < SK_STAGES; ++s) sk_mbar_init(&full[s], 1);
@@ -804,10 +805,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   SkCtx ctx;
   ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.bpart = bpart;
   ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
-  ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
+  ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.NP = NP; ctx.ld = ld; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
   ctx.uold_s = uold_s;
-  ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)N * 4u;
+  ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)NP * 4u;
   ctx.keep_rows = (row1 - row0) * keep_pct / 100;
+  ctx.tid = tid; ctx.warp = warp; ctx.lane = lane;
+  ctx.pf = pf_stages;
+  ctx.total = (uint32_t)iters * (uint32_t)nst;
   ctx.kfac = exp2f(norm * LOG2E - c_mu);                             // a_i = 2^(u_i + m_i - c_mu) = kfac / rowsum_i
 
   // the band is re-streamed every iteration: stages are counted across iterations
@@ -881,7 +885,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
           float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 5
           for (int c = lane; c < G; c += 32) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(ps + (size_t)c * N) + tile);
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(ps + (size_t)c * NP) + tile);
             sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
           }
 #pragma unroll
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
             sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
             sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
           }
-          if (lane < 4) {
+          if (lane < 4 && tile * 4 + lane < N) {
             const int j = tile * 4 + lane;
             float sj = lane == 0 ? sm.x : lane == 1 ? sm.y : lane == 2 ? sm.z : sm.w;
             const float mj = c_mu - __ldcg(v + j) * LOG2E;            // the stabiliser used above (old v)
@@ -902,10 +906,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
           const int sub = lane >> 2, j = tile * 4 + (lane & 3);
           L2Acc a; a.init();
 #pragma unroll 2
-          for (int c = sub; c < G; c += 8) a.merge(__ldcg(pm + (size_t)c * N + j), __ldcg(ps + (size_t)c * N + j));
+          for (int c = sub; c < G; c += 8) a.merge(__ldcg(pm + (size_t)c * NP + j), __ldcg(ps + (size_t)c * NP + j));
 #pragma unroll
           for (int o = 4; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-          if (sub == 0) {
+          if (sub == 0 && j < N) {
             a.add(extra_col);
             v[j] = norm - a.lse_ln();
           }
@@ -936,13 +940,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
     }
     if (!(dbg & 2)) grid_barrier(); else __syncthreads();
-    if (fast_ok && __ldcg(flag) != 0 && !dbg) {
+    if (fast_ok && __ldcg(flag) != 0 && !(dbg & 7)) {
       // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode
       fast_ok = false;
       for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
       for (int i = cta * SK_THREADS + tid; i <= M; i += G * SK_THREADS) u[i] = 0.f;
       const uint32_t old_total = rg.total;
       rg.total = rg.seq + (uint32_t)iters * (uint32_t)nst;
+      ctx.total = rg.total;
       if (tid == 0)      // stages below min(old_total, seq + SK_STAGES) are already in flight
         for (uint32_t s = min(old_total, rg.seq + SK_STAGES); s < rg.total && s < rg.seq + SK_STAGES; ++s) sk_issue(ctx, s);
       it = -1;
@@ -951,13 +956,23 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   }
 }
 
-static bool sinkhorn_fused_ok(int M, int N) { return N % 4 == 0 && N <= SK_MAXN && N >= 64 && M >= 1; }
+// the row pitch must hold whole float4 groups (bulk copies are 16-byte granular); N itself may be anything in [64, SK_MAXN]
+static bool sinkhorn_fused_ok(const float* S, int M, int N, int ld) {
+  return (ld & 3) == 0 && ld >= ((N + 3) & ~3) && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && N <= SK_MAXN && N >= 64 && M >= 1;
+}
+// columns [N, round_up(N, 4)) of every row <- -1e30: the fused kernel then treats them as ordinary columns of weight 0
+__global__ void sk_pad_fill_kernel(float* S, int M, int N, int ld) {
+  const int npad = ((N + 3) & ~3) - N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * npad) return;
+  S[(size_t)(i / npad) * ld + N + i % npad] = -1e30f;
+}
 static int g_sinkhorn_fast = 1;   // 1 = a-priori stabilisers after the first two iterations, 0 = running maxima throughout
 
 // returns 0 when the fused kernel ran, 1 when the shape is unsupported (caller falls back to the two-pass kernels)
-static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int iters, float* u, float* v, AssignWs& w,
+static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, int iters, float* u, float* v, AssignWs& w,
                                  cudaStream_t st) {
-  if (!sinkhorn_fused_ok(M, N) || iters <= 0) return 1;
+  if (!sinkhorn_fused_ok(S, M, N, ld) || iters <= 0) return 1;
   static int coop = -1, sms = 0;   // B200 boxes are homogeneous: queried once
   if (coop < 0) {
     int dev = 0;
@@ -966,7 +981,8 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (!coop || sms <= 0 || sms > 256) return 1;
-  const size_t smem = (size_t)SK_STAGES * SK_ROWS * N * sizeof(float);
+  const int NP = (N + 3) & ~3;
+  const size_t smem = (size_t)SK_STAGES * SK_ROWS * NP * sizeof(float);
   static bool attr_seen[64] = {};
   if (i4d_first_use_on_device(attr_seen)) {
     if (cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -978,7 +994,8 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   if (rpc > SK_MAX_BAND) return 1;
   G = (M + rpc - 1) / rpc;                      // CTAs that actually own rows (<= sms <= 256 partial slots)
   cudaMemsetAsync(u, 0, (size_t)(M + 1) * sizeof(float), st);
-  cudaMemsetAsync(v, 0, (size_t)(N + 1) * sizeof(float), st);
+  cudaMemsetAsync(v, 0, (size_t)(NP + 1) * sizeof(float), st);       // v[N+1 .. NP] are read (never written) as the pad columns' potentials
+  if (NP != N) sk_pad_fill_kernel<<<i4d_cdiv(M * (NP - N), 256), 256, 0, st>>>(S, M, N, ld);
   float* pm = w.pm; float* ps = w.ps;
   int* flag = w.pi;
   cudaMemsetAsync(flag, 0, 2 * sizeof(int), st);   // [0] fast-mode trip flag, [1] grid-barrier arrival counter
@@ -991,8 +1008,12 @@ static int sinkhorn_fused_launch(const float* S, int M, int N, float alpha, int 
   }
   static int dbg = -1;           // timing experiments only (I4D_SK_DBG): 1 = no column combine, 2 = no second grid barrier, 4 = no first one
   if (dbg < 0) { const char* e = getenv("I4D_SK_DBG"); dbg = e ? atoi(e) : 0; }
-  void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
-                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct, (void*)&dbg};
+  // L2 prefetch distance in stages (cp.async.bulk.prefetch.L2 of a later stage with every shared-memory refill): 1 measured
+  // best at 8192^2 (48.8 -> 46.3 us per iteration; 2: 47.3, 3: 48.4).  I4D_SK_PF overrides, for experiments.
+  static int pf_stages = -1;
+  if (pf_stages < 0) { const char* e = getenv("I4D_SK_PF"); pf_stages = e ? atoi(e) : 1; if (pf_stages < 0 || pf_stages > 16) pf_stages = 1; }
+  void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&ld, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
+                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct, (void*)&dbg, (void*)&pf_stages};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;

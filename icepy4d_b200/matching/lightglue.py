@@ -215,7 +215,7 @@ class LightGlueB200:
                 sim = tc.similarity(X, x0.shape[0], x1.shape[0], A)
             else:
                 md0, md1 = ops.gemm_f32(x0, A["wf"], A["bf"]), ops.gemm_f32(x1, A["wf"], A["bf"])
-                sim = ops.gemm_f32(md0, md1)
+                sim = ops.gemm_f32(md0, md1, out=ops.padded_scores(md0.shape[0], md1.shape[0], md0.device))
             z0, z1 = self._lin1(x0, A["wm"], A["bm"]).contiguous(), self._lin1(x1, A["wm"], A["bm"]).contiguous()
             if collect is not None:
                 collect.append(sim)

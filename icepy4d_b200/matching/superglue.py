@@ -114,7 +114,7 @@ class SuperGlueB200:
     def scores_f32(self, d0, d1) -> torch.Tensor:
         m0 = ops.gemm_f32(d0, self.w.wf, self.w.bf)
         m1 = ops.gemm_f32(d1, self.w.wf, self.w.bf)
-        return ops.gemm_f32(m0, m1, alpha=1.0 / 16.0)
+        return ops.gemm_f32(m0, m1, alpha=1.0 / 16.0, out=ops.padded_scores(m0.shape[0], m1.shape[0], m0.device))
 
     def match(self, kpts0, sc0, desc0, shape0, kpts1, sc1, desc1, shape1, collect=None):
         """kpts [n,2], sc [n], desc [n,256] (token-major) on the device; shape = (H, W) of the image tensor.

@@ -248,19 +248,33 @@ def set_sinkhorn_mode(mode: int) -> None:
     N.call("i4d_set_sinkhorn_mode", int(mode))
 
 
+def _chk_pitched(t: torch.Tensor, name="matrix") -> int:
+    """2-D f32 CUDA matrix with unit column stride; returns its row pitch in floats (`padded_scores` makes pitched ones)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        raise ValueError(f"{name} must be a 2-D float32 CUDA tensor with unit column stride")
+    return t.stride(0)
+
+
+def padded_scores(M: int, N_: int, device) -> torch.Tensor:
+    """[M, N] f32 view of a buffer whose row pitch is N rounded up to 4 floats: every row starts 16-byte aligned, which is
+    what the fused Sinkhorn kernel (bulk row copies) and the 128-bit loads of the row/column passes need for any N."""
+    return torch.empty((M, (N_ + 3) & ~3), device=device, dtype=torch.float32)[:, :N_]
+
+
 def sinkhorn(scores: torch.Tensor, bin_score: float, iters: int, ws=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    _chk(scores)
+    """-> u [M+1], v [N+1].  For N % 4 != 0 a pitched `scores` has its pad columns overwritten (see i4d_sinkhorn)."""
+    ld = _chk_pitched(scores, "scores")
     M, N_ = scores.shape
     ws = _ws(ws, M, N_, scores.device)
     u = torch.empty(M + 1, device=scores.device, dtype=torch.float32)
-    v = torch.empty(N_ + 1, device=scores.device, dtype=torch.float32)
-    N.call("i4d_sinkhorn", scores, M, N_, float(bin_score), int(iters), u, v, ws.buf, ws.nbytes, _st())
-    return u, v
+    v = torch.empty(N_ + 4, device=scores.device, dtype=torch.float32)
+    N.call("i4d_sinkhorn", scores, M, N_, ld, float(bin_score), int(iters), u, v, ws.buf, ws.nbytes, _st())
+    return u, v[: N_ + 1]
 
 
 def sg_assign(scores: torch.Tensor, bin_score: float, iters: int, thr: float, ws=None):
     """-> matches0 [M] i32, matches1 [N] i32, mscores0 [M], mscores1 [N]"""
-    _chk(scores)
+    ld = _chk_pitched(scores, "scores")
     M, N_ = scores.shape
     ws = _ws(ws, M, N_, scores.device)
     dev = scores.device
@@ -269,14 +283,14 @@ def sg_assign(scores: torch.Tensor, bin_score: float, iters: int, thr: float, ws
     s0 = torch.empty(M, device=dev, dtype=torch.float32)
     s1 = torch.empty(N_, device=dev, dtype=torch.float32)
     u = torch.empty(M + 1, device=dev, dtype=torch.float32)
-    v = torch.empty(N_ + 1, device=dev, dtype=torch.float32)
-    N.call("i4d_sg_assign", scores, M, N_, float(bin_score), int(iters), float(thr), m0, m1, s0, s1, u, v, ws.buf,
+    v = torch.empty(N_ + 4, device=dev, dtype=torch.float32)
+    N.call("i4d_sg_assign", scores, M, N_, ld, float(bin_score), int(iters), float(thr), m0, m1, s0, s1, u, v, ws.buf,
            ws.nbytes, _st())
     return m0, m1, s0, s1
 
 
 def lg_assign(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor, thr: float, ws=None):
-    _chk(sim)
+    ld = _chk_pitched(sim, "sim")
     M, N_ = sim.shape
     ws = _ws(ws, M, N_, sim.device)
     dev = sim.device
@@ -284,7 +298,7 @@ def lg_assign(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor, thr: float,
     m1 = torch.empty(N_, device=dev, dtype=torch.int32)
     s0 = torch.empty(M, device=dev, dtype=torch.float32)
     s1 = torch.empty(N_, device=dev, dtype=torch.float32)
-    N.call("i4d_lg_assign", sim, M, N_, _chk(z0.reshape(-1)), _chk(z1.reshape(-1)), float(thr), m0, m1, s0, s1, ws.buf,
+    N.call("i4d_lg_assign", sim, M, N_, ld, _chk(z0.reshape(-1)), _chk(z1.reshape(-1)), float(thr), m0, m1, s0, s1, ws.buf,
            ws.nbytes, _st())
     return m0, m1, s0, s1
 

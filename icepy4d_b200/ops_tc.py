@@ -134,7 +134,7 @@ class SuperGlueTensorCore:
         b = self._buffers(nt)
         b["x32"][:n0] = d0
         b["x32"][n0:] = d1
-        scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
+        scores = ops.padded_scores(n0, n1, self.dev)
         return self._schedule(b, n0, n1, scores, collect)
 
     # -- CUDA-graph replay of the schedule (75 launches per tile pair): one graph per (n0, n1), static buffers, the caller's
@@ -155,7 +155,7 @@ class SuperGlueTensorCore:
         try:
             if ent == "seen":
                 b = self._alloc(n0 + n1)
-                scores = torch.empty((n0, n1), device=self.dev, dtype=torch.float32)
+                scores = ops.padded_scores(n0, n1, self.dev)
                 launches0 = N.LAUNCHES
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -244,6 +244,6 @@ class LightGlueTensorCore:
         b = self.buffers(nt)
         md = b["md"][:nt]
         gemm_tc(b["x16"][:nt, :256], self._w(A["wf"]), A["bf"], out16=md)
-        sim = torch.empty((m, n), device=X.device, dtype=torch.float32)
+        sim = ops.padded_scores(m, n, X.device)
         gemm_tc(md[:m], md[m:], out32=sim)
         return sim

@@ -136,20 +136,27 @@ size_t i4d_assignment_workspace_bytes(int M, int N);
 int i4d_row_lse(const float* S, int M, int N, float scale, const float* coloff, float* out, void* stream);
 int i4d_col_lse(const float* S, int M, int N, float scale, const float* rowoff, float* out, void* workspace,
                 size_t workspace_bytes, void* stream);
-/* superglue.py:152-186 — log-domain Sinkhorn potentials u[M+1], v[N+1] of the dustbin-augmented problem. */
-int i4d_sinkhorn(const float* scores, int M, int N, float bin_score, int iters, float* u, float* v, void* workspace,
+/* superglue.py:152-186 — log-domain Sinkhorn potentials u[M+1], v[N+1] of the dustbin-augmented problem.
+ * scores [M, N] row-major with a row pitch of `ld` floats (ld >= N).  Buffers: u holds M + 1 floats, v must have room for
+ * N + 4 floats (entries past v[N] are scratch).  When ld is a multiple of 4 that covers N rounded up to 4 (and `scores` is
+ * 16-byte aligned) any 64 <= N <= 8192 takes the fused kernel; for N % 4 != 0 it OVERWRITES the pad columns
+ * scores[:, N .. round_up(N, 4)) with -1e30.  Other shapes run the two-pass row/column kernels. */
+int i4d_sinkhorn(float* scores, int M, int N, int ld, float bin_score, int iters, float* u, float* v, void* workspace,
                  size_t workspace_bytes, void* stream);
 /* Sinkhorn implementation switch (tests / comparisons): 0 = fused persistent kernel (one HBM read of the score matrix
- * per iteration; used when N % 4 == 0 and 64 <= N <= 8192), 1 = always the two-pass row/column kernels. */
+ * per iteration; see i4d_sinkhorn for the shapes it takes), 1 = always the two-pass row/column kernels, 2 = fused kernel
+ * with running maxima in every iteration. */
 int i4d_set_sinkhorn_mode(int mode);
 /* superglue.py:152-186 + :288-298 — Sinkhorn, then mutual nearest neighbours with threshold.
- * matches0 [M] / matches1 [N] int32 (-1 = unmatched), mscores0/1 f32; u [M+1], v [N+1] scratch/outputs. */
-int i4d_sg_assign(const float* scores, int M, int N, float bin_score, int iters, float match_threshold,
+ * matches0 [M] / matches1 [N] int32 (-1 = unmatched), mscores0/1 f32; u [M+1], v [N+4] scratch/outputs; `ld` and the pad
+ * columns as for i4d_sinkhorn. */
+int i4d_sg_assign(float* scores, int M, int N, int ld, float bin_score, int iters, float match_threshold,
                   int* matches0, int* matches1, float* mscores0, float* mscores1, float* u, float* v,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* lightglue.py:253-266 + :290-306 — sigmoid/log double softmax + mutual NN with threshold, from sim [M,N] and
- * matchability logits z0 [M], z1 [N].  The (M+1)x(N+1) log-assignment matrix is never written. */
-int i4d_lg_assign(const float* sim, int M, int N, const float* z0, const float* z1, float filter_threshold,
+ * matchability logits z0 [M], z1 [N]; sim has a row pitch of `ld` floats (128-bit loads when ld % 4 == 0).  The
+ * (M+1)x(N+1) log-assignment matrix is never written. */
+int i4d_lg_assign(const float* sim, int M, int N, int ld, const float* z0, const float* z1, float filter_threshold,
                   int* matches0, int* matches1, float* mscores0, float* mscores1, void* workspace,
                   size_t workspace_bytes, void* stream);
 

@@ -6,8 +6,10 @@ from icepy4d_b200 import ops
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-S = torch.randn(N, N, device="cuda") * 3
-ws = ops.AssignWorkspace(N, N, S.device)
+M = int(sys.argv[3]) if len(sys.argv) > 3 else N          # rows (keypoints of image 0); N = columns
+S = ops.padded_scores(M, N, "cuda")
+S.copy_(torch.randn(M, N, device="cuda") * 3)
+ws = ops.AssignWorkspace(M, N, S.device)
 for mode in (0, 2):
     ops.set_sinkhorn_mode(mode)
     for _ in range(2):
@@ -20,6 +22,6 @@ for mode in (0, 2):
         ops.sinkhorn(S, 1.0, iters, ws)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"mode {mode}: {ms:.3f} ms / {iters} iterations = {ms / iters * 1e3:.2f} us/iter, "
-          f"{2 * N * N * 4 * iters / ms / 1e6:.0f} GB/s algorithmic, {N * N * 4 * iters / ms / 1e6:.0f} GB/s single-read")
+    print(f"{M}x{N} mode {mode}: {ms:.3f} ms / {iters} iterations = {ms / iters * 1e3:.2f} us/iter, "
+          f"{2 * M * N * 4 * iters / ms / 1e6:.0f} GB/s algorithmic, {M * N * 4 * iters / ms / 1e6:.0f} GB/s single-read")
 ops.set_sinkhorn_mode(0)

@@ -223,6 +223,44 @@ def test_sinkhorn_fused_vs_two_pass_large(ops, M, N, iters):
         assert torch.allclose(m0[2], m1[2], atol=1e-3)
 
 
+def _pitched(ops, S):
+    P = ops.padded_scores(S.shape[0], S.shape[1], "cuda")
+    P.copy_(S)
+    return P
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("M,N,iters", [(301, 301, 25), (513, 1023, 30), (700, 8189, 6), (2047, 4097, 12), (64, 66, 5)])
+def test_sinkhorn_ragged_n_takes_the_fused_kernel(ops, M, N, iters, mode):
+    """Real tiles have arbitrary keypoint counts.  With a pitched score matrix (row pitch = N rounded up to 4 floats, what
+    the matchers allocate) N % 4 != 0 runs the fused kernel (pad columns set to -1e30 by the launcher): same potentials and
+    matches as the CPU oracle (superglue.py:152-186, :288-298), and exactly one cooperative launch + the pad fill."""
+    from icepy4d_b200 import _native
+    gen = torch.Generator().manual_seed(M * 11 + N)
+    S = torch.randn(M, N, generator=gen) * 3
+    for i in range(0, min(M, N), 2):
+        S[i, (i * 7) % N] += 25.0
+    P = sg_oracle.log_optimal_transport(S, torch.tensor(1.0), iters)
+    r0, r1, rs0, rs1 = sg_oracle.mutual_nn(P, 0.2)
+    ops.set_sinkhorn_mode(mode)
+    try:
+        Sp = _pitched(ops, S)
+        assert Sp.stride(0) % 4 == 0 and Sp.stride(0) >= N
+        n0 = _native.LAUNCHES
+        u, v = ops.sinkhorn(Sp, 1.0, iters)
+        assert _native.LAUNCHES - n0 == (2 if N % 4 else 1)
+        assert u.shape == (M + 1,) and v.shape == (N + 1,)
+        m0, m1, s0, s1 = (t.cpu() for t in ops.sg_assign(_pitched(ops, S), 1.0, iters, 0.2))
+    finally:
+        ops.set_sinkhorn_mode(0)
+    Z = torch.full((M + 1, N + 1), 1.0)
+    Z[:M, :N] = S
+    Pg = Z + u.cpu()[:, None] + v.cpu()[None, :] + np.log(M + N)
+    assert torch.allclose(Pg, P, atol=2e-3)
+    assert torch.equal(m0.long(), r0) and torch.equal(m1.long(), r1)
+    assert torch.allclose(s0, rs0, atol=1e-3) and torch.allclose(s1, rs1, atol=1e-3)
+
+
 def test_sinkhorn_fast_mode_restart(ops):
     """Potentials that jump by hundreds of nats between iterations underflow the a-priori stabilisers: the fused kernel
     must notice, restart in exact mode on the device and still agree with the two-pass kernels."""
@@ -241,7 +279,7 @@ def test_sinkhorn_fast_mode_restart(ops):
     assert float((u0 - u1).abs().max()) < 5e-2 and float((v0 - v1).abs().max()) < 5e-2
 
 
-@pytest.mark.parametrize("M,N", [(3, 5), (256, 200), (700, 513)])
+@pytest.mark.parametrize("M,N", [(3, 5), (256, 200), (700, 513), (1030, 2051)])
 def test_lg_assign(ops, M, N):
     gen = torch.Generator().manual_seed(M * 5 + N)
     sim = torch.randn(M, N, generator=gen) * 2
@@ -252,9 +290,10 @@ def test_lg_assign(ops, M, N):
     P = sim.new_zeros(M + 1, N + 1)
     P[:M, :N] = F.log_softmax(sim, 1) + F.log_softmax(sim, 0) + F.logsigmoid(z0) + F.logsigmoid(z1).t()
     r0, r1, rs0, rs1 = sg_oracle.mutual_nn(P, 0.1)
-    m0, m1, s0, s1 = (t.cpu() for t in ops.lg_assign(sim.cuda(), z0.cuda(), z1.cuda(), 0.1))
-    assert torch.equal(m0.long(), r0) and torch.equal(m1.long(), r1)
-    assert torch.allclose(s0, rs0, atol=1e-4) and torch.allclose(s1, rs1, atol=1e-4)
+    for dev_sim in (sim.cuda(), _pitched(ops, sim)):           # contiguous (scalar tail) and pitched (128-bit loads) layouts
+        m0, m1, s0, s1 = (t.cpu() for t in ops.lg_assign(dev_sim, z0.cuda(), z1.cuda(), 0.1))
+        assert torch.equal(m0.long(), r0) and torch.equal(m1.long(), r1)
+        assert torch.allclose(s0, rs0, atol=1e-4) and torch.allclose(s1, rs1, atol=1e-4)
 
 
 # ------------------------------------------------------------------ geometry
