@@ -486,9 +486,10 @@ struct SkCtx {
   const float* S; float* stage_buf; uint64_t* full; uint64_t* bpart;
   float (*part_m)[SK_ROWS][SK_WARPS]; float (*part_s)[SK_ROWS][SK_WARPS];
   float* u; const float* v; float* pm; float* ps; int* flag;
+  float* unew_s;         // this iteration's u of the band, log2 domain (shared memory; the next iteration's uold_s)
   int M, N, NP, ld, n4, row0, row1, nst, cta, keep_rows, pf, tid, warp, lane; uint32_t total;   // NP = 4 * n4: N rounded up to whole float4 groups
   float norm, c_mu, c_nu, extra_row, kfac;
-  const float* uold_s;   // previous-iteration u of this CTA's band, pre-scaled by log2(e) (shared memory)
+  const float* uold_s;   // previous-iteration u of this CTA's band, log2 domain (shared memory)
   uint32_t row_bytes;
 };
 // ring / barrier phase bookkeeping carried across stages, bands and iterations (one copy per thread, all identical)
@@ -634,7 +635,8 @@ __device__ __forceinline__ void sk_band_exact(const SkCtx& c, SkRing& rg, const 
 // checks the sums and refills the shared-memory buffer the stage has released; nobody waits for it.
 template <bool FULL>
 __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t seq, uint32_t fq, SkRing& rg,
-                                             const float (&e)[SK_ROWS][SK_GROUPS][4], float2 (&cs)[SK_GROUPS][2]) {
+                                             const float (&e)[SK_ROWS][SK_GROUPS][4], float2 (&cs)[SK_GROUPS][2], float& csN,
+                                             bool refill = true) {
   const int warp = c.warp, lane = c.lane;
   const uint32_t pp = fq & 1u, slot = fq & 3u;
   const int row = lane >> 4;
@@ -649,6 +651,7 @@ __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t s
   for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   const float sm = t + ex;
   const float a = valid ? __fdividef(c.kfac, sm) : 0.f;
+  csN = fmaf(ex, a, csN);                                           // dustbin column (every lane; lanes 0 / 16 of warp 0 are read)
   const float a0 = __shfl_sync(0xffffffffu, a, 0), a1 = __shfl_sync(0xffffffffu, a, 16);
   const float2 a0v = make_float2(a0, a0), a1v = make_float2(a1, a1);
 #pragma unroll
@@ -662,10 +665,12 @@ __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t s
     cs[g][1] = __ffma2_rn(make_float2(e[1][g][2], e[1][g][3]), a1v, cs[g][1]);
   }
   if (warp == (int)(fq & (SK_WARPS - 1))) {                                               // duty: off everybody's critical path
-    if (lane == 0 && seq + SK_STAGES < rg.total) sk_issue(c, seq + SK_STAGES);
+    if (refill && lane == 0 && seq + SK_STAGES < rg.total) sk_issue(c, seq + SK_STAGES);
     if ((lane & 15) == 0 && valid) {
       if (!(sm > 0.f && sm < INFINITY)) atomicExch(c.flag, 1);
-      c.u[c.row0 + idx * SK_ROWS + row] = c.norm - (mr + __log2f(sm)) * LN2;
+      const float ul = c.norm * LOG2E - (mr + __log2f(sm));
+      c.unew_s[idx * SK_ROWS + row] = ul;
+      c.u[c.row0 + idx * SK_ROWS + row] = ul * LN2;
     }
   }
 }
@@ -675,7 +680,7 @@ __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t s
 // FULL = both rows exist and every thread owns SK_GROUPS complete float4 column groups (N == SK_MAXN).
 template <bool FULL, bool HAVE_PREV, bool PREV_FULL>
 __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_prev, SkRing& rg,
-                                              const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2],
+                                              const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2], float& csN,
                                               float (&e_cur)[SK_ROWS][SK_GROUPS][4], const float (&e_prev)[SK_ROWS][SK_GROUPS][4]) {
   const int tid = c.tid, warp = c.warp, lane = c.lane;
   const int N = c.NP, n4 = c.n4;
@@ -720,22 +725,21 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
   if ((lane & 15) == 0) c.part_s[slot][lane >> 4][warp] = keep;
   __syncwarp();
   if (lane == 0) sk_mbar_arrive(&c.bpart[pp]);                       // release: this warp's partials, and its reads of the buffer
-  if (HAVE_PREV) sk_col_accum<PREV_FULL>(c, idx_prev, rg.seq - 1, rg.fq - 1, rg, e_prev, cs);
+  if (HAVE_PREV) sk_col_accum<PREV_FULL>(c, idx_prev, rg.seq - 1, rg.fq - 1, rg, e_prev, cs, csN);
   rg.advance();
   ++rg.fq;
 }
 
-__device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const float4 (&vraw)[SK_GROUPS]) {
-  const int tid = threadIdx.x;
-  const int N = c.NP, n4 = c.n4, nst = c.nst;
-  float2 vl[SK_GROUPS][2];                                         // old v of my columns, log2 domain
-  float2 cs[SK_GROUPS][2];                                         // column sums relative to the stabiliser m_j = c_mu - v_j
+// One pass over the band with the potentials vl (log2 domain) of this thread's columns.  Results stay in registers: cs = column
+// sums relative to the stabiliser m_j = c_mu - v_j, csN = the dustbin column's (valid in lanes 0 / 16 of warp 0: rows 0 / 1 of
+// every stage).  The shared-memory buffer of the band's LAST stage is not refilled here: the caller stages the reduction of the
+// column sums through it and refills it afterwards (stage rg.seq - 1 + SK_STAGES).
+__device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2],
+                                             float& csN) {
+  const int n4 = c.n4, nst = c.nst;
 #pragma unroll
-  for (int g = 0; g < SK_GROUPS; ++g) {
-    const float4 t = vraw[g];
-    vl[g][0] = make_float2(t.x * LOG2E, t.y * LOG2E); vl[g][1] = make_float2(t.z * LOG2E, t.w * LOG2E);
-    cs[g][0] = cs[g][1] = make_float2(0.f, 0.f);
-  }
+  for (int g = 0; g < SK_GROUPS; ++g) cs[g][0] = cs[g][1] = make_float2(0.f, 0.f);
+  csN = 0.f;
   const bool rev = ((rg.seq / (uint32_t)nst) & 1u) != 0;
   // everything but (possibly) the band's last row block is complete: the ragged block — the first stage of a backward
   // pass, the last of a forward one — takes the predicated instantiation
@@ -748,13 +752,13 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
   {                                                                                                          \
     const int i_ = SK_IDX(st), ip_ = SK_IDX((st) - 1);                                                       \
     const bool f_ = SK_ISFULL(i_), fp_ = SK_ISFULL(ip_);                                                     \
-    if (f_ && fp_) sk_stage_fast<true, true, true>(c, i_, ip_, rg, vl, cs, cur, prev);                      \
-    else if (f_) sk_stage_fast<true, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                       \
-    else sk_stage_fast<false, true, false>(c, i_, ip_, rg, vl, cs, cur, prev);                              \
+    if (f_ && fp_) sk_stage_fast<true, true, true>(c, i_, ip_, rg, vl, cs, csN, cur, prev);                 \
+    else if (f_) sk_stage_fast<true, true, false>(c, i_, ip_, rg, vl, cs, csN, cur, prev);                  \
+    else sk_stage_fast<false, true, false>(c, i_, ip_, rg, vl, cs, csN, cur, prev);                         \
   }
   int st = 1;
-  if (SK_ISFULL(SK_IDX(0))) sk_stage_fast<true, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
-  else sk_stage_fast<false, false, false>(c, SK_IDX(0), 0, rg, vl, cs, eA, eB);
+  if (SK_ISFULL(SK_IDX(0))) sk_stage_fast<true, false, false>(c, SK_IDX(0), 0, rg, vl, cs, csN, eA, eB);
+  else sk_stage_fast<false, false, false>(c, SK_IDX(0), 0, rg, vl, cs, csN, eA, eB);
 #pragma unroll 1
   for (; st + 1 < nst; st += 2) {
     SK_STAGE(st, eB, eA);
@@ -762,30 +766,25 @@ __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const f
   }
   if (st < nst) {
     SK_STAGE(st, eB, eA);
-    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eB, cs);
+    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eB, cs, csN, false);
   } else {
-    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eA, cs);
+    sk_col_accum<false>(c, SK_IDX(nst - 1), rg.seq - 1, rg.fq - 1, rg, eA, cs, csN, false);
   }
 #undef SK_STAGE
 #undef SK_ISFULL
 #undef SK_IDX
-  // ---- column partials of this CTA ----
-#pragma unroll
-  for (int g = 0; g < SK_GROUPS; ++g) {
-    const int gi = g * SK_THREADS + tid;
-    if (gi < n4) reinterpret_cast<float4*>(c.ps + (size_t)c.cta * N)[gi] = make_float4(cs[g][0].x, cs[g][0].y, cs[g][1].x, cs[g][1].y);
-  }
 }
 
 __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const float* __restrict__ S, int M, int N, int ld, float alpha,
                                                                        int iters, float* u, float* v, float* pm, float* ps,
-                                                                       int* flag, int rows_per_cta, int allow_fast, int keep_pct, int dbg, int pf_stages) {
+                                                                       int* flag, unsigned long long* acc_base, int fx_shift, int rows_per_cta, int allow_fast,
+                                                                       int keep_pct, int pf_stages) {
   extern __shared__ __align__(128) unsigned char sk_smem[];
   float* stage_buf = reinterpret_cast<float*>(sk_smem);                         // [SK_STAGES][SK_ROWS][N]
   __shared__ __align__(8) uint64_t full[SK_STAGES], bpart[2];
   __shared__ __align__(8) float part_m[2][SK_ROWS][SK_WARPS], part_s[4][SK_ROWS][SK_WARPS];
   __shared__ float red_m[SK_WARPS], red_s[SK_WARPS];
-  __shared__ __align__(8) float uold_s[SK_MAX_BAND];
+  __shared__ __align__(8) float uold_s[2][SK_MAX_BAND];           // u of the band, log2 domain: previous / this iteration
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int row0 = min(M, cta * rows_per_cta), row1 = min(M, row0 + rows_per_cta);
@@ -806,7 +805,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.bpart = bpart;
   ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
   ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.NP = NP; ctx.ld = ld; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
-  ctx.uold_s = uold_s;
+  ctx.uold_s = uold_s[0]; ctx.unew_s = uold_s[1];
   ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)NP * 4u;
   ctx.keep_rows = (row1 - row0) * keep_pct / 100;
   ctx.tid = tid; ctx.warp = warp; ctx.lane = lane;
@@ -840,9 +839,150 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
     __syncthreads();
   };
 
+  // ---- state of the fast iterations (registers / shared memory, never through HBM) ----
+  float2 vl[SK_GROUPS][2];               // v of my 16 columns, log2 domain
+  float vN_l = 0.f, uM_l = 0.f;          // dustbin column / dustbin row potentials, log2 domain
+  bool v_regs = false;                   // vl / vN_l / uM_l / uold are current (else: reload from u, v in global memory)
+  uint32_t fit = 0;                      // fast iterations so far: sums of iteration f go through acc[f % 3]
+  float* uold = uold_s[0];
+  float* unew = uold_s[1];
+  const float alpha_l = alpha * LOG2E, norm_l = norm * LOG2E;
+  const float fx_up = __int_as_float((127 + fx_shift) << 23), fx_dn = __int_as_float((127 - fx_shift) << 23);   // 2^shift, 2^-shift
+  const size_t acc_stride = (size_t)NP + 2;                           // u64 per accumulation buffer: NP columns, [NP] = dustbin column
+
   for (int it = 0; it < iters; ++it) {
     const bool fast = fast_ok && it >= SK_EXACT_ITERS;
-    // all the loads of the prologue are in flight together: v of my columns, the dustbin term, the band's previous u
+    if (fast) {
+      // ================= fast iteration: ONE grid barrier =================
+      // Column sums leave the CTA as 64-bit fixed-point numbers and are added up by the L2 (one bulk reduction per CTA): integer
+      // addition is associative, so the result does not depend on the order in which the CTAs arrive (bit-reproducible), and
+      // after the barrier EVERY CTA derives the new v of its threads' columns itself — no combine phase, no second barrier.
+      float uM_prev;
+      if (!v_regs) {
+        // first fast iteration (or after exact ones): potentials come from global memory
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          const int gi = g * SK_THREADS + tid;
+          const float4 t = (gi < n4) ? __ldcg(reinterpret_cast<const float4*>(v) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vl[g][0] = make_float2(t.x * LOG2E, t.y * LOG2E); vl[g][1] = make_float2(t.z * LOG2E, t.w * LOG2E);
+        }
+        vN_l = __ldcg(v + N) * LOG2E;
+        uM_prev = __ldcg(u + M) * LOG2E;
+        for (int i = tid; i < row1 - row0; i += SK_THREADS) uold[i] = __ldcg(u + row0 + i) * LOG2E;
+      } else {
+        uM_prev = uM_l;
+      }
+      // dustbin row: u_M = log_mu_last - LSE_{j <= N}(alpha + v_j).  alpha + v_j <= m_M = c_nu - u_M(previous) (same a-priori
+      // bound as for the other rows), so plain sums of 2^(alpha + v_j - m_M) are safe; every CTA computes it (same order: same bits)
+      const float m_M = c_nu - uM_prev;
+      {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          const int j = (g * SK_THREADS + tid) * 4;
+          if (j + 0 < N) t += sk_ex2(alpha_l + vl[g][0].x - m_M);
+          if (j + 1 < N) t += sk_ex2(alpha_l + vl[g][0].y - m_M);
+          if (j + 2 < N) t += sk_ex2(alpha_l + vl[g][1].x - m_M);
+          if (j + 3 < N) t += sk_ex2(alpha_l + vl[g][1].y - m_M);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) red_s[warp] = t;
+      }
+      ctx.extra_row = alpha_l + vN_l;                                 // dustbin column term of every row sum
+      ctx.uold_s = uold; ctx.unew_s = unew;
+      __syncthreads();
+      bool bad = false;
+      {
+        float t = sk_ex2(alpha_l + vN_l - m_M);
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) t += red_s[w];
+        bad = !(t > 0.f && t < INFINITY);
+        uM_l = log_mu_last * LOG2E - (m_M + __log2f(t));
+      }
+      float2 cs[SK_GROUPS][2];
+      float csN;
+      sk_band_fast(ctx, rg, vl, cs, csN);
+      // ---- column sums -> fixed point -> the shared-memory buffer of the band's last stage (free: every warp has passed the wait
+      //      for that stage's partials, i.e. every warp has taken its elements out of it) -> one bulk reduction into acc ----
+      unsigned long long* acc = acc_base + (size_t)(fit % 3u) * acc_stride;
+      {
+        const uint32_t last_buf = (rg.buf == 0 ? SK_STAGES : rg.buf) - 1u;
+        ulonglong2* stg = reinterpret_cast<ulonglong2*>(stage_buf + (size_t)last_buf * SK_ROWS * NP);
+#pragma unroll
+        for (int g = 0; g < SK_GROUPS; ++g) {
+          const int gi = g * SK_THREADS + tid;
+          if (gi < n4) {
+            stg[2 * gi] = make_ulonglong2(__float2ull_rn(cs[g][0].x * fx_up), __float2ull_rn(cs[g][0].y * fx_up));
+            stg[2 * gi + 1] = make_ulonglong2(__float2ull_rn(cs[g][1].x * fx_up), __float2ull_rn(cs[g][1].y * fx_up));
+          }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");             // my generic-proxy writes (shared and global) before the bulk engine's
+        const float csN1 = __shfl_sync(0xffffffffu, csN, 16);
+        __syncthreads();
+        if (tid == 0) {
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
+                       ::"l"(acc), "r"((uint32_t)__cvta_generic_to_shared(stg)), "r"((uint32_t)NP * 8u) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          atomicAdd(acc + NP, __float2ull_rn((csN + csN1) * fx_up));  // dustbin column: one more 64-bit integer add
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer read: hand it back to the ring
+          if (rg.seq - 1u + SK_STAGES < rg.total) sk_issue(ctx, rg.seq - 1u + SK_STAGES);
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the reduction is performed before this CTA arrives
+        }
+      }
+      grid_barrier();
+      // ---- every CTA: new v of my columns from the reduced sums; recycle the buffer of two iterations ago ----
+      {
+        unsigned long long* old = acc_base + (size_t)((fit + 2u) % 3u) * acc_stride;
+        for (size_t i = (size_t)cta * SK_THREADS + tid; i < acc_stride; i += (size_t)G * SK_THREADS) old[i] = 0ull;
+      }
+      const float extra_col = alpha_l + uM_l;
+#pragma unroll
+      for (int g = 0; g < SK_GROUPS; ++g) {
+        const int gi = g * SK_THREADS + tid;
+        if (gi < n4) {
+          const ulonglong2 s01 = __ldcg(reinterpret_cast<const ulonglong2*>(acc) + 2 * gi);
+          const ulonglong2 s23 = __ldcg(reinterpret_cast<const ulonglong2*>(acc) + 2 * gi + 1);
+          const float fs[4] = {__ull2float_rn(s01.x) * fx_dn, __ull2float_rn(s01.y) * fx_dn, __ull2float_rn(s23.x) * fx_dn,
+                               __ull2float_rn(s23.y) * fx_dn};
+          float vo[4] = {vl[g][0].x, vl[g][0].y, vl[g][1].x, vl[g][1].y};
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float mj = c_mu - vo[cc];                            // the stabiliser used in the band (old v)
+            const float sj = fs[cc] + sk_ex2(extra_col - mj);          // + dustbin row
+            if (gi * 4 + cc < N && !(sj > 0.f && sj < INFINITY)) bad = true;
+            vo[cc] = norm_l - (mj + __log2f(sj));
+          }
+          vl[g][0] = make_float2(vo[0], vo[1]); vl[g][1] = make_float2(vo[2], vo[3]);
+        }
+      }
+      {
+        const float mN = c_mu - vN_l;
+        const float sN = __ull2float_rn(__ldcg(acc + NP)) * fx_dn + sk_ex2(extra_col - mN);
+        if (!(sN > 0.f && sN < INFINITY)) bad = true;
+        vN_l = log_nu_last * LOG2E - (mN + __log2f(sN));
+      }
+      { float* t = uold; uold = unew; unew = t; }
+      v_regs = true;
+      ++fit;
+      if (__syncthreads_or((bad || __ldcg(flag) != 0) ? 1 : 0)) {
+        // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode.  Every
+        // CTA sees the same sums and the same flag, so all of them take this branch together.
+        fast_ok = false; v_regs = false;
+        for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
+        for (int i = cta * SK_THREADS + tid; i <= M; i += G * SK_THREADS) u[i] = 0.f;
+        const uint32_t old_total = rg.total;
+        rg.total = rg.seq + (uint32_t)iters * (uint32_t)nst;
+        ctx.total = rg.total;
+        if (tid == 0)      // stages below min(old_total, seq + SK_STAGES) are already in flight
+          for (uint32_t sq = min(old_total, rg.seq + SK_STAGES); sq < rg.total && sq < rg.seq + SK_STAGES; ++sq) sk_issue(ctx, sq);
+        it = -1;
+        grid_barrier();
+      }
+      continue;
+    }
+    // ================= exact iteration: running maxima, column partials in global memory, two grid barriers =================
+    v_regs = false;
     float4 vraw[SK_GROUPS];
 #pragma unroll
     for (int g = 0; g < SK_GROUPS; ++g) {
@@ -850,7 +990,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       vraw[g] = (gi < n4) ? __ldcg(reinterpret_cast<const float4*>(v) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     ctx.extra_row = (alpha + __ldcg(v + N)) * LOG2E;                  // dustbin column term of every row LSE (old v)
-    for (int i = tid; i < row1 - row0; i += SK_THREADS) uold_s[i] = __ldcg(u + row0 + i) * LOG2E;
     // dustbin row: u[M] = log_mu_last - LSE_j(alpha + v_j), j in [0, N]   (last CTA: its band is the short one)
     if (cta == G - 1) {
       L2Acc a; a.init();
@@ -872,52 +1011,25 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
     }
     __syncthreads();
-    if (fast) sk_band_fast(ctx, rg, vraw);
-    else sk_band_exact(ctx, rg, vraw);
-    if (!(dbg & 4)) grid_barrier(); else __syncthreads();
+    sk_band_exact(ctx, rg, vraw);
+    grid_barrier();
     // ---- combine: v_j = log_nu_j - LSE_i(S_ij + u_i) incl. the dustbin row; v[N] from all u ----
     {
       const float extra_col = (alpha + __ldcg(u + M)) * LOG2E;
-      // one warp per 4-column tile: lane l sums the partials of CTAs l, l + 32, ... for all four columns (independent 16-byte
-      // loads), a butterfly over the lanes finishes the sums and lanes 0..3 each finalise one column.
-      for (int tile = cta * SK_WARPS + warp; tile < ((dbg & 1) ? 0 : n4); tile += G * SK_WARPS) {
-        if (fast) {
-          float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-          for (int c = lane; c < G; c += 32) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(ps + (size_t)c * NP) + tile);
-            sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
-            sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
-          }
-          if (lane < 4 && tile * 4 + lane < N) {
-            const int j = tile * 4 + lane;
-            float sj = lane == 0 ? sm.x : lane == 1 ? sm.y : lane == 2 ? sm.z : sm.w;
-            const float mj = c_mu - __ldcg(v + j) * LOG2E;            // the stabiliser used above (old v)
-            sj += sk_ex2(extra_col - mj);
-            if (!(sj > 0.f && sj < INFINITY)) atomicExch(flag, 1);
-            v[j] = norm - (mj + __log2f(sj)) * LN2;
-          }
-        } else {
-          // lane = 4 * sub + column: 8 lanes share a column
-          const int sub = lane >> 2, j = tile * 4 + (lane & 3);
-          L2Acc a; a.init();
+      // one warp per 4-column tile, lane = 4 * sub + column: 8 lanes share a column
+      for (int tile = cta * SK_WARPS + warp; tile < n4; tile += G * SK_WARPS) {
+        const int sub = lane >> 2, j = tile * 4 + (lane & 3);
+        L2Acc a; a.init();
 #pragma unroll 2
-          for (int c = sub; c < G; c += 8) a.merge(__ldcg(pm + (size_t)c * NP + j), __ldcg(ps + (size_t)c * NP + j));
+        for (int c = sub; c < G; c += 8) a.merge(__ldcg(pm + (size_t)c * NP + j), __ldcg(ps + (size_t)c * NP + j));
 #pragma unroll
-          for (int o = 4; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
-          if (sub == 0 && j < N) {
-            a.add(extra_col);
-            v[j] = norm - a.lse_ln();
-          }
+        for (int o = 4; o < 32; o <<= 1) a.merge(__shfl_xor_sync(0xffffffffu, a.m, o), __shfl_xor_sync(0xffffffffu, a.s, o));
+        if (sub == 0 && j < N) {
+          a.add(extra_col);
+          v[j] = norm - a.lse_ln();
         }
       }
       if (cta == G - 1) {                                             // v[N] = log_nu_last - LSE_{i <= M}(alpha + u_i)
-        // (the last CTA owns the short band and no column tile at N = 8192: this reduction is off the other CTAs' critical
-        // path as long as it is one L2 round trip — all loads first, then the dependent accumulation)
         L2Acc a; a.init();
         for (int i0 = tid; i0 <= M; i0 += 16 * SK_THREADS) {
           float uu[16];
@@ -939,20 +1051,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
         }
       }
     }
-    if (!(dbg & 2)) grid_barrier(); else __syncthreads();
-    if (fast_ok && __ldcg(flag) != 0 && !(dbg & 7)) {
-      // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode
-      fast_ok = false;
-      for (int j = cta * SK_THREADS + tid; j <= N; j += G * SK_THREADS) v[j] = 0.f;
-      for (int i = cta * SK_THREADS + tid; i <= M; i += G * SK_THREADS) u[i] = 0.f;
-      const uint32_t old_total = rg.total;
-      rg.total = rg.seq + (uint32_t)iters * (uint32_t)nst;
-      ctx.total = rg.total;
-      if (tid == 0)      // stages below min(old_total, seq + SK_STAGES) are already in flight
-        for (uint32_t s = min(old_total, rg.seq + SK_STAGES); s < rg.total && s < rg.seq + SK_STAGES; ++s) sk_issue(ctx, s);
-      it = -1;
-      grid_barrier();
+    grid_barrier();
+  }
+  // the potentials of the last fast iteration are still in registers: CTA 0 writes them out (u_i, i < M, went out row by row)
+  if (v_regs && cta == 0) {
+#pragma unroll
+    for (int g = 0; g < SK_GROUPS; ++g) {
+      const int j = (g * SK_THREADS + tid) * 4;
+      if (j + 0 < N) v[j + 0] = vl[g][0].x * LN2;
+      if (j + 1 < N) v[j + 1] = vl[g][0].y * LN2;
+      if (j + 2 < N) v[j + 2] = vl[g][1].x * LN2;
+      if (j + 3 < N) v[j + 3] = vl[g][1].y * LN2;
     }
+    if (tid == 0) { v[N] = vN_l * LN2; u[M] = uM_l * LN2; }
   }
 }
 
@@ -999,6 +1110,13 @@ static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, in
   float* pm = w.pm; float* ps = w.ps;
   int* flag = w.pi;
   cudaMemsetAsync(flag, 0, 2 * sizeof(int), st);   // [0] fast-mode trip flag, [1] grid-barrier arrival counter
+  // three rotating accumulation buffers of (NP + 2) 64-bit fixed-point column sums (the argmax-index partials of the workspace
+  // are free during the solve).  Column sums relative to their stabilisers are bounded by M / N (total row mass over the
+  // largest column marginal): scale 2^shift with (M / N) * 2^shift < 2^62.
+  unsigned long long* acc_base = reinterpret_cast<unsigned long long*>(w.pi + 4);   // (the first 16 bytes hold flag / barrier counter)
+  cudaMemsetAsync(acc_base, 0, 3 * ((size_t)NP + 2) * sizeof(unsigned long long), st);
+  int fx_shift = 61;
+  for (long long r = 1; r * (long long)N < (long long)M; r *= 2) --fx_shift;
   int allow_fast = g_sinkhorn_fast;
   static int keep_pct = -1;      // share of every band pinned in L2 with evict_last (I4D_SK_KEEP_PCT overrides, for experiments)
   if (keep_pct < 0) {
@@ -1006,14 +1124,12 @@ static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, in
     keep_pct = e ? atoi(e) : SK_KEEP_PCT_DEFAULT;
     if (keep_pct < 0 || keep_pct > 100) keep_pct = SK_KEEP_PCT_DEFAULT;
   }
-  static int dbg = -1;           // timing experiments only (I4D_SK_DBG): 1 = no column combine, 2 = no second grid barrier, 4 = no first one
-  if (dbg < 0) { const char* e = getenv("I4D_SK_DBG"); dbg = e ? atoi(e) : 0; }
   // L2 prefetch distance in stages (cp.async.bulk.prefetch.L2 of a later stage with every shared-memory refill): 1 measured
   // best at 8192^2 (48.8 -> 46.3 us per iteration; 2: 47.3, 3: 48.4).  I4D_SK_PF overrides, for experiments.
   static int pf_stages = -1;
   if (pf_stages < 0) { const char* e = getenv("I4D_SK_PF"); pf_stages = e ? atoi(e) : 1; if (pf_stages < 0 || pf_stages > 16) pf_stages = 1; }
   void* args[] = {(void*)&S, (void*)&M, (void*)&N, (void*)&ld, (void*)&alpha, (void*)&iters, (void*)&u, (void*)&v, (void*)&pm, (void*)&ps,
-                  (void*)&flag, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct, (void*)&dbg, (void*)&pf_stages};
+                  (void*)&flag, (void*)&acc_base, (void*)&fx_shift, (void*)&rpc, (void*)&allow_fast, (void*)&keep_pct, (void*)&pf_stages};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)sinkhorn_fused_kernel, dim3(G), dim3(SK_THREADS), args, smem, st);
   if (e != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;

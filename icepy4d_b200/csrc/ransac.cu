@@ -466,47 +466,64 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  // every loop below has compile-time bounds and is fully unrolled: L, x, y live in registers (no local-memory round trips
+  // on the dependent chains of this single-thread solve)
   double L[9][9];
   double tr = 0;
   {
     int t = 0;
+#pragma unroll
     for (int p = 0; p < 9; ++p)
-      for (int q = p; q < 9; ++q) { L[q][p] = cov[t]; L[p][q] = cov[t]; ++t; }
+#pragma unroll
+      for (int q = p; q < 9; ++q) { L[q][p] = cov[t]; ++t; }
+#pragma unroll
     for (int p = 0; p < 9; ++p) tr += L[p][p];
   }
   if (!(tr > 0)) { st->converged[j] = 1; return; }   // no support: keep the previous model
   const double eps = 1e-13 * tr;
   // Cholesky of C + eps I (lower triangle, in place)
+#pragma unroll
   for (int j = 0; j < 9; ++j) {
     double d = L[j][j] + eps;
+#pragma unroll
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
     if (!(d > 0)) d = eps;            // rank-deficient input: regularise the pivot
     d = sqrt(d);
     L[j][j] = d;
     const double inv = 1.0 / d;
+#pragma unroll
     for (int i = j + 1; i < 9; ++i) {
       double v = L[i][j];
+#pragma unroll
       for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
       L[i][j] = v * inv;
     }
   }
   double x[9], y[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;       // generic start (not orthogonal to the null direction)
+#pragma unroll 1
   for (int it = 0; it < 16; ++it) {
+#pragma unroll
     for (int i = 0; i < 9; ++i) {                                  // L y = x
       double v = x[i];
+#pragma unroll
       for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
       y[i] = v / L[i][i];
     }
+#pragma unroll
     for (int i = 8; i >= 0; --i) {                                 // L^T z = y (z overwrites y)
       double v = y[i];
+#pragma unroll
       for (int k = i + 1; k < 9; ++k) v -= L[k][i] * y[k];
       y[i] = v / L[i][i];
     }
     double nrm = 0;
+#pragma unroll
     for (int i = 0; i < 9; ++i) nrm += y[i] * y[i];
     nrm = 1.0 / sqrt(nrm);
     double diff = 0, diffn = 0;
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
       const double z = y[i] * nrm;
       diff += (z - x[i]) * (z - x[i]);
