@@ -120,6 +120,8 @@ def _count(name: str, args) -> int:
         n, ld, iters = int(args[2]), int(args[3]), int(args[5])
         fused = ld % 4 == 0 and ld >= (n + 3) // 4 * 4 and 64 <= n <= 8192   # one persistent cooperative launch for all iterations
         return (1 + (1 if n % 4 else 0) if fused else 5 * iters) + (5 if name == "i4d_sg_assign" else 0)
+    if name == "i4d_essential_ransac":
+        return 2 + 3 * min(64, -(-int(args[5]) // 512))
     if name == "i4d_fundamental_ransac":
         rounds = min(24, -(-int(args[5]) // 4096))
         return 1 + 5 * rounds + 1 + 2 * int(args[8]) + 2

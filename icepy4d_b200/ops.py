@@ -381,6 +381,20 @@ def fundamental_ransac(x0: torch.Tensor, x1: torch.Tensor, threshold: float = 0.
     return F, mask, n_inl
 
 
+def essential_ransac(xn0: torch.Tensor, xn1: torch.Tensor, threshold_norm: float, confidence: float = 0.9999, max_iters: int = 2048,
+                     seed: int = 0):
+    """Five-point RANSAC on K-normalised coordinates [n,2] f32 (n >= 5) -> (E [9] f64, n_inliers int32[1]) on the device."""
+    _chk(xn0, name="xn0"), _chk(xn1, name="xn1")
+    n = xn0.shape[0]
+    dev = xn0.device
+    ws = torch.empty(N.lib().i4d_essential_workspace_bytes(), device=dev, dtype=torch.uint8)
+    E = torch.empty(9, device=dev, dtype=torch.float64)
+    n_inl = torch.zeros(1, device=dev, dtype=torch.int32)
+    N.call("i4d_essential_ransac", xn0, xn1, n, float(threshold_norm), float(confidence), int(max_iters), int(seed) & 0xFFFFFFFF, E,
+           n_inl, ws, ws.numel(), _st())
+    return E, n_inl
+
+
 def essential_pose(E: torch.Tensor, xn0: torch.Tensor, xn1: torch.Tensor, threshold_norm: float, distance_threshold: float = 1e9):
     """E [9] f64 device, xn0 / xn1 [n,2] f32 normalised -> (E_proj [9], R [9], t [3] f64, mask [n] u8, n_good int32[2]) on the device."""
     _chk(xn0, name="xn0"), _chk(xn1, name="xn1")

@@ -215,6 +215,15 @@ int i4d_fundamental_ransac(const float* x0, const float* x1, int n, double thres
  * the inliers (depth in both cameras in (0, distance_threshold)) and keeps the best in OpenCV's candidate order.
  * Outputs (device): E_out [9], R_out [9] row-major, t_out [3] (unit), mask [n] u8 = inlier AND in front of both cameras,
  * n_good [2] = {votes of the chosen candidate, Sampson inliers}. */
+/* sfm/geometry.py:63-65 (cv2.findEssentialMat(..., method=cv2.RANSAC) on K-normalised coordinates) — five-point RANSAC.
+ * xn0 / xn1 [n,2] f32 K-normalised coordinates (n >= 5), threshold_norm = pixel threshold / focal length.  Seeded batches of
+ * 512 minimal samples (Nister's five-point solver, up to 10 solutions each), every solution scored on all correspondences by
+ * its Sampson-inlier count, OpenCV's adaptive stopping rule, at most max_iters samples (rounded up to whole batches).
+ * Outputs (device): E_out [9] row-major, unit Frobenius norm (NaN when no sample produced a model), n_inliers [1]. */
+size_t i4d_essential_workspace_bytes(void);
+int i4d_essential_ransac(const float* xn0, const float* xn1, int n, double threshold_norm, double confidence, int max_iters,
+                         unsigned int seed, double* E_out, int* n_inliers, void* workspace, size_t workspace_bytes,
+                         void* stream);
 size_t i4d_pose_workspace_bytes(int n);
 int i4d_essential_pose(const double* E_in, const float* xn0, const float* xn1, int n, double threshold_norm,
                        double distance_threshold, double* E_out, double* R_out, double* t_out, unsigned char* mask,
