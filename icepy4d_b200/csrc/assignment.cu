@@ -430,6 +430,8 @@ extern "C" __attribute__((visibility("default"))) int i4d_lg_assign(const float*
 #define SK_EXACT_ITERS 1
 #define SK_MAX_BAND 1024            // rows per CTA the previous-u staging buffer can hold
 #define SK_KEEP_PCT_DEFAULT 0
+// row pitch of the shared-memory stages for NP (= N rounded up to 4) columns
+__host__ __device__ inline int sk_smem_pitch(int NP) { return (NP * 8 >= SK_MAXN * 7) ? SK_MAXN : NP; }
 
 __device__ __forceinline__ float sk_ex2(float x) {
   float y;
@@ -487,7 +489,7 @@ struct SkCtx {
   float (*part_m)[SK_ROWS][SK_WARPS]; float (*part_s)[SK_ROWS][SK_WARPS];
   float* u; const float* v; float* pm; float* ps; int* flag;
   float* unew_s;         // this iteration's u of the band, log2 domain (shared memory; the next iteration's uold_s)
-  int M, N, NP, ld, n4, row0, row1, nst, cta, keep_rows, pf, tid, warp, lane; uint32_t total;   // NP = 4 * n4: N rounded up to whole float4 groups
+  int M, N, NP, NS, ld, n4, row0, row1, nst, cta, keep_rows, pf, tid, warp, lane; uint32_t total;   // NP = 4 * n4: N rounded up to whole float4 groups; NS = row pitch of the smem stages
   float norm, c_mu, c_nu, extra_row, kfac;
   const float* uold_s;   // previous-iteration u of this CTA's band, log2 domain (shared memory)
   uint32_t row_bytes;
@@ -522,7 +524,7 @@ __device__ __forceinline__ void sk_issue(const SkCtx& c, uint32_t seq) {
   else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   sk_mbar_expect(&c.full[buf], nr * c.row_bytes);
   for (int k = 0; k < nr; ++k)
-    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.NP, c.S + (size_t)(r + k) * c.ld, c.row_bytes, &c.full[buf], policy);
+    sk_bulk_load(c.stage_buf + ((size_t)buf * SK_ROWS + k) * c.NS, c.S + (size_t)(r + k) * c.ld, c.row_bytes, &c.full[buf], policy);
   if (c.pf > 0 && seq + (uint32_t)c.pf < c.total) {      // pull a later stage of the band from HBM into L2 ahead of its smem fill
     const int rp = c.row0 + sk_idx(seq + (uint32_t)c.pf, c.nst) * SK_ROWS;
     const int np = min(SK_ROWS, c.row1 - rp);
@@ -542,7 +544,7 @@ template <bool FULL>
 __device__ __forceinline__ void sk_stage_exact(const SkCtx& c, int idx, SkRing& rg, const float (&vl)[SK_GROUPS][4],
                                                L2Acc (&col)[SK_GROUPS][4]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = c.NP, n4 = c.n4;
+  const int N = c.NS, n4 = c.n4;
   const int pp = rg.seq & 1;
   const int r_base = c.row0 + idx * SK_ROWS;
   const int nr = FULL ? SK_ROWS : min(SK_ROWS, c.row1 - r_base);
@@ -610,7 +612,7 @@ __device__ __forceinline__ void sk_band_exact(const SkCtx& c, SkRing& rg, const 
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) col[g][cc].init();
   }
-  const bool full_cols = n4 == SK_GROUPS * SK_THREADS;
+  const bool full_cols = c.NS == SK_MAXN;
   const bool rev = ((rg.seq / (uint32_t)c.nst) & 1u) != 0;
 #pragma unroll 1
   for (int st = 0; st < c.nst; ++st) {
@@ -683,7 +685,7 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
                                               const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2], float& csN,
                                               float (&e_cur)[SK_ROWS][SK_GROUPS][4], const float (&e_prev)[SK_ROWS][SK_GROUPS][4]) {
   const int tid = c.tid, warp = c.warp, lane = c.lane;
-  const int N = c.NP, n4 = c.n4;
+  const int N = c.NS, n4 = c.n4;
   // partial sums go to slot fq % 4: a warp may run a stage ahead of another one that has arrived for stage s+1 but not yet read
   // the partials of stage s, so a slot is only rewritten four stages later (behind the wait on stage s+2's barrier)
   const uint32_t pp = rg.fq & 1u, slot = rg.fq & 3u;
@@ -736,15 +738,15 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
 // column sums through it and refills it afterwards (stage rg.seq - 1 + SK_STAGES).
 __device__ __forceinline__ void sk_band_fast(const SkCtx& c, SkRing& rg, const float2 (&vl)[SK_GROUPS][2], float2 (&cs)[SK_GROUPS][2],
                                              float& csN) {
-  const int n4 = c.n4, nst = c.nst;
+  const int nst = c.nst;
 #pragma unroll
   for (int g = 0; g < SK_GROUPS; ++g) cs[g][0] = cs[g][1] = make_float2(0.f, 0.f);
   csN = 0.f;
   const bool rev = ((rg.seq / (uint32_t)nst) & 1u) != 0;
   // everything but (possibly) the band's last row block is complete: the ragged block — the first stage of a backward
   // pass, the last of a forward one — takes the predicated instantiation
-  const bool all_full = (n4 == SK_GROUPS * SK_THREADS) && (c.row0 + nst * SK_ROWS == c.row1);
-  const int ragged = all_full ? -1 : ((n4 == SK_GROUPS * SK_THREADS) ? nst - 1 : -2);   // -2: every stage is predicated
+  const bool all_full = (c.NS == SK_MAXN) && (c.row0 + nst * SK_ROWS == c.row1);
+  const int ragged = all_full ? -1 : ((c.NS == SK_MAXN) ? nst - 1 : -2);                // -2: every stage is predicated
   float eA[SK_ROWS][SK_GROUPS][4], eB[SK_ROWS][SK_GROUPS][4];      // registers rotate between the two (loop unrolled by 2)
 #define SK_IDX(st) (rev ? nst - 1 - (st) : (st))
 #define SK_ISFULL(idx) (ragged == -1 || (ragged >= 0 && (idx) != ragged))
@@ -793,18 +795,24 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
   const float log_mu_last = logf((float)N) + norm, log_nu_last = logf((float)M) + norm;
   const float c_mu = fmaxf(norm, log_mu_last) * LOG2E, c_nu = fmaxf(norm, log_nu_last) * LOG2E;   // log2 of the largest marginals
   const int n4 = (N + 3) >> 2, NP = n4 * 4;      // columns [N, NP) hold -1e30 (filled by the launcher): they add 0 to every sum
+  // Wide matrices (N >= 7/8 of the maximum) use the maximal smem row pitch: the bulk copies fill the first NP floats of a row,
+  // the tail [NP, SK_MAXN) is set to -1e30 once, and every stage takes the straight-line (unpredicated) instantiation.
+  const int NS = sk_smem_pitch(NP);
 
   if (tid == 0) {
     for (int s = 0; s < SK_STAGES; ++s) sk_mbar_init(&full[s], 1);
     for (int s = 0; s < 2; ++s) sk_mbar_init(&bpart[s], SK_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (NS != NP)
+    for (int i = tid; i < SK_STAGES * SK_ROWS * (NS - NP); i += SK_THREADS)
+      stage_buf[(size_t)(i / (NS - NP)) * NS + NP + i % (NS - NP)] = -1e30f;
   __syncthreads();
 
   SkCtx ctx;
   ctx.S = S; ctx.stage_buf = stage_buf; ctx.full = full; ctx.bpart = bpart;
   ctx.part_m = part_m; ctx.part_s = part_s; ctx.u = u; ctx.v = v;
-  ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.NP = NP; ctx.ld = ld; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
+  ctx.pm = pm; ctx.ps = ps; ctx.flag = flag; ctx.M = M; ctx.N = N; ctx.NP = NP; ctx.NS = NS; ctx.ld = ld; ctx.n4 = n4; ctx.row0 = row0; ctx.row1 = row1;
   ctx.uold_s = uold_s[0]; ctx.unew_s = uold_s[1];
   ctx.nst = nst; ctx.cta = cta; ctx.norm = norm; ctx.c_mu = c_mu; ctx.c_nu = c_nu; ctx.row_bytes = (uint32_t)NP * 4u;
   ctx.keep_rows = (row1 - row0) * keep_pct / 100;
@@ -908,13 +916,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       unsigned long long* acc = acc_base + (size_t)(fit % 3u) * acc_stride;
       {
         const uint32_t last_buf = (rg.buf == 0 ? SK_STAGES : rg.buf) - 1u;
-        ulonglong2* stg = reinterpret_cast<ulonglong2*>(stage_buf + (size_t)last_buf * SK_ROWS * NP);
+        // The staging area is the DATA part of the buffer's two rows (16 n4 bytes each = half of the 32 n4 bytes of sums): the
+        // -1e30 tails [NP, NS) of the rows must survive.  16-byte unit w (two columns) goes to row w / n4, offset (w % n4) * 16.
+        unsigned char* stg0 = reinterpret_cast<unsigned char*>(stage_buf + (size_t)last_buf * SK_ROWS * NS);
+        unsigned char* stg1 = stg0 + (size_t)NS * 4;
 #pragma unroll
         for (int g = 0; g < SK_GROUPS; ++g) {
           const int gi = g * SK_THREADS + tid;
           if (gi < n4) {
-            stg[2 * gi] = make_ulonglong2(__float2ull_rn(cs[g][0].x * fx_up), __float2ull_rn(cs[g][0].y * fx_up));
-            stg[2 * gi + 1] = make_ulonglong2(__float2ull_rn(cs[g][1].x * fx_up), __float2ull_rn(cs[g][1].y * fx_up));
+            const int w0 = 2 * gi, w1 = 2 * gi + 1;
+            *reinterpret_cast<ulonglong2*>(w0 < n4 ? stg0 + (size_t)w0 * 16 : stg1 + (size_t)(w0 - n4) * 16) =
+                make_ulonglong2(__float2ull_rn(cs[g][0].x * fx_up), __float2ull_rn(cs[g][0].y * fx_up));
+            *reinterpret_cast<ulonglong2*>(w1 < n4 ? stg0 + (size_t)w1 * 16 : stg1 + (size_t)(w1 - n4) * 16) =
+                make_ulonglong2(__float2ull_rn(cs[g][1].x * fx_up), __float2ull_rn(cs[g][1].y * fx_up));
           }
         }
         asm volatile("fence.proxy.async;" ::: "memory");             // my generic-proxy writes (shared and global) before the bulk engine's
@@ -922,7 +936,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
         __syncthreads();
         if (tid == 0) {
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
-                       ::"l"(acc), "r"((uint32_t)__cvta_generic_to_shared(stg)), "r"((uint32_t)NP * 8u) : "memory");
+                       ::"l"(acc), "r"((uint32_t)__cvta_generic_to_shared(stg0)), "r"((uint32_t)n4 * 16u) : "memory");
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
+                       ::"l"(acc + 2 * (size_t)n4), "r"((uint32_t)__cvta_generic_to_shared(stg1)), "r"((uint32_t)n4 * 16u) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           atomicAdd(acc + NP, __float2ull_rn((csN + csN1) * fx_up));  // dustbin column: one more 64-bit integer add
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer read: hand it back to the ring
@@ -1093,7 +1109,7 @@ static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, in
   }
   if (!coop || sms <= 0 || sms > 256) return 1;
   const int NP = (N + 3) & ~3;
-  const size_t smem = (size_t)SK_STAGES * SK_ROWS * NP * sizeof(float);
+  const size_t smem = (size_t)SK_STAGES * SK_ROWS * sk_smem_pitch(NP) * sizeof(float);
   static bool attr_seen[64] = {};
   if (i4d_first_use_on_device(attr_seen)) {
     if (cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
   }
   if (!(tr > 0)) { st->converged[j] = 1; return; }   // no support: keep the previous model
   const double eps = 1e-13 * tr;
-  // Cholesky of C + eps I (lower triangle, in place)
+  // Cholesky of C + eps I (lower triangle, in place); reciprocals of the pivots are kept: the 18 divisions per inverse-iteration
+  // step become multiplications (the iteration is self-correcting, the fixed point is the same)
+  double Linv[9];
 #pragma unroll
   for (int j = 0; j < 9; ++j) {
     double d = L[j][j] + eps;
@@ -491,6 +493,7 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
     d = sqrt(d);
     L[j][j] = d;
     const double inv = 1.0 / d;
+    Linv[j] = inv;
 #pragma unroll
     for (int i = j + 1; i < 9; ++i) {
       double v = L[i][j];
@@ -509,14 +512,14 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
       double v = x[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
-      y[i] = v / L[i][i];
+      y[i] = v * Linv[i];
     }
 #pragma unroll
     for (int i = 8; i >= 0; --i) {                                 // L^T z = y (z overwrites y)
       double v = y[i];
 #pragma unroll
       for (int k = i + 1; k < 9; ++k) v -= L[k][i] * y[k];
-      y[i] = v / L[i][i];
+      y[i] = v * Linv[i];
     }
     double nrm = 0;
 #pragma unroll
