@@ -19,6 +19,13 @@
 // warp shuffles -> split back to hi/lo bf16 or f32).  Accumulators are double-buffered in TMEM (all 512 columns), so the
 // epilogue of one region overlaps the MMAs of the next.
 //
+// FUSE variant (conv1b only): the activation planes of conv1a never exist in HBM.  Four extra warps compute relu(conv1a) of the
+// region's 18 x 18 halo box straight from the grey image (1 -> 64 channels, 9 f32 FMAs per value in the order of sp_conv1a.cu,
+// so the values are bit-identical to the stand-alone kernel's), split them into (hi, lo) and write them into the A slot in the
+// very layout the TMA box load produces (rows of 128 bytes, 128B swizzle: 16-byte chunk c of row r at chunk c ^ (r & 7));
+// pixels outside the image are zeros (conv1b's padding).  That removes conv1a's 1 GB of stores per 2000 x 2000 tile and
+// conv1b's 1.3 GB of loads; the producer's ~2 k instructions per region hide behind the region's ~7 k clk of MMA work.
+//
 // Reference behaviour replaced: conv1b..convDb of thirdparty/SuperGlue/models/superpoint.py:154-168,193-196 (and the
 // LightGlue copy, lightglue/superpoint.py:155-170,189-192), which run as f32 cuDNN/MKL convolutions there.
 #include <cuda_fp16.h>
@@ -38,6 +45,7 @@ struct ConvTcParams {
   float* y32; int ld32; int planar;
   int cout;
   int fmt;          // 16-bit operand format of the split planes and weights: 0 = IEEE half (f16x3), 1 = bfloat16 (bf16x3)
+  const float* img; const float* w1a; const float* b1a;     // FUSE: grey image [H][W], conv1a weights [64][9] and bias [64]
 };
 
 // v -> (hi, lo) pair of 16-bit values, packed two by two: hi = round16(v), lo = round16(v - hi).  bf16x3 carries 16 mantissa
@@ -71,8 +79,10 @@ template <int N_T, int T> struct ConvCfg {
   static_assert(SMEM <= 232448 - 512, "shared memory budget");
 };
 
-template <int N_T, int T>
-__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi,
+#define CV_FUSE_THREADS 128      // conv1a producer warps of the FUSE variant (warps 12-15)
+
+template <int N_T, int T, bool FUSE>
+__global__ void __launch_bounds__(CV_THREADS + (FUSE ? CV_FUSE_THREADS : 0), 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi,
                                                                  const __grid_constant__ CUtensorMap tmLo,
                                                                  const __grid_constant__ CUtensorMap tmW, ConvTcParams p) {
   using C = ConvCfg<N_T, T>;
@@ -84,6 +94,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       t_full[2], t_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[512];
+  __shared__ float patch_s[FUSE ? 2 : 1][FUSE ? (8 * T + 4) * (CV_TILE_H + 4) : 1];      // FUSE: grey patch under the halo box, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bw = 8 * T + 2 * p.halo, bh = CV_TILE_H + 2 * p.halo;
@@ -92,19 +103,86 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmHi); tc::prefetch_tmap(&tmLo); tc::prefetch_tmap(&tmW);
-    for (int s = 0; s < CV_A_SLOTS; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < CV_A_SLOTS; ++s) { tc::mbar_init(&a_full[s], FUSE ? CV_FUSE_THREADS : 1); tc::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < CV_B_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 256); }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.NT * N_T; i += CV_THREADS) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.NT * N_T; i += blockDim.x) bias_s[i] = p.bias[i];
   if (warp == 3) tc::tmem_alloc(&tmem_base_s, C::TMEM_COLS);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
+  bool is_producer = false;
+  if constexpr (FUSE) if (warp >= CV_THREADS / 32) {
+    is_producer = true;
+    // ---- conv1a producer (FUSE): thread = (8-channel group cg, every 16th pixel of the 18 x 18 halo box); the 72 weights of
+    // the group stay in registers ----
+    const int pt = threadIdx.x - CV_THREADS, cg = pt & 7;
+    float w[9][8], b[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      b[c] = __ldg(p.b1a + cg * 8 + c);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w[t][c] = __ldg(p.w1a + (cg * 8 + c) * 9 + t);
+    }
+    constexpr int BW = 8 * T + 2, BH = CV_TILE_H + 2, PW = BW + 2, PH = BH + 2;     // halo box of conv1b; grey patch under it
+    static_assert(BW % 3 == 0 && (BH * (BW / 3) * 8) <= 7 * CV_FUSE_THREADS, "item decomposition");
+    int ai = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
+      const int rem = u % tiles;
+      const int x0 = (rem % p.tiles_x) * 8 * T - 1, y0 = (rem / p.tiles_x) * CV_TILE_H - 1;     // origin of the halo box
+      const int s = ai % CV_A_SLOTS;
+      float* patch = patch_s[ai & 1];
+      // grey patch (PH x PW, zero outside the image = conv1a's padding): one coalesced pass, then everything reads shared memory
+      for (int i = pt; i < PW * PH; i += CV_FUSE_THREADS) {
+        const int yy = y0 - 1 + i / PW, xx = x0 - 1 + i % PW;
+        patch[i] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) ? __ldg(p.img + (size_t)yy * p.W + xx) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(CV_FUSE_THREADS) : "memory");   // patch complete; everybody is done with the patch of 2 tiles ago
+      tc::mbar_wait(&a_empty[s], ((ai / CV_A_SLOTS) & 1) ^ 1);
+      uint8_t* dst = a_base + s * C::A_SLOT;
+      // item = (halo row, 3-pixel segment, channel group): BH * BW/3 * 8 = 864 items, 7 rounds of 128 threads
+#pragma unroll 1
+      for (int it = pt; it < BH * (BW / 3) * 8; it += CV_FUSE_THREADS) {
+        const int q = it >> 3, row = q / (BW / 3), px0 = (q - row * (BW / 3)) * 3;
+        float v[3][5];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) v[dy][dx] = patch[(row + dy) * PW + px0 + dx];
+        const int yy = y0 + row;
+#pragma unroll
+        for (int px = 0; px < 3; ++px) {
+          const int xx = x0 + px0 + px;
+          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {           // outside the image the ACTIVATION is zero (conv1b's padding)
+            float2 acc[4] = {make_float2(b[0], b[1]), make_float2(b[2], b[3]), make_float2(b[4], b[5]), make_float2(b[6], b[7])};
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float a = v[t / 3][px + t % 3];
+              const float2 a2 = make_float2(a, a);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[c] = __ffma2_rn(a2, make_float2(w[t][2 * c], w[t][2 * c + 1]), acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cv_split2(fmaxf(acc[c].x, 0.f), fmaxf(acc[c].y, 0.f), p.fmt, hi[c], lo[c]);
+          }
+          const int r = row * BW + px0 + px;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cg ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + C::A_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      tc::fence_proxy_async_smem();          // my generic-proxy stores before the tensor core's (async proxy) reads
+      tc::mbar_arrive(&a_full[s]);
+    }
+  }
+  if (is_producer) {
+    // (done above)
+  } else if (warp == 0 && !FUSE) {
     // ---- activation producer: one (hi, lo) halo box per 64-channel chunk ----
     if (tc::elect_one()) {
       const uint32_t bytes = 2u * (uint32_t)(bw * bh * 128);
@@ -296,18 +374,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 3) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int N_T, int T>
+template <int N_T, int T, bool FUSE = false>
 static int launch_conv(const CUtensorMap& tmHi, const CUtensorMap& tmLo, const CUtensorMap& tmW, ConvTcParams p, cudaStream_t st) {
   using C = ConvCfg<N_T, T>;
   static bool attr_seen[64] = {};
   if (i4d_first_use_on_device(attr_seen)) {
-    I4D_CUDA_CALL(cudaFuncSetAttribute(conv_tc_kernel<N_T, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(conv_tc_kernel<N_T, T, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   }
   p.tiles_x = i4d_cdiv(p.W, 8 * T);
   p.tiles_y = i4d_cdiv(p.H, CV_TILE_H);
   const long long units = (long long)p.tiles_x * p.tiles_y * p.NT;
   const int grid = (int)(units < i4d_num_sms() ? units : i4d_num_sms());
-  conv_tc_kernel<N_T, T><<<grid, CV_THREADS, C::SMEM, st>>>(tmHi, tmLo, tmW, p);
+  conv_tc_kernel<N_T, T, FUSE><<<grid, CV_THREADS + (FUSE ? CV_FUSE_THREADS : 0), C::SMEM, st>>>(tmHi, tmLo, tmW, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
@@ -341,4 +419,22 @@ extern "C" __attribute__((visibility("default"))) int i4d_conv_bf16x3_tc(
   if (int rc = i4d_make_tmap_2d_bf16(&tmW, w_packed, wrows, 64, 64, 2 * n_t, 64)) return rc;
   if (n_t == 64) return launch_conv<64, 2>(tmHi, tmLo, tmW, p, (cudaStream_t)stream);
   return launch_conv<128, 1>(tmHi, tmLo, tmW, p, (cudaStream_t)stream);
+}
+
+// conv1a + conv1b in one kernel (FUSE variant above): image [H][W] f32 -> relu(conv1b(relu(conv1a(image)))) as split planes,
+// optionally 2x2 max-pooled.  conv1a's weights are f32 [64][9] + bias [64]; conv1b's are packed as for i4d_conv_bf16x3_tc.
+extern "C" __attribute__((visibility("default"))) int i4d_sp_conv1ab_tc(
+    const float* image, int H, int W, const float* w1a, const float* b1a, const void* w1b_packed, const float* b1b, int pool,
+    void* y_hi, void* y_lo, int operand_format, void* stream) {
+  I4D_CHECK_ARG(image && w1a && b1a && w1b_packed && b1b && y_hi && y_lo, "null pointer");
+  I4D_CHECK_ARG(H > 0 && W > 0 && (!pool || (H >= 2 && W >= 2)), "bad image size");
+  I4D_CHECK_ARG(operand_format == 0 || operand_format == 1, "operand_format: 0 = f16 split planes, 1 = bf16 split planes");
+  ConvTcParams p{};
+  p.H = H; p.W = W; p.KC = 1; p.taps = 9; p.NT = 1; p.halo = 1; p.relu = 1; p.pool = pool;
+  p.bias = b1b; p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
+  p.ld16 = 64; p.y32 = nullptr; p.ld32 = 0; p.planar = 0; p.cout = 64; p.fmt = operand_format;
+  p.img = image; p.w1a = w1a; p.b1a = b1a;
+  CUtensorMap tmW;
+  if (int rc = i4d_make_tmap_2d_bf16(&tmW, w1b_packed, (uint64_t)9 * 2 * 64, 64, 64, 2 * 64, 64)) return rc;
+  return launch_conv<64, 2, true>(tmW, tmW, tmW, p, (cudaStream_t)stream);      // the activation tensor maps are unused
 }

@@ -90,24 +90,26 @@ __global__ void __launch_bounds__(256) sp_conv1a_split_kernel(const float* __res
       const int yy = y + dy - 1, xx = x0 + dx - 1;
       v[dy][dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (size_t)yy * W + xx) : 0.f;
     }
-  float acc[4][8];
+  // packed f32x2 accumulators (two channels per FFMA2: same rounding as two FFMAs, half the issue slots)
+  float2 acc[4][4];
   {
     const float4 b0 = *reinterpret_cast<const float4*>(b_s + cg * 8), b1 = *reinterpret_cast<const float4*>(b_s + cg * 8 + 4);
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
-      acc[px][0] = b0.x; acc[px][1] = b0.y; acc[px][2] = b0.z; acc[px][3] = b0.w;
-      acc[px][4] = b1.x; acc[px][5] = b1.y; acc[px][6] = b1.z; acc[px][7] = b1.w;
+      acc[px][0] = make_float2(b0.x, b0.y); acc[px][1] = make_float2(b0.z, b0.w);
+      acc[px][2] = make_float2(b1.x, b1.y); acc[px][3] = make_float2(b1.z, b1.w);
     }
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const float4 w0 = *reinterpret_cast<const float4*>(w_s + t * 64 + cg * 8), w1 = *reinterpret_cast<const float4*>(w_s + t * 64 + cg * 8 + 4);
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float2 w[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       const float a = v[t / 3][px + t % 3];
+      const float2 a2 = make_float2(a, a);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[px][c] = fmaf(a, w[c], acc[px][c]);
+      for (int c = 0; c < 4; ++c) acc[px][c] = __ffma2_rn(a2, w[c], acc[px][c]);
     }
   }
   const size_t plane = (size_t)H * W * 64;
@@ -117,17 +119,20 @@ __global__ void __launch_bounds__(256) sp_conv1a_split_kernel(const float* __res
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
-      const float a = fmaxf(acc[px][c], 0.f), b = fmaxf(acc[px][c + 1], 0.f);
+      const float a = fmaxf(acc[px][c >> 1].x, 0.f), b = fmaxf(acc[px][c >> 1].y, 0.f);
       if (fmt) {                                                     // bf16 (hi, lo)
         const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         const float2 hf = __bfloat1622float2(h);
-        const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        const float2 rem = __fadd2_rn(make_float2(a, b), make_float2(-hf.x, -hf.y));
+        const __nv_bfloat162 l = __floats2bfloat162_rn(rem.x, rem.y);
         hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-      } else {                                                       // IEEE half (hi, lo)
-        const __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+      } else {                                                       // IEEE half (hi, lo); values beyond the half range saturate
+        const float as = fminf(a, 65504.f), bs = fminf(b, 65504.f);
+        const __half2 h = __floats2half2_rn(as, bs);
         const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(fminf(a, 65504.f) - hf.x, fminf(b, 65504.f) - hf.y);
+        const float2 rem = __fadd2_rn(make_float2(as, bs), make_float2(-hf.x, -hf.y));
+        const __half2 l = __floats2half2_rn(rem.x, rem.y);
         hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
       }

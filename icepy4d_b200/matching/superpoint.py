@@ -13,6 +13,7 @@ of the reference; accepts a state_dict with the reference's parameter names.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -70,6 +71,7 @@ class SuperPointB200:
         self.w1a = (state_dict["conv1a.weight"].to(self.device, torch.float32).contiguous(),
                     state_dict["conv1a.bias"].to(self.device, torch.float32).contiguous())
         self._kws = {}
+        self.fuse_conv1 = os.environ.get("I4D_NO_CONV1_FUSION", "0") != "1"     # cross-check switch: separate conv1a / conv1b kernels
 
     # -- backbone (cuDNN through torch; channels-last so the heads come out HWC for the gather kernel) --
     def _conv(self, x, name, pad, relu=True):
@@ -87,8 +89,12 @@ class SuperPointB200:
 
     def _backbone_split(self, image: torch.Tensor):
         pk = self.pk
-        x = ops.sp_conv1a_relu_split(image, self.w1a[0], self.w1a[1], self.split_dtype)
-        x = ops.conv_bf16x3(x, pk["conv1b"], pool=True)
+        if self.fuse_conv1:
+            # conv1a computed inside conv1b's operand producer: its 1 GB (2000 x 2000 tile) activation never goes to HBM
+            x = ops.sp_conv1ab_fused(image, self.w1a[0], self.w1a[1], pk["conv1b"], pool=True)
+        else:
+            x = ops.sp_conv1a_relu_split(image, self.w1a[0], self.w1a[1], self.split_dtype)
+            x = ops.conv_bf16x3(x, pk["conv1b"], pool=True)
         x = ops.conv_bf16x3(ops.conv_bf16x3(x, pk["conv2a"]), pk["conv2b"], pool=True)
         x = ops.conv_bf16x3(ops.conv_bf16x3(x, pk["conv3a"]), pk["conv3b"], pool=True)
         x = ops.conv_bf16x3(ops.conv_bf16x3(x, pk["conv4a"]), pk["conv4b"])

@@ -110,6 +110,19 @@ def conv_bf16x3(x: torch.Tensor, pk: PackedConv, relu: bool = True, pool: bool =
     return y16 if y16 is not None else y32
 
 
+def sp_conv1ab_fused(image: torch.Tensor, w1a: torch.Tensor, b1a: torch.Tensor, pk: PackedConv, pool: bool = True) -> torch.Tensor:
+    """image [1,1,H,W] f32 -> relu(conv1b(relu(conv1a(image)))) as split planes [2,Ho,Wo,64] (2x2 max-pool fused when pool):
+    one kernel, conv1a's activation never touches HBM (i4d_sp_conv1ab_tc)."""
+    _chk(image, name="image")
+    assert pk.cin == 64 and pk.cout == 64 and pk.ksize == 3
+    H, W = int(image.shape[-2]), int(image.shape[-1])
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    y = torch.empty((2, Ho, Wo, 64), device=image.device, dtype=pk.dtype)
+    N.call("i4d_sp_conv1ab_tc", image, H, W, _chk(w1a.reshape(64, 9), name="w1a"), _chk(b1a, name="b1a"), pk.w, pk.b, int(pool),
+           y[0], y[1], 1 if pk.dtype == torch.bfloat16 else 0, _st())
+    return y
+
+
 class KeypointWorkspace:
     """Reusable device buffers for candidate compaction + top-k of one score map size."""
 

@@ -54,6 +54,12 @@ int i4d_maxpool2x2_nhwc(const void* in, int H, int W, int C, void* out, int elem
  *   operand_format : 1 = bfloat16 pairs as described ("bf16x3", 16 mantissa bits per value); 0 = IEEE-half pairs ("f16x3",
  *                22 mantissa bits, values clamped to +-65504): same three products, same speed, f32-grade results */
 int i4d_conv_tile_cout(int cout_pad);
+/* superpoint.py:154-156 — relu(conv1a) -> relu(conv1b) (-> MaxPool2d(2,2) when pool = 1) in ONE kernel: conv1a's 64-channel
+ * activation (1 GB per 2000 x 2000 tile as split planes) never goes to HBM; warps of the conv1b kernel compute it from the grey
+ * image into the shared-memory operand buffers (bit-identical values to i4d_sp_conv1a_relu).  image [H][W] f32, w1a [64][9],
+ * b1a [64], w1b_packed / b1b as for i4d_conv_bf16x3_tc (Cin = 64, cout = 64), outputs y_hi / y_lo [Ho][Wo][64] split planes. */
+int i4d_sp_conv1ab_tc(const float* image, int H, int W, const float* w1a, const float* b1a, const void* w1b_packed,
+                      const float* b1b, int pool, void* y_hi, void* y_lo, int operand_format, void* stream);
 int i4d_conv_bf16x3_tc(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_packed, const float* bias,
                        int cout_pad, int cout, int ksize, int relu, int pool, void* y_hi, void* y_lo, float* y32, int ld32,
                        int y32_planar, int operand_format, void* stream);

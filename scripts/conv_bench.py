@@ -28,6 +28,8 @@ pk = sp.pk
 x1 = ops.sp_conv1a_relu_split(img, *sp.w1a)
 t = ev(lambda: ops.sp_conv1a_relu_split(img, *sp.w1a))
 print(f"conv1a (SIMT f32 -> split planes)        {t * 1e3:8.1f} us   {H * W * 64 * 4 / t / 1e6:7.0f} GB/s written")
+t = ev(lambda: ops.sp_conv1ab_fused(img, sp.w1a[0], sp.w1a[1], sp.pk["conv1b"], pool=True))
+print(f"conv1a+conv1b fused (one kernel, pooled)  {t * 1e3:8.1f} us")
 plan = [("conv1b", True), ("conv2a", False), ("conv2b", True), ("conv3a", False), ("conv3b", True), ("conv4a", False), ("conv4b", False)]
 x = x1
 total = t

@@ -93,3 +93,20 @@ def test_superpoint_backbone_bf16x3_vs_f32(mode, tol):
     k0 = {tuple(p) for p in f0.keypoints[:f0.n].cpu().numpy().tolist()}
     k1 = {tuple(p) for p in f1.keypoints[:f1.n].cpu().numpy().tolist()}
     assert len(k0 & k1) / len(k0 | k1) > 0.99
+
+
+@pytest.mark.parametrize("H,W,pool", [(16, 16, True), (37, 53, True), (38, 54, False), (130, 199, True), (401, 333, True)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fused_conv1a_conv1b_is_bit_identical_to_the_two_kernels(ops, H, W, pool, dtype):
+    """i4d_sp_conv1ab_tc computes relu(conv1a) inside conv1b's operand producer (the activation never goes to HBM).  Same f32
+    FMA order, same (hi, lo) split, same shared-memory layout as the TMA box load with its zero fill: the output planes must be
+    BIT-identical to i4d_sp_conv1a_relu followed by i4d_conv_bf16x3_tc (superpoint.py:154-156), at image borders included."""
+    sd = weights.make_superpoint_state(1)
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    img = torch.rand(1, 1, H, W, generator=gen).cuda()
+    w1a, b1a = sd["conv1a.weight"].float().cuda().contiguous(), sd["conv1a.bias"].float().cuda().contiguous()
+    pk = ops.PackedConv(sd["conv1b.weight"], sd["conv1b.bias"], "cuda", dtype)
+    ref = ops.conv_bf16x3(ops.sp_conv1a_relu_split(img, w1a, b1a, dtype), pk, pool=pool)
+    got = ops.sp_conv1ab_fused(img, w1a, b1a, pk, pool=pool)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
