@@ -37,6 +37,8 @@ struct RansacState {
   double topF[RS_NPOL][9];      // the RS_NPOL best fully-scored hypotheses so far (topF[0] == bestF), starts of the polisher
   double top_score[RS_NPOL];
   double polishF[RS_NPOL][9];
+  double polishX[RS_NPOL][9];   // the polisher's last eigenvector (normalised coordinates): start of the next inverse iteration
+  int have_x[RS_NPOL];
   double final_score[RS_NPOL + 1];   // quality of {bestF, polishF[0..]} under the selection rule of the polish mode
   int converged[RS_NPOL];       // polisher j reached its fixed point: its remaining polish work is skipped
   int polish_done;              // polish iterations executed (all starts)
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(1024) rs_norm_kernel(const float* __restrict__
     st->best_score = -1.0; st->best_inliers = 0; st->done = 0; st->hyp_tested = 0;
     st->polish_done = 0; st->failed = 0; st->use_polished = 0;
     for (int j = 0; j < RS_NPOL; ++j) {
-      st->converged[j] = 0; st->top_score[j] = -1.0;
+      st->converged[j] = 0; st->top_score[j] = -1.0; st->have_x[j] = 0;
       for (int i = 0; i < 9; ++i) st->topF[j][i] = 0.0;
     }
     for (int i = 0; i < 9; ++i) st->bestF[i] = 0.0;
@@ -503,8 +505,12 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
     }
   }
   double x[9], y[9];
+  // start: the eigenvector of the previous polish iteration (the re-weighted moment matrix changes little from one IRLS step to
+  // the next, so 2-3 inverse-iteration steps reach the same 1e-14 agreement that takes ~16 from a generic start), else a generic
+  // vector that is not orthogonal to the null direction
+  const bool warm = st->have_x[j] != 0;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;       // generic start (not orthogonal to the null direction)
+  for (int i = 0; i < 9; ++i) x[i] = warm ? st->polishX[j][i] : 1.0 / 3.0 + 0.01 * i;
 #pragma unroll 1
   for (int it = 0; it < 16; ++it) {
 #pragma unroll
@@ -536,7 +542,8 @@ __global__ void __launch_bounds__(64) rs_polish_solve_kernel(RansacState* st, co
     if (it > 0 && fmin(diff, diffn) < 1e-28) break;               // converged up to sign
   }
   double Fn[9];
-  for (int i = 0; i < 9; ++i) Fn[i] = x[i];
+  for (int i = 0; i < 9; ++i) { Fn[i] = x[i]; st->polishX[j][i] = x[i]; }
+  st->have_x[j] = 1;
   rs_rank2(Fn);
   double F[9];
   rs_denormalise(Fn, st->T0, st->T1, F);

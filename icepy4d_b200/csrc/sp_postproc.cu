@@ -191,63 +191,6 @@ __device__ void bitonic_sort_desc_smem(unsigned long long* a, int n_pow2) {
   }
 }
 
-// Register-blocked bitonic sort (descending) of n_pow2 = E * blockDim.x keys in shared memory: thread t owns the E consecutive
-// keys [E t, E t + E).  Compare-exchange distances j < E stay inside a thread, E <= j < 32 E inside a warp (64-bit shuffles),
-// only j >= 32 E goes through shared memory with block barriers: 15 barrier steps instead of 91 for 8192 keys.
-template <int E>
-__device__ void bitonic_sort_desc_blocked(unsigned long long* a, int n_pow2) {
-  const int t = threadIdx.x, lane = t & 31;
-  unsigned long long r[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) r[e] = a[t * E + e];
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j >= E; j >>= 1) {
-      if (j >= 32 * E) {
-        __syncthreads();                                   // everybody is done reading the previous exchange
-#pragma unroll
-        for (int e = 0; e < E; ++e) a[t * E + e] = r[e];
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int i = t * E + e;
-          const unsigned long long y = a[i ^ j];
-          const bool keep_max = (((i & j) == 0) == ((i & k) == 0));
-          r[e] = keep_max ? (r[e] > y ? r[e] : y) : (r[e] < y ? r[e] : y);
-        }
-      } else {
-        const int lj = j / E;                              // partner lane distance
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int i = t * E + e;
-          const unsigned long long y = __shfl_xor_sync(0xffffffffu, r[e], lj);
-          const bool keep_max = (((i & j) == 0) == ((i & k) == 0));
-          r[e] = keep_max ? (r[e] > y ? r[e] : y) : (r[e] < y ? r[e] : y);
-        }
-      }
-    }
-    // distances below E: inside the thread, compile-time register indices
-#pragma unroll
-    for (int jj = E / 2; jj > 0; jj >>= 1) {
-      if (jj <= (k >> 1)) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if ((e & jj) == 0) {
-            const int i = t * E + e;
-            const bool desc = (i & k) == 0;
-            const unsigned long long x = r[e], y = r[e | jj];
-            if (desc ? (x < y) : (x > y)) { r[e] = y; r[e | jj] = x; }
-          }
-        }
-      }
-    }
-  }
-  (void)lane;
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < E; ++e) a[t * E + e] = r[e];
-  __syncthreads();
-}
-
 // mode 0: keys are (score|~idx), mode 1: keys are (~idx|score)
 __device__ __forceinline__ void emit_keypoint(unsigned long long key, int mode, int W, float* kp, float* sc) {
   unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)(key & 0xFFFFFFFFull);
@@ -458,43 +401,58 @@ __device__ unsigned long long block_radix_kth(const unsigned long long* __restri
   return *s_prefix;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) topk_finish_kernel(const unsigned long long* __restrict__ cand, TopkState* st, int W,
-                                                                  const unsigned long long* __restrict__ sel,
-                                                                  const unsigned long long* __restrict__ ties,
-                                                                  float* __restrict__ kpts, float* __restrict__ sc) {
-  extern __shared__ __align__(16) unsigned long long skeys[];  // SEL_MAX_SMEM_KEYS
+// Gathers the result set (unordered) into `sel[0, m)`: the keys above the k-th value are there already (compaction order), the
+// `need` ties with the lowest linear indices are appended; in keep-all mode every candidate goes in with its halves swapped
+// (index-major keys: the reference's row-major nonzero() order).
+__global__ void __launch_bounds__(SEL_THREADS) topk_finish_kernel(const unsigned long long* __restrict__ cand, TopkState* st,
+                                                                  unsigned long long* __restrict__ sel,
+                                                                  const unsigned long long* __restrict__ ties) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_cnt;
   const int m = st->m, keep_all = st->keep_all;
-  int p2 = 1;
-  while (p2 < m) p2 <<= 1;
-  for (int i = threadIdx.x; i < p2; i += blockDim.x) skeys[i] = 0ull;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   if (keep_all) {
-    for (int i = threadIdx.x; i < m; i += blockDim.x) { unsigned long long key = cand[i]; skeys[i] = (key << 32) | (key >> 32); }
-  } else {
-    const int n_gt = min(st->n_gt, m), n_tie = st->n_tie, need = min(st->remaining, m - n_gt);
-    for (int i = threadIdx.x; i < n_gt; i += blockDim.x) skeys[i] = sel[i];
-    if (need > 0 && n_tie > 0) {
-      // the `need` ties with the largest keys = the lowest linear indices
-      unsigned long long kth = (need >= n_tie) ? 0ull : block_radix_kth(ties, n_tie, need, hist, &s_prefix, &s_remaining);
-      __syncthreads();
-      for (int i = threadIdx.x; i < n_tie; i += blockDim.x) {
-        unsigned long long key = ties[i];
-        if (key >= kth) {
-          int slot = atomicAdd(&s_cnt, 1);
-          if (slot < need) skeys[n_gt + slot] = key;
-        }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { unsigned long long key = cand[i]; sel[i] = (key << 32) | (key >> 32); }
+    return;
+  }
+  const int n_gt = min(st->n_gt, m), n_tie = st->n_tie, need = min(st->remaining, m - n_gt);
+  if (need > 0 && n_tie > 0) {
+    // the `need` ties with the largest keys = the lowest linear indices
+    unsigned long long kth = (need >= n_tie) ? 0ull : block_radix_kth(ties, n_tie, need, hist, &s_prefix, &s_remaining);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tie; i += blockDim.x) {
+      unsigned long long key = ties[i];
+      if (key >= kth) {
+        int slot = atomicAdd(&s_cnt, 1);
+        if (slot < need) sel[n_gt + slot] = key;
       }
     }
   }
+}
+
+// Sort + emit without a sort: the keys are distinct (the linear index is part of every key), so the output position of a key is
+// the number of keys greater than it.  CTA = 32 keys x 8 threads each (a thread compares its key with every 8th key of the set in
+// shared memory: consecutive lanes read consecutive words, no bank conflicts), 3 shuffles, one write.  m <= 16384 keys: 256 / 512
+// independent CTAs of ~1 k iterations instead of ONE CTA running a 91-step bitonic network (105 us for 8192 keys).
+#define RANK_THREADS 256
+__global__ void __launch_bounds__(RANK_THREADS) topk_rank_emit_kernel(const unsigned long long* __restrict__ keys, const TopkState* st,
+                                                                      int W, float* __restrict__ kpts, float* __restrict__ sc) {
+  extern __shared__ __align__(16) unsigned long long rk[];
+  const int m = st->m, mode = st->keep_all ? 1 : 0;
+  if ((int)blockIdx.x * (RANK_THREADS / 8) >= m) return;
+  for (int i = threadIdx.x; i < m; i += RANK_THREADS) rk[i] = keys[i];
   __syncthreads();
-  if (p2 == 8 * SEL_THREADS) bitonic_sort_desc_blocked<8>(skeys, p2);            // 8192 keys: the cfg2 case
-  else if (p2 == 16 * SEL_THREADS) bitonic_sort_desc_blocked<16>(skeys, p2);     // 16384 keys: cfg5
-  else bitonic_sort_desc_smem(skeys, p2);
-  for (int i = threadIdx.x; i < m; i += blockDim.x) emit_keypoint(skeys[i], keep_all ? 1 : 0, W, kpts + 2 * i, sc + i);
+  const int part = threadIdx.x & 7, idx = blockIdx.x * (RANK_THREADS / 8) + (threadIdx.x >> 3);
+  const unsigned long long mine = idx < m ? rk[idx] : 0ull;
+  int cnt = 0;
+#pragma unroll 8
+  for (int j = part; j < m; j += 8) cnt += rk[j] > mine ? 1 : 0;
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+  if (part == 0 && idx < m) emit_keypoint(mine, mode, W, kpts + 2 * cnt, sc + cnt);
 }
 
 __global__ void bitonic_global_step(unsigned long long* a, int n_pow2, int k, int j) {
@@ -619,10 +577,9 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_select_topk(const u
   }
   if (k >= 1 && k <= SEL_MAX_SMEM_KEYS) {
     // multi-CTA radix select; scratch: `spill` holds [TopkState | selected keys (k) | ties (rest)]
-    static bool attr2 = false;
-    if (!attr2) {
-      I4D_CUDA_CALL(cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_MAX_SMEM_KEYS * 8));
-      attr2 = true;
+    static bool attr2_seen[64] = {};
+    if (i4d_first_use_on_device(attr2_seen)) {
+      I4D_CUDA_CALL(cudaFuncSetAttribute(topk_rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_MAX_SMEM_KEYS * 8));
     }
     const size_t st_words = (sizeof(TopkState) + 7) / 8;
     // spill layout (2 * cand_cap + 4096 keys, see the header): [TopkState (< 4096 words) | selected keys (k <= 16384 <= cand_cap) | ties (cand_cap)]
@@ -639,7 +596,9 @@ extern "C" __attribute__((visibility("default"))) int i4d_sp_select_topk(const u
       topk_scan_kernel<<<1, 1024, 0, st>>>(tks, pass);
     }
     topk_compact_kernel<<<G, 256, 0, st>>>(cand_keys, tks, sel, ties);
-    topk_finish_kernel<<<1, SEL_THREADS, SEL_MAX_SMEM_KEYS * 8, st>>>(cand_keys, tks, W, sel, ties, kpts, scores);
+    topk_finish_kernel<<<1, SEL_THREADS, 0, st>>>(cand_keys, tks, sel, ties);
+    const int m_max = k < out_cap ? k : out_cap;                     // the result holds at most min(k, out_cap) keypoints
+    topk_rank_emit_kernel<<<i4d_cdiv(m_max, RANK_THREADS / 8), RANK_THREADS, (size_t)m_max * 8, st>>>(sel, tks, W, kpts, scores);
     I4D_CUDA_LAUNCH_CHECK();
     return I4D_OK;
   }
