@@ -69,6 +69,7 @@ struct AttnParams {
   __nv_bfloat16* O; int ldo;           // O rows are indexed like Q rows (q_row0 + i)
   float* part;                         // [2 * n_ctas] part slots: slot 2c = CTA c's first segment, 2c + 1 = its last
   int* counters;                       // per item: parts arrived (zeroed before the launch)
+  const int* nk_dev;                   // optional: per problem, how many of the nk keys are real (device memory; the rest is masked)
 };
 
 #define FA_DEFAULT_POLY 0
@@ -210,6 +211,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
 #pragma unroll
     for (int i = 1; i < FA_MAX_PROBLEMS; ++i)
       if (z == i) { pr = p.prob[i]; nblk = p.nblk[i]; n_qt = p.n_qt[i]; uoff = p.unit_off[i]; ioff = p.item_off[i]; }
+    // keys beyond the device-side count are padding of a shape bucket: masked like the ragged tail of the last block
+    if (p.nk_dev != nullptr) pr.nk = min(pr.nk, __ldg(p.nk_dev + z));
     const int r = (int)(u - uoff), it = r / nblk, kb0 = r - it * nblk;
     const long long item_start = (long long)uoff + (long long)it * nblk;
     const int kb1 = (int)min((long long)nblk, (long long)kb0 + (u_end - u));
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           const float m_blk = mx * p.scale_log2;
           // lazy running maximum: move only when the block exceeds it by more than 2^TAU (both partner threads decide alike)
           const bool need = jj > 0 && m_blk > m_run + FA_TAU;
-          const float m_new = (jj == 0 || need) ? m_blk : m_run;
+          const float m_new = (jj == 0 || need) ? fmaxf(m_blk, -1e30f) : m_run;   // finite even if the block holds no real key
           if (jj > 0) {
             tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
             if (__any_sync(0xffffffffu, need)) {
@@ -472,7 +475,7 @@ extern "C" __attribute__((visibility("default"))) size_t i4d_attention_workspace
 
 extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
     const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads, const int* problems_host, int n_problems,
-    float scale, void* O, int ldo, void* workspace, size_t workspace_bytes, void* stream) {
+    const int* key_counts_dev, float scale, void* O, int ldo, void* workspace, size_t workspace_bytes, void* stream) {
   I4D_CHECK_ARG(X && O && problems_host, "null pointer");
   I4D_CHECK_ARG(n_problems >= 1 && n_problems <= FA_MAX_PROBLEMS && heads >= 1, "1..4 problems, heads >= 1");
   I4D_CHECK_ARG((ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "O must be 16-byte aligned with ldo % 8 == 0");
@@ -501,6 +504,7 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = reinterpret_cast<__nv_bfloat16*>(O); p.ldo = ldo;
+  p.nk_dev = key_counts_dev;
   CUtensorMap tmX;
   if (int rc = i4d_make_tmap_2d_bf16(&tmX, X, (uint64_t)rows, (uint64_t)ld, (uint64_t)ld, FA_BN, FA_D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;

@@ -38,8 +38,11 @@ def gemm_tc(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = Non
 
 
 def attention_tc(X: torch.Tensor, problems: Sequence[Tuple[int, int, int, int]], out: torch.Tensor, q_col: int, k_col: int,
-                 v_col: int, heads: int = 4, scale: float = 0.125):
-    """X [rows, ld] bf16 holding Q/K/V column blocks; problems = [(q_row0, nq, k_row0, nk), ...]; out [rows, >=64*heads] bf16."""
+                 v_col: int, heads: int = 4, scale: float = 0.125, key_counts: Optional[torch.Tensor] = None):
+    """X [rows, ld] bf16 holding Q/K/V column blocks; problems = [(q_row0, nq, k_row0, nk), ...]; out [rows, >=64*heads] bf16.
+    key_counts (optional, device int32 [len(problems)]): how many of each problem's nk keys are real — the rest is masked on the
+    device, so a launch (or a captured graph) with bucketed sizes serves every keypoint count of the bucket."""
+    assert key_counts is None or (key_counts.dtype == torch.int32 and key_counts.is_cuda and key_counts.numel() >= len(problems))
     assert X.dtype == BF16 and out.dtype == BF16 and X.is_contiguous() and out.stride(1) == 1
     pr = np.ascontiguousarray(np.asarray(problems, dtype=np.int32).reshape(-1))
     key = (X.device.index, torch.cuda.current_stream().cuda_stream)      # one split-merge scratch per device and stream
@@ -47,7 +50,7 @@ def attention_tc(X: torch.Tensor, problems: Sequence[Tuple[int, int, int, int]],
     if ws is None:
         ws = _ATTN_WS[key] = torch.empty(N.lib().i4d_attention_workspace_bytes(), device=X.device, dtype=torch.uint8)
     N.call("i4d_attention_bf16_tc", X, X.shape[0], X.shape[1], int(q_col), int(k_col), int(v_col), int(heads), pr, len(problems),
-           float(scale), out, out.stride(0), ws, ws.numel(), _st())
+           key_counts, float(scale), out, out.stride(0), ws, ws.numel(), _st())
     return out
 
 
@@ -95,6 +98,7 @@ class SuperGlueTensorCore:
         self.wf, self.bf = h(w.wf), w.bf
         self._buf = {}
         self._graphs = {}
+        self._static_buf = None
 
     def _buffers(self, nt):
         if self._buf.get("nt") != nt:
@@ -107,15 +111,20 @@ class SuperGlueTensorCore:
                 "qkv": torch.empty((nt, 768), device=d, dtype=BF16), "att": torch.empty((nt, 256), device=d, dtype=BF16),
                 "hid": torch.empty((nt, 512), device=d, dtype=BF16), "md": torch.empty((nt, 256), device=d, dtype=BF16)}
 
-    def _schedule(self, b, n0: int, n1: int, scores: torch.Tensor, collect=None) -> torch.Tensor:
-        """The 18-layer GNN + final projection + score GEMM on buffers `b`; b["x32"] already holds the encoded descriptors."""
-        x32, xm, qkv, hid, md = b["x32"], b["xm"], b["qkv"], b["hid"], b["md"]
+    def _schedule(self, b, n0: int, n1: int, scores: torch.Tensor, collect=None, counts=None) -> torch.Tensor:
+        """The 18-layer GNN + final projection + score GEMM on buffers `b`; b["x32"] already holds the encoded descriptors of
+        image 0 in rows [0, n0) and of image 1 in rows [n0, n0 + n1).  counts (device int32 [4] = real n0, n1, n1, n0) masks the
+        padding keys when n0 / n1 are bucket sizes."""
+        nt = n0 + n1
+        x32, xm, qkv, hid, md = b["x32"][:nt], b["xm"][:nt], b["qkv"][:nt], b["hid"][:nt], b["md"][:nt]
         to_bf16(x32, xm[:, :256])
         self_p = [(0, n0, 0, n0), (n0, n1, n0, n1)]
         cross_p = [(0, n0, n0, n1), (n0, n1, 0, n0)]
+        kc_self, kc_cross = (None, None) if counts is None else (counts[:2], counts[2:])
         for l, L in enumerate(self.layers):
             gemm_tc(xm[:, :256], L["wqkv"], L["bqkv"], out16=qkv)
-            attention_tc(qkv, cross_p if l % 2 == 1 else self_p, xm[:, 256:], 0, 256, 512)
+            cross = l % 2 == 1
+            attention_tc(qkv, cross_p if cross else self_p, xm[:, 256:], 0, 256, 512, key_counts=kc_cross if cross else kc_self)
             gemm_tc(xm, L["w1"], L["b1"], out16=hid, relu=True)
             gemm_tc(hid, L["w2"], L["b2"], residual=x32, out32=x32, out16=xm[:, :256])
             if collect is not None:
@@ -127,7 +136,7 @@ class SuperGlueTensorCore:
     def gnn_and_scores(self, d0: torch.Tensor, d1: torch.Tensor, collect=None) -> torch.Tensor:
         n0, n1 = d0.shape[0], d1.shape[0]
         nt = n0 + n1
-        if collect is None and self.use_graphs and min(n0, n1) >= 1024:
+        if collect is None and self.use_graphs and min(n0, n1) >= self.GRAPH_MIN:
             out = self._graphed(d0, d1)
             if out is not None:
                 return out
@@ -137,37 +146,66 @@ class SuperGlueTensorCore:
         scores = ops.padded_scores(n0, n1, self.dev)
         return self._schedule(b, n0, n1, scores, collect)
 
-    # -- CUDA-graph replay of the schedule (75 launches per tile pair): one graph per (n0, n1), static buffers, the caller's
-    #    descriptors are copied in front of the replay.  The returned score matrix is the graph's own buffer: it is consumed (by
-    #    the assignment kernels, same stream) before the next replay overwrites it.  Any failure disables graphs for good.
+    # -- CUDA-graph replay of the schedule (75 launches per tile pair).  Graphs are keyed on SHAPE BUCKETS: both keypoint counts
+    #    are rounded up to a multiple of GRAPH_BUCKET, the graph is captured at the bucket size on one set of static buffers
+    #    (shared by all graphs, sized for the largest bucket seen), and the real counts live in a small device tensor the
+    #    attention kernel reads (padding keys are masked; padding query rows cost a little arithmetic and are never read).  So
+    #    tiles with uneven keypoint counts stay on the graph path.  The returned score matrix is a [n0, n1] view of the static
+    #    buffer (row pitch = the bucket's n1): it is consumed (by the assignment kernels, same stream) before the next replay
+    #    overwrites it.  The first call of a bucket runs eagerly (it also warms every kernel up); any capture failure disables
+    #    graphs for good.
     use_graphs = os.environ.get("I4D_NO_GRAPHS", "0") != "1"
-    MAX_GRAPHS = 3
+    MAX_GRAPHS = 16
+    GRAPH_MIN = 1024
+    GRAPH_BUCKET = 256
+
+    def _static(self, nt: int, n_scores: int):
+        st = self._static_buf
+        if st is None or st["nt"] < nt or st["scores"].numel() < n_scores:
+            self._graphs.clear()                                              # graphs hold pointers into the old buffers
+            nt = max(nt, 0 if st is None else st["nt"])
+            n_scores = max(n_scores, 0 if st is None else st["scores"].numel())
+            st = self._static_buf = self._alloc(nt)
+            st["scores"] = torch.empty(n_scores, device=self.dev, dtype=torch.float32)
+            st["counts"] = torch.zeros(4, device=self.dev, dtype=torch.int32)
+        return st
 
     def _graphed(self, d0: torch.Tensor, d1: torch.Tensor):
         n0, n1 = d0.shape[0], d1.shape[0]
-        key = (n0, n1, torch.cuda.current_stream().cuda_stream)
+        B = self.GRAPH_BUCKET
+        p0, p1 = -(-n0 // B) * B, -(-n1 // B) * B
+        key = (p0, p1, torch.cuda.current_stream().cuda_stream)
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= self.MAX_GRAPHS:
-                return None
-            self._graphs[key] = "seen"           # first call of a shape runs eagerly (it also warms every kernel up)
+                self._graphs.pop(next(iter(self._graphs)))                    # oldest bucket out
+            self._graphs[key] = "seen"
             return None
         try:
+            st = self._static(p0 + p1, p0 * p1)
+            if key not in self._graphs:                                       # the static buffers grew: every graph was dropped
+                self._graphs[key] = ent = "seen"
+            scores = st["scores"][: p0 * p1].view(p0, p1)
             if ent == "seen":
-                b = self._alloc(n0 + n1)
-                scores = ops.padded_scores(n0, n1, self.dev)
                 launches0 = N.LAUNCHES
+                st["x32"][: p0 + p1].zero_()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._schedule(b, n0, n1, scores)
-                ent = self._graphs[key] = {"g": g, "b": b, "scores": scores, "launches": N.LAUNCHES - launches0}
+                    self._schedule(st, p0, p1, scores, counts=st["counts"])
+                ent = self._graphs[key] = {"g": g, "launches": N.LAUNCHES - launches0}
                 N.LAUNCHES = launches0           # capture launched nothing
-            b = ent["b"]
-            b["x32"][:n0] = d0
-            b["x32"][n0:] = d1
+            x32 = st["x32"]
+            x32[:n0] = d0
+            x32[p0: p0 + n1] = d1
+            if n0 < p0:
+                x32[n0:p0].zero_()               # padding rows restart from zero every replay (the residual stream is in place)
+            if n1 < p1:
+                x32[p0 + n1: p0 + p1].zero_()
+            # pageable source: the driver stages it before the call returns, so the host may run ahead of the stream
+            st["counts"].copy_(torch.tensor([n0, n1, n1, n0], dtype=torch.int32))
             ent["g"].replay()
             N.LAUNCHES += ent["launches"]
-            return ent["scores"]
+            return scores[:n0, :n1]
         except Exception as err:                 # noqa: BLE001 - eager execution is always available
             import logging
             logging.getLogger(__name__).warning(f"CUDA-graph capture of the SuperGlue schedule failed ({err}); running eagerly")

@@ -128,11 +128,14 @@ int i4d_layernorm_gelu_bf16(const float* X, int ldx, const float* gamma, const f
  * one launch: both images of a self/cross layer).  O [rows, ldo] bf16, row-indexed like Q.  `workspace` (nullable,
  * i4d_attention_workspace_bytes()) lets the persistent kernel cut the key blocks of all (problem, head, 256-query tile) items into
  * equal per-SM ranges and merge the parts of items a range boundary cuts; without it every CTA runs whole items.
+ * key_counts_dev (nullable, DEVICE ints, one per problem): only the first key_counts_dev[z] of the problem's nk keys are real, the
+ * rest is masked — the launch geometry stays that of a shape bucket (a captured CUDA graph serves every keypoint count of the
+ * bucket), the true counts are read on the device.
  * Replaces superglue.py:87-93 and lightglue.py:108-130 on the throughput path. */
 size_t i4d_attention_workspace_bytes(void);
 int i4d_attention_bf16_tc(const void* X, int rows, int ld, int q_col, int k_col, int v_col, int heads,
-                          const int* problems_host, int n_problems, float scale, void* O, int ldo, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          const int* problems_host, int n_problems, const int* key_counts_dev, float scale, void* O,
+                          int ldo, void* workspace, size_t workspace_bytes, void* stream);
 /* row-major f32 -> bf16 with leading dimensions (cols % 4 == 0). */
 int i4d_f32_to_bf16(const float* X, int ldx, void* Y, int ldy, int rows, int cols, void* stream);
 

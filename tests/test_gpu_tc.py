@@ -123,3 +123,58 @@ def test_lightglue_bf16_matches_reference(golden_dir):
     iou = len(a & b) / max(1, len(a | b))
     print("LightGlue bf16 tensor-core match IoU vs reference:", iou, len(a), len(b))
     assert iou >= 0.99, iou
+
+
+@pytest.mark.parametrize("n0,n1,p0,p1", [(300, 200, 512, 256), (1000, 777, 1024, 1024), (2300, 2050, 2304, 2560), (129, 1, 256, 256)])
+def test_attention_tc_device_side_key_counts(tc, n0, n1, p0, p1):
+    """Shape buckets: the launch runs at the padded sizes (p0, p1), the real key counts are read on the device.  Real query rows
+    must equal the exact-size launch (padding keys hold large garbage, they must not leak; blocks with no real key at all and
+    stream-K segments that start in one are covered by the larger cases)."""
+    gen = torch.Generator().manual_seed(n0 * 5 + n1)
+    X = (torch.randn(p0 + p1, 768, generator=gen) * 1.5).bfloat16()
+    X[n0:p0] = 50.0                                                  # padding rows: would dominate every softmax if they leaked
+    X[p0 + n1:] = -50.0
+    q, k, v = X[:, :256], X[:, 256:512], X[:, 512:]
+    Xd = X.cuda()
+    out = torch.zeros(p0 + p1, 256, device="cuda", dtype=torch.bfloat16)
+    counts = torch.tensor([n0, n1, n1, n0], device="cuda", dtype=torch.int32)
+    tc.attention_tc(Xd, [(0, p0, 0, p0), (p0, p1, p0, p1)], out, 0, 256, 512, key_counts=counts[:2])
+    ref = torch.cat([_attn_ref(q[:n0], k[:n0], v[:n0]), _attn_ref(q[p0:p0 + n1], k[p0:p0 + n1], v[p0:p0 + n1])])
+    got = torch.cat([out[:n0], out[p0:p0 + n1]]).cpu().double()
+    assert torch.isfinite(out.float()).all()
+    assert (got - ref).abs().max().item() < 0.03
+    out.zero_()
+    tc.attention_tc(Xd, [(0, p0, p0, p1), (p0, p1, 0, p0)], out, 0, 256, 512, key_counts=counts[2:])
+    ref = torch.cat([_attn_ref(q[:n0], k[p0:p0 + n1], v[p0:p0 + n1]), _attn_ref(q[p0:p0 + n1], k[:n0], v[:n0])])
+    got = torch.cat([out[:n0], out[p0:p0 + n1]]).cpu().double()
+    assert torch.isfinite(out.float()).all()
+    assert (got - ref).abs().max().item() < 0.03
+
+
+def test_superglue_graph_buckets_serve_uneven_keypoint_counts(tc):
+    """Tiles of real images have different keypoint counts: the CUDA-graph path is keyed on 256-keypoint buckets and must give
+    what the eager schedule gives at the exact sizes (same kernels; only the stream-K split of the attention differs)."""
+    from icepy4d_b200 import weights
+    from icepy4d_b200.matching.superglue import SuperGlueWeights
+    w = SuperGlueWeights(weights.make_superglue_state(2), "cuda")
+    net = tc.SuperGlueTensorCore(w, "cuda")
+    assert net.use_graphs
+    gen = torch.Generator().manual_seed(4)
+    sizes = [(1500, 1301), (1410, 1290), (1536, 1280), (1281, 1025)]       # the first three share the (1536, 1536) / (1536, 1280) buckets
+    for rep in range(2):
+        for n0, n1 in sizes:
+            d0 = torch.nn.functional.normalize(torch.randn(n0, 256, generator=gen), dim=1).cuda()
+            d1 = torch.nn.functional.normalize(torch.randn(n1, 256, generator=gen), dim=1).cuda()
+            got = net.gnn_and_scores(d0, d1).clone()
+            type(net).use_graphs = False
+            try:
+                ref = net.gnn_and_scores(d0, d1).clone()
+            finally:
+                type(net).use_graphs = True
+            assert got.shape == ref.shape == (n0, n1)
+            err = (got - ref).abs().max().item()
+            assert err < 2e-2 * max(1.0, ref.abs().max().item()), (n0, n1, rep, err)
+            assert (got.argmax(1) == ref.argmax(1)).float().mean().item() > 0.995
+    graphs = [k for k, v in net._graphs.items() if isinstance(v, dict)]
+    assert len(graphs) >= 2, "bucketed graphs were not captured"
+    assert all(k[0] % 256 == 0 and k[1] % 256 == 0 for k in graphs)
