@@ -297,6 +297,75 @@ def golden_helmert():
     print("helmert: scale", np.cbrt(np.linalg.det(T[:3, :3])), "params", prm)
 
 
+def golden_containers():
+    """core/features.py:208-632, core/points.py:172-514 and io/export2bundler.py:90-172 run from the reference itself: the
+    Features / Points fill (`append_*_from_numpy`), their read-out and filters, and the Bundler .out file for a two-camera epoch."""
+    ref_shims.install_shims()
+    import tempfile
+    from icepy4d.core import Camera, Features, Points
+    from icepy4d.io.export2bundler import write_bundler_out
+
+    rng = np.random.default_rng(33)
+    n = 240
+    x, y = rng.uniform(1, 6000, n).astype(np.float32), rng.uniform(1, 4000, n).astype(np.float32)
+    descr = rng.normal(size=(128, n)).astype(np.float32)
+    scores = rng.uniform(0, 1, n).astype(np.float32)
+    out = {"x": x, "y": y, "descr": descr, "scores": scores}
+    f = Features()
+    f.append_features_from_numpy(x[:160], y[:160], descr[:, :160], scores[:160], epoch=3)
+    ids2 = [int(i) for i in range(1000, 1080)]
+    f.append_features_from_numpy(x[160:], y[160:], descr[:, 160:], scores[160:], track_ids=ids2, epoch=3)
+    out["f_len"], out["f_last"] = np.array(len(f)), np.array(f.last_track_id)
+    out["f_ids"] = np.array(f.get_track_ids())
+    d = f.to_numpy(get_descr=True, get_score=True)
+    out["f_kpts"], out["f_descr"], out["f_scores"] = d["kpts"], d["descr"], d["scores"]
+    one = f[1005]
+    out["f_1005"] = np.concatenate([one.xy.reshape(-1), [one.score], one.descr.reshape(-1)[:4], [one.track_id], [one.epoch]]).astype(np.float64)
+    out["f_1005_descr_shape"] = np.array(one.descr.shape)
+    # duplicate ids -> progressive ids
+    f.append_features_from_numpy(x[:5], y[:5], descr[:, :5], scores[:5], track_ids=[0, 1, 2, 3, 4])
+    out["f_ids_dup"] = np.array(f.get_track_ids())
+    mask = rng.uniform(size=len(f)) < 0.6
+    f.filter_feature_by_mask(list(mask))
+    out["mask"], out["f_ids_masked"], out["f_kpts_masked"] = mask, np.array(f.get_track_ids()), f.kpts_to_numpy()
+    keep = [int(i) for i in np.array(f.get_track_ids())[::3]]
+    f.filter_feature_by_index(keep)
+    out["f_ids_indexed"], out["f_scores_indexed"] = np.array(f.get_track_ids()), f.scores_to_numpy()
+    out["f_contains"] = np.array([keep[0] in f, 999999 in f])
+
+    m = 200
+    fa, fb = Features(), Features()
+    fa.append_features_from_numpy(x[:m], y[:m], descr[:, :m], scores[:m])
+    fb.append_features_from_numpy(x[:m] - rng.uniform(5, 40, m).astype(np.float32), y[:m] + rng.normal(0, 1, m).astype(np.float32),
+                                  descr[:, :m], scores[:m])
+    out["fb_kpts"] = fb.kpts_to_numpy()
+    xyz = rng.uniform(-300, 300, (m, 3))
+    colors = rng.uniform(0, 1, (m, 3))
+    pts = Points()
+    pts.append_points_from_numpy(xyz[:120], colors=colors[:120])
+    pts.append_points_from_numpy(xyz[120:], track_ids=[int(i) for i in range(120, m)], colors=colors[120:])
+    out["xyz"], out["colors"] = xyz, colors
+    out["p_xyz"], out["p_col"], out["p_col8"] = pts.to_numpy(), pts.colors_to_numpy(), pts.colors_to_numpy(as_uint8=True)
+    out["p_ids"], out["p_last"] = np.array(pts.get_track_ids()), np.array(pts.last_track_id)
+    sc = synthetic.two_view_scene(n=8, seed=0, outlier_frac=0.0)["cams"]
+    cams = {"cam1": Camera(6012, 4008, K=sc[0].K.copy(), dist=sc[0].dist.copy(), R=sc[0].R.copy(), t=sc[0].t.copy()),
+            "cam2": Camera(6012, 4008, K=sc[1].K.copy(), dist=sc[1].dist.copy(), R=sc[1].R.copy(), t=sc[1].t.copy())}
+
+    class _Img:
+        def __init__(self, path):
+            self.path = path
+    with tempfile.TemporaryDirectory() as td:
+        write_bundler_out(td, "epoch", {"cam1": _Img("/data/cam1/a.jpg"), "cam2": _Img("/data/cam2/a.jpg")}, cams,
+                          {"cam1": fa, "cam2": fb}, pts)
+        out["bundler_out"] = np.frombuffer(open(os.path.join(td, "epoch.out"), "rb").read(), dtype=np.uint8)
+        out["bundler_imlist"] = np.frombuffer(open(os.path.join(td, "im_list.txt"), "rb").read(), dtype=np.uint8)
+    pmask = rng.uniform(size=m) < 0.5
+    pts.filter_point_by_mask(pmask)
+    out["pmask"], out["p_ids_masked"], out["p_last_masked"] = pmask, np.array(pts.get_track_ids()), np.array(pts.last_track_id)
+    np.savez_compressed(os.path.join(OUT, "containers.npz"), **out)
+    print("containers: features", out["f_len"], "points", len(out["p_xyz"]), "bundler bytes", len(out["bundler_out"]))
+
+
 if __name__ == "__main__":
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -315,3 +384,4 @@ if __name__ == "__main__":
     golden_matchers()
     golden_preselection()
     golden_helmert()
+    golden_containers()

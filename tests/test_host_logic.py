@@ -132,3 +132,72 @@ def test_product_fails_loudly_without_gpu():
         SuperGlueMatcher({"weights": "outdoor", "keypoint_threshold": 0.001, "max_keypoints": 128, "match_threshold": 0.2,
                           "force_cpu": False, "superpoint_state": weights.make_superpoint_state(1),
                           "superglue_state": weights.make_superglue_state(2)})
+
+
+def test_features_points_containers_and_bundler_vs_reference(golden_dir, tmp_path):
+    """the array-backed Features / Points containers and the Bundler exporter against what the reference's own
+    classes (core/features.py, core/points.py, io/export2bundler.py) produced for the same seeded inputs
+    (oracle/make_golden.py::golden_containers): same track ids (incl. the duplicate-id fallback), same arrays, same filters,
+    and a byte-identical .out file."""
+    from icepy4d_b200 import synthetic
+    from icepy4d_b200.core import Feature, Features, Points
+    from icepy4d_b200.io import write_bundler_out
+
+    g = np.load(os.path.join(golden_dir, "containers.npz"))
+    x, y, descr, scores = g["x"], g["y"], g["descr"], g["scores"]
+    f = Features()
+    f.append_features_from_numpy(x[:160], y[:160], descr[:, :160], scores[:160], epoch=3)
+    f.append_features_from_numpy(x[160:], y[160:], descr[:, 160:], scores[160:], track_ids=[int(i) for i in range(1000, 1080)], epoch=3)
+    assert len(f) == int(g["f_len"]) and int(f.last_track_id) == int(g["f_last"]) and f.num_features == len(f)
+    assert np.array_equal(np.array(f.get_track_ids()), g["f_ids"])
+    d = f.to_numpy(get_descr=True, get_score=True)
+    for k, ref in (("kpts", "f_kpts"), ("descr", "f_descr"), ("scores", "f_scores")):
+        assert d[k].dtype == np.float32 and np.array_equal(d[k], g[ref]), k
+    assert set(f.to_numpy(get_score=True)) == {"kpts"}                       # the reference returns scores only with the descriptors
+    one = f[1005]
+    assert isinstance(one, Feature) and one.descr.shape == tuple(g["f_1005_descr_shape"]) and one.xy.shape == (1, 2)
+    got = np.concatenate([one.xy.reshape(-1), [one.score], one.descr.reshape(-1)[:4], [one.track_id], [one.epoch]]).astype(np.float64)
+    assert np.array_equal(got, g["f_1005"])
+    assert isinstance(one.track_id, np.int32) and f[999999] is None
+    assert [ft.track_id for _, ft in zip(range(3), f)] == [0, 1, 2]
+    f.append_features_from_numpy(x[:5], y[:5], descr[:, :5], scores[:5], track_ids=[0, 1, 2, 3, 4])      # duplicates -> progressive ids
+    assert np.array_equal(np.array(f.get_track_ids()), g["f_ids_dup"])
+    f.filter_feature_by_mask(list(g["mask"]))
+    assert np.array_equal(np.array(f.get_track_ids()), g["f_ids_masked"]) and np.array_equal(f.kpts_to_numpy(), g["f_kpts_masked"])
+    keep = [int(i) for i in np.array(f.get_track_ids())[::3]]
+    f.filter_feature_by_index(keep)
+    assert np.array_equal(np.array(f.get_track_ids()), g["f_ids_indexed"]) and np.array_equal(f.scores_to_numpy(), g["f_scores_indexed"])
+    assert np.array_equal(np.array([keep[0] in f, 999999 in f]), g["f_contains"])
+    assert f.get_features_as_dict(get_track_id=True)["descriptors0"].shape == (128, len(f))
+    with pytest.raises(AssertionError):
+        f.append_features_from_numpy(x[:3], y[:3], np.zeros((256, 3), np.float32))                        # descriptor size mismatch
+    with pytest.raises(ValueError):
+        Features().append_features_from_numpy(x[:3].astype(np.float16), y[:3])
+    e = Features()
+    e.append_features_from_numpy(np.zeros(4, np.float32), np.zeros(4, np.float32))                        # `if not np.any(x)`: nothing done
+    assert len(e) == 0 and e.last_track_id == -1
+
+    m = 200
+    fa, fb = Features(), Features()
+    fa.append_features_from_numpy(x[:m], y[:m], descr[:, :m], scores[:m])
+    kb = g["fb_kpts"]
+    fb.append_features_from_numpy(kb[:, 0].copy(), kb[:, 1].copy(), descr[:, :m], scores[:m])
+    pts = Points()
+    pts.append_points_from_numpy(g["xyz"][:120], colors=g["colors"][:120])
+    pts.append_points_from_numpy(g["xyz"][120:], track_ids=[int(i) for i in range(120, m)], colors=g["colors"][120:])
+    assert np.array_equal(pts.to_numpy(), g["p_xyz"]) and np.array_equal(pts.colors_to_numpy(), g["p_col"])
+    assert np.array_equal(pts.colors_to_numpy(as_uint8=True), g["p_col8"]) and np.array_equal(np.array(pts.get_track_ids()), g["p_ids"])
+    assert int(pts.last_track_id) == int(g["p_last"]) and np.array_equal(pts[7].coordinates, g["p_xyz"][7])
+
+    class Cam:
+        width, height = 6012, 4008
+
+        def __init__(self, c):
+            self.K, self.dist, self.R, self.t = c.K, c.dist, c.R, c.t
+    sc = synthetic.two_view_scene(n=8, seed=0, outlier_frac=0.0)["cams"]
+    assert write_bundler_out(tmp_path, "epoch", {"cam1": "/data/cam1/a.jpg", "cam2": "/data/cam2/a.jpg"},
+                             {"cam1": Cam(sc[0]), "cam2": Cam(sc[1])}, {"cam1": fa, "cam2": fb}, pts) is True
+    assert open(tmp_path / "epoch.out", "rb").read() == g["bundler_out"].tobytes()
+    assert open(tmp_path / "im_list.txt", "rb").read() == g["bundler_imlist"].tobytes()
+    pts.filter_point_by_mask(g["pmask"])
+    assert np.array_equal(np.array(pts.get_track_ids()), g["p_ids_masked"]) and int(pts.last_track_id) == int(g["p_last_masked"])
