@@ -42,6 +42,15 @@ ms = timeit(lambda: ops.row_lse(S, 1.0, v)); res["row_lse 8192^2"] = (ms, f"{N*N
 ms = timeit(lambda: ops.col_lse(S, 1.0, u, ws)); res["col_lse 8192^2 (partial+combine)"] = (ms, f"{N*N*4/ms/1e6:.0f} GB/s")
 ms = timeit(lambda: ops.sinkhorn(S, 1.0, 10, ws), reps=5); res["sinkhorn 10 iters 8192^2"] = (ms, f"{ms/10*1000:.1f} us/iter, {2*N*N*4*10/ms/1e6:.0f} GB/s algorithmic")
 ms = timeit(lambda: ops.sg_assign(S, 1.0, 100, 0.2, ws), reps=3, warm=1); res["sg_assign 100 iters 8192^2"] = (ms, f"{ms/100*1000:.1f} us/iter")
+ms = timeit(lambda: ops.sg_assign(S, 1.0, 0, 0.2, ws)); res["sg_assign 0 iters 8192^2 (row+col arg-max in one read, mutual NN)"] = (ms, f"{N*N*4/ms/1e6:.0f} GB/s on one read")
+z0 = torch.randn(N, device=dev); z1 = torch.randn(N, device=dev)
+ms = timeit(lambda: ops.lg_assign(S, z0, z1, 0.1, ws)); res["lg_assign 8192^2 (double softmax + mutual NN, two reads of sim)"] = (ms, f"{2*N*N*4/ms/1e6:.0f} GB/s on two reads")
+if os.environ.get("KB_LG16K", "1") == "1":
+    N2 = 16384
+    S2 = torch.randn(N2, N2, device=dev); ws2 = ops.AssignWorkspace(N2, N2, S2.device)
+    z0 = torch.randn(N2, device=dev); z1 = torch.randn(N2, device=dev)
+    ms = timeit(lambda: ops.lg_assign(S2, z0, z1, 0.1, ws2), reps=5); res["lg_assign 16384^2 (two reads of sim)"] = (ms, f"{2*N2*N2*4/ms/1e6:.0f} GB/s on two reads")
+    del S2, ws2
 # superpoint
 i0, _ = synthetic.stereo_pair(1999, 1999, seed=1, channels=1)
 img = torch.tensor(i0 / 255.0, dtype=torch.float)[None, None].cuda()

@@ -296,6 +296,28 @@ def test_lg_assign(ops, M, N):
         assert torch.allclose(s0, rs0, atol=1e-4) and torch.allclose(s1, rs1, atol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,spread", [(700, 513, False), (1030, 2051, True), (129, 640, True)])
+def test_lg_assign_one_read_passes_and_their_exact_fallback(ops, M, N, spread):
+    """The double softmax reads `sim` twice in total (row + column LSE in one pass, row + column arg-max in another).  With
+    `spread`, one column and one row sit 200 nats below everything else: the shared-exponential column sums of the LSE pass
+    underflow there, the device flag goes up and the exact two-pass kernels redo the LSE — the result must still be torch's."""
+    gen = torch.Generator().manual_seed(M + 7 * N)
+    sim = torch.randn(M, N, generator=gen) * 3
+    for i in range(0, min(M, N), 3):
+        sim[i, (i * 5) % N] += 15.0
+    if spread:
+        sim[:, N // 3] -= 200.0
+        sim[M // 2, :] -= 200.0
+    z0, z1 = torch.randn(M, 1, generator=gen) * 3, torch.randn(N, 1, generator=gen) * 3
+    F = torch.nn.functional
+    P = sim.new_zeros(M + 1, N + 1)
+    P[:M, :N] = (F.log_softmax(sim.double(), 1) + F.log_softmax(sim.double(), 0) + F.logsigmoid(z0.double()) + F.logsigmoid(z1.double()).t()).float()
+    r0, r1, rs0, rs1 = sg_oracle.mutual_nn(P, 0.1)
+    m0, m1, s0, s1 = (t.cpu() for t in ops.lg_assign(_pitched(ops, sim), z0.cuda(), z1.cuda(), 0.1))
+    assert torch.equal(m0.long(), r0) and torch.equal(m1.long(), r1)
+    assert torch.allclose(s0, rs0, atol=1e-4) and torch.allclose(s1, rs1, atol=1e-4)
+
+
 # ------------------------------------------------------------------ geometry
 def test_undistort_bit_exact_vs_opencv(ops):
     sc = synthetic.two_view_scene(n=20000, seed=3)
