@@ -72,7 +72,7 @@ struct AttnParams {
   const int* nk_dev;                   // optional: per problem, how many of the nk keys are real (device memory; the rest is masked)
 };
 
-#define FA_DEFAULT_POLY 0
+#define FA_DEFAULT_POLY 25                      // a quarter of the exponentials on the FMA pipe: 1-4 % faster than all-MUFU on every box measured (profiles/r2_attn_experiments.txt)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
