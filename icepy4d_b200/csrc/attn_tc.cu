@@ -72,6 +72,19 @@ struct AttnParams {
   const int* nk_dev;                   // optional: per problem, how many of the nk keys are real (device memory; the rest is masked)
 };
 
+// Timeline instrumentation (scripts/attn_trace.py builds a second library with -DFA_TRACE): CTA 0 records %clock64 at the
+// synchronisation points of one softmax warp per tile for its first FA_TRACE_MAX key blocks.
+#ifdef FA_TRACE
+#define FA_TRACE_MAX 96
+__device__ unsigned long long fa_trace_buf[2][FA_TRACE_MAX][8];
+#define FA_STAMP(k) do { if (blockIdx.x == 0 && (sw & 7) == 0 && lane == 0 && bb + jj < FA_TRACE_MAX) { unsigned long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); fa_trace_buf[t][bb + jj][k] = c_; } } while (0)
+extern "C" __attribute__((visibility("default"))) int i4d_attention_trace_dump(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, fa_trace_buf, sizeof(fa_trace_buf));
+}
+#else
+#define FA_STAMP(k) do { } while (0)
+#endif
 #define FA_DEFAULT_POLY 25                      // a quarter of the exponentials on the FMA pipe: 1-4 % faster than all-MUFU on every box measured (profiles/r2_attn_experiments.txt)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -321,7 +334,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       if (tile_valid) {
         for (int jj = 0; jj < nb; ++jj) {
           const uint32_t ph = (bb + (uint32_t)jj) & 1u;
+          FA_STAMP(0);
           tc::mbar_wait(&s_full[t], ph);
+          FA_STAMP(1);
           tc::tcgen05_fence_after();
           uint32_t v[64];
           tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
@@ -339,7 +354,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           for (int i = 0; i < 64; i += 2) mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
           float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
           xch[t][ph][hf][q] = mx;
+          FA_STAMP(2);
           named_bar_sync(pair_bar, 64);                                       // the two warps that share this lane quarter
+          FA_STAMP(3);
           mx = fmaxf(mx, xch[t][ph][hf ^ 1][q]);
           const float m_blk = mx * p.scale_log2;
           // lazy running maximum: move only when the block exceeds it by more than 2^TAU (both partner threads decide alike)
@@ -347,6 +364,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           const float m_new = (jj == 0 || need) ? fmaxf(m_blk, -1e30f) : m_run;   // finite even if the block holds no real key
           if (jj > 0) {
             tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
+            FA_STAMP(4);
             if (__any_sync(0xffffffffu, need)) {
               tc::tcgen05_fence_after();
               const float alpha = need ? ex2_approx(m_run - m_new) : 1.f;     // O_t and the row sum are relative to m_run
@@ -384,9 +402,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
             if ((tt & 3) == 3) tmem_st16(tP + (tt >> 2) * 16, pk);
           }
           l_part += rs2.x + rs2.y;
+          FA_STAMP(5);
           tmem_st_wait();
           tc::tcgen05_fence_before();
           tc::mbar_arrive(&p_full[t]);
+          FA_STAMP(6);
         }
         // ---- row sum of both halves, O_t (my 32 dims) into registers
         lsum_s[t][hf][q] = l_part;
