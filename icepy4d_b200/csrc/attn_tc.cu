@@ -56,6 +56,21 @@
 // polynomial, relative error 7.7e-5 — far below the bf16 rounding of P): bit e of the mask selects pair e of every 8-element
 // chunk; even / odd chunks use the low / high nibble.  0x100 = no exponential at all (timing experiments only).
 
+// Two measured-and-rejected variants stay behind compile-time switches (numbers in profiles/r2_attn_experiments.txt, session 3):
+//   -DFA_WARP_ARRIVE   softmax-side mbarrier arrivals by one lane per warp instead of every thread: the two tiles then run their
+//                      exponential phases TOGETHER (and idle the MUFU pipe together): 209 us against 196-203
+//   -DFA_TURNS=1       explicit turn-taking of the two tiles on the MUFU pipe (A(n), B(n), A(n+1), ...): the phases alternate as
+//                      intended, but the loads / row maxima of one tile now compete with the other's exponentials: 216 us
+#ifdef FA_WARP_ARRIVE
+#define FA_ARRIVALS 8
+#define FA_ARRIVE(bar) do { __syncwarp(); if (lane == 0) tc::mbar_arrive(bar); } while (0)
+#else
+#define FA_ARRIVALS 256
+#define FA_ARRIVE(bar) tc::mbar_arrive(bar)
+#endif
+#ifndef FA_TURNS
+#define FA_TURNS 0
+#endif
 struct AttnProblem { int q_row0, nq, k_row0, nk; };
 struct AttnParams {
   AttnProblem prob[FA_MAX_PROBLEMS];
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   uint8_t* sK = sQ + 2 * FA_Q_BYTES;                               // K ring: stage s at sK + s*16K
   uint8_t* sV = sK + FA_KV_STAGES * FA_KV_BYTES;                   // V ring
   __shared__ __align__(8) uint64_t q_full, k_full[FA_KV_STAGES], k_empty[FA_KV_STAGES], v_full[FA_KV_STAGES], v_empty[FA_KV_STAGES];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], pv_done[2], turn[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int merge_flag_s;
   __shared__ float lsum_s[2][2][FA_BM];                            // [tile][column half][row]: row sums for the final exchange
@@ -201,8 +216,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < 2; ++t) {
-      tc::mbar_init(&s_full[t], 1); tc::mbar_init(&s_empty[t], 256); tc::mbar_init(&p_full[t], 256);
-      tc::mbar_init(&pv_done[t], 1);
+      tc::mbar_init(&s_full[t], 1); tc::mbar_init(&s_empty[t], FA_ARRIVALS); tc::mbar_init(&p_full[t], FA_ARRIVALS);
+      tc::mbar_init(&pv_done[t], 1); tc::mbar_init(&turn[t], FA_ARRIVALS);
     }
     tc::fence_barrier_init();
   }
@@ -213,6 +228,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   const uint32_t tmem = tmem_base_s;
 
   uint32_t seg = 0, kv_base = 0, blk_base[2] = {0u, 0u};           // segments / K-V blocks / blocks per tile processed so far
+  uint32_t turn_base = 0;                                          // key blocks of segments in which BOTH tiles ran (MUFU turn-taking)
   for (long long u = u_begin; u < u_end;) {
     // ---- this segment: item (z, h, qt), key blocks [kb0, kb1) ----
     int z = 0;
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
           tc::tmem_ld_wait();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&s_empty[t]);                                       // QK_t(jj + 1) may overwrite the score buffer now
+          FA_ARRIVE(&s_empty[t]);                                       // QK_t(jj + 1) may overwrite the score buffer now
           const int kvalid = pr.nk - (kb0 + jj) * FA_BN - hf * 64;            // keys of my half that exist
           if (kvalid < 64) {                                                  // only in the problem's last block
 #pragma unroll
@@ -386,6 +402,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           float2 rs2 = make_float2(0.f, 0.f);
           const float2 nm2 = make_float2(-m_new, -m_new);
           uint32_t pk[16];
+          // experiment (off): the two tiles take turns on the SM's MUFU pipe, A(n), B(n), A(n+1), ...
+          if (FA_TURNS && validB) {
+            const uint32_t n = turn_base + (uint32_t)jj;
+            if (t == 1) tc::mbar_wait(&turn[0], n & 1u);                      // A finished its n-th exponential phase
+            else if (n > 0) tc::mbar_wait(&turn[1], (n - 1u) & 1u);           // B finished its (n-1)-th
+          }
 #pragma unroll
           for (int tt = 0; tt < 8; ++tt) {
 #pragma unroll
@@ -402,10 +424,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
             if ((tt & 3) == 3) tmem_st16(tP + (tt >> 2) * 16, pk);
           }
           l_part += rs2.x + rs2.y;
+          if (FA_TURNS && validB) FA_ARRIVE(&turn[t]);                        // the pipe is the other tile's
           FA_STAMP(5);
           tmem_st_wait();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&p_full[t]);
+          FA_ARRIVE(&p_full[t]);
           FA_STAMP(6);
         }
         // ---- row sum of both halves, O_t (my 32 dims) into registers
@@ -478,7 +501,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
       }
     }
     u = item_start + kb1;
-    ++seg; kv_base += (uint32_t)nb; blk_base[0] += (uint32_t)nb; if (validB) blk_base[1] += (uint32_t)nb;
+    ++seg; kv_base += (uint32_t)nb; blk_base[0] += (uint32_t)nb; if (validB) { blk_base[1] += (uint32_t)nb; turn_base += (uint32_t)nb; }
     // ---- next segment: the softmax groups have O_t in registers (they waited for the last PV), Q / O / P may be overwritten
     tc::tcgen05_fence_before();
     __syncthreads();
