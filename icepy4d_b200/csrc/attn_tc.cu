@@ -68,6 +68,12 @@
 #define FA_ARRIVALS 256
 #define FA_ARRIVE(bar) tc::mbar_arrive(bar)
 #endif
+#ifndef FA_SOFTMAX_REGS
+#define FA_SOFTMAX_REGS 104             // 0 = no setmaxnreg (every thread keeps the 96 registers of the launch)
+#endif
+#ifndef FA_ISSUER_REGS
+#define FA_ISSUER_REGS 40
+#endif
 #ifndef FA_TURNS
 #define FA_TURNS 0
 #endif
@@ -187,6 +193,37 @@ __device__ __forceinline__ int fa_cta_of_unit(const AttnParams& p, long long u) 
   return (int)(((u + 1) * p.n_ctas + total - 1) / total) - 1;
 }
 
+// ---- one segment of this CTA's unit range: item (z, h, qt), key blocks [kb0, kb1).  Every role runs its own copy of the segment
+// loop (the role branches never re-join, so each keeps the register budget setmaxnreg gave it); the loops stay in step through
+// the block-wide barrier at the end of every segment.
+#define FA_SEGMENT_DECODE \
+    int z = 0; \
+    _Pragma("unroll") \
+    for (int i = 1; i < FA_MAX_PROBLEMS; ++i) \
+      if (u >= p.unit_off[i] && p.unit_off[i] < p.unit_off[FA_MAX_PROBLEMS]) z = i; \
+    AttnProblem pr = p.prob[0]; \
+    int nblk = p.nblk[0], n_qt = p.n_qt[0], uoff = p.unit_off[0], ioff = p.item_off[0]; \
+    _Pragma("unroll") \
+    for (int i = 1; i < FA_MAX_PROBLEMS; ++i) \
+      if (z == i) { pr = p.prob[i]; nblk = p.nblk[i]; n_qt = p.n_qt[i]; uoff = p.unit_off[i]; ioff = p.item_off[i]; } \
+    if (p.nk_dev != nullptr) pr.nk = min(pr.nk, __ldg(p.nk_dev + z)); \
+    const int r = (int)(u - uoff), it = r / nblk, kb0 = r - it * nblk; \
+    const long long item_start = (long long)uoff + (long long)it * nblk; \
+    const int kb1 = (int)min((long long)nblk, (long long)kb0 + (u_end - u)); \
+    const int nb = kb1 - kb0; \
+    const bool whole = kb0 == 0 && kb1 == nblk; \
+    const int h = it / n_qt, qt = it - h * n_qt; \
+    const int q0 = qt * (2 * FA_BM); \
+    const bool validB = q0 + FA_BM < pr.nq; \
+    const int slot = (u == u_begin) ? 0 : 1;
+// next segment: the softmax groups have O_t in registers (they waited for the last PV), Q / O / P may be overwritten
+#define FA_SEGMENT_ADVANCE \
+    u = item_start + kb1; \
+    ++seg; kv_base += (uint32_t)nb; blk_base[0] += (uint32_t)nb; if (validB) { blk_base[1] += (uint32_t)nb; turn_base += (uint32_t)nb; } \
+    tc::tcgen05_fence_before(); \
+    __syncthreads(); \
+    tc::tcgen05_fence_after();
+
 template <int POLY_MASK>
 __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmX, AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -229,283 +266,279 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
 
   uint32_t seg = 0, kv_base = 0, blk_base[2] = {0u, 0u};           // segments / K-V blocks / blocks per tile processed so far
   uint32_t turn_base = 0;                                          // key blocks of segments in which BOTH tiles ran (MUFU turn-taking)
-  for (long long u = u_begin; u < u_end;) {
-    // ---- this segment: item (z, h, qt), key blocks [kb0, kb1) ----
-    int z = 0;
-#pragma unroll
-    for (int i = 1; i < FA_MAX_PROBLEMS; ++i)
-      if (u >= p.unit_off[i] && p.unit_off[i] < p.unit_off[FA_MAX_PROBLEMS]) z = i;
-    AttnProblem pr = p.prob[0];
-    int nblk = p.nblk[0], n_qt = p.n_qt[0], uoff = p.unit_off[0], ioff = p.item_off[0];
-#pragma unroll
-    for (int i = 1; i < FA_MAX_PROBLEMS; ++i)
-      if (z == i) { pr = p.prob[i]; nblk = p.nblk[i]; n_qt = p.n_qt[i]; uoff = p.unit_off[i]; ioff = p.item_off[i]; }
-    // keys beyond the device-side count are padding of a shape bucket: masked like the ragged tail of the last block
-    if (p.nk_dev != nullptr) pr.nk = min(pr.nk, __ldg(p.nk_dev + z));
-    const int r = (int)(u - uoff), it = r / nblk, kb0 = r - it * nblk;
-    const long long item_start = (long long)uoff + (long long)it * nblk;
-    const int kb1 = (int)min((long long)nblk, (long long)kb0 + (u_end - u));
-    const int nb = kb1 - kb0;
-    const bool whole = kb0 == 0 && kb1 == nblk;
-    const int h = it / n_qt, qt = it - h * n_qt;
-    const int q0 = qt * (2 * FA_BM);
-    const bool validB = q0 + FA_BM < pr.nq;                         // tile A always has rows
-    const int slot = (u == u_begin) ? 0 : 1;
+  // Register re-partition: the producer / issuer warpgroup (warps 0-3) hands registers to the four softmax warpgroups
+  // (96 -> FA_SOFTMAX_REGS per thread): the softmax loop keeps its barrier / exchange addresses in registers instead of
+  // recomputing them in every key block.
+  if (warp < 4) {
+#if FA_SOFTMAX_REGS
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA_ISSUER_REGS));   // (96 - 40) x 128 registers freed >= (104 - 96) x 512 taken
+#endif
     if (warp == 0) {
-      // ------------------------------------------------ TMA producer
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(&q_full, validB ? 2 * FA_Q_BYTES : FA_Q_BYTES);
-        tc::tma_load_2d(sQ, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0);
-        if (validB) tc::tma_load_2d(sQ + FA_Q_BYTES, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0 + FA_BM);
-        auto load_k = [&](int jj) {
-          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
-          tc::mbar_wait(&k_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(&k_full[s], FA_KV_BYTES);
-          tc::tma_load_2d(sK + s * FA_KV_BYTES, &tmX, &k_full[s], p.k_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
-        };
-        auto load_v = [&](int jj) {
-          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
-          tc::mbar_wait(&v_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(&v_full[s], FA_KV_BYTES);
-          tc::tma_load_2d(sV + s * FA_KV_BYTES, &tmX, &v_full[s], p.v_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
-        };
-        for (int jj = 0; jj < FA_KV_STAGES && jj < nb; ++jj) load_k(jj);
-        for (int jj = 0; jj < nb; ++jj) {
-          load_v(jj);
-          if (jj + FA_KV_STAGES < nb) load_k(jj + FA_KV_STAGES);
-        }
+      for (long long u = u_begin; u < u_end;) {
+        FA_SEGMENT_DECODE
+          // ------------------------------------------------ TMA producer
+          if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(&q_full, validB ? 2 * FA_Q_BYTES : FA_Q_BYTES);
+            tc::tma_load_2d(sQ, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0);
+            if (validB) tc::tma_load_2d(sQ + FA_Q_BYTES, &tmX, &q_full, p.q_col + h * FA_D, pr.q_row0 + q0 + FA_BM);
+            auto load_k = [&](int jj) {
+              const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
+              tc::mbar_wait(&k_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
+              tc::mbar_arrive_expect_tx(&k_full[s], FA_KV_BYTES);
+              tc::tma_load_2d(sK + s * FA_KV_BYTES, &tmX, &k_full[s], p.k_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
+            };
+            auto load_v = [&](int jj) {
+              const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
+              tc::mbar_wait(&v_empty[s], ((g / FA_KV_STAGES) & 1u) ^ 1u);
+              tc::mbar_arrive_expect_tx(&v_full[s], FA_KV_BYTES);
+              tc::tma_load_2d(sV + s * FA_KV_BYTES, &tmX, &v_full[s], p.v_col + h * FA_D, pr.k_row0 + (kb0 + jj) * FA_BN);
+            };
+            for (int jj = 0; jj < FA_KV_STAGES && jj < nb; ++jj) load_k(jj);
+            for (int jj = 0; jj < nb; ++jj) {
+              load_v(jj);
+              if (jj + FA_KV_STAGES < nb) load_k(jj + FA_KV_STAGES);
+            }
+          }
+          __syncwarp();
+        FA_SEGMENT_ADVANCE
       }
-      __syncwarp();
-    } else if (warp == 1 || (warp == 2 && validB)) {
-      // ------------------------------------------------ MMA issuers: warp 1 drives tile A, warp 2 tile B (one elected lane each;
-      // operands stay in uniform registers).  The tiles share nothing but the K / V stages, so neither issuer ever waits for the
-      // other tile's softmax group: S_t(j+1) is issued the moment the group has S_t(j) in registers.
-      if (tc::elect_one()) {
-        const int t = warp - 1;
-        constexpr uint32_t idesc_qk = tc::make_idesc(FA_BM, FA_BN, 0, 0, 1);   // A = Q (K-major), B = K (K-major)
-        constexpr uint32_t idesc_pv = tc::make_idesc(FA_BM, FA_D, 0, 1, 1);    // A = P (TMEM, K-major), B = V (MN-major)
-        constexpr uint32_t hi_k = tc::desc_hi_sw128(1024);                     // K-major operands and MN-major V: SBO = 1024
-        const uint32_t dQ = tc::desc_lo_sw128(tc::smem_u32(sQ)) + (uint32_t)(t * (FA_Q_BYTES >> 4));
-        const uint32_t dK0 = tc::desc_lo_sw128(tc::smem_u32(sK));
-        // V descriptor: MN-major, 8-key groups 1024 B apart (SBO), one 64-wide N atom: LBO field = 1024 >> 4 as well
-        const uint32_t dV0 = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
-        const uint32_t tS = tmem + (uint32_t)t * FA_BN;
-        const uint32_t tO = tmem + FA_TMEM_O + (uint32_t)t * FA_D, tP = tmem + FA_TMEM_P + (uint32_t)t * (FA_BN / 2);
-        const uint32_t bb = blk_base[t];                                      // this tile's block counter at the segment start
-        const bool twice = !validB;                                           // tile A alone: both stage-release arrivals are mine
-        auto issue_qk = [&](int jj) {                                         // S_t = Q_t K_jj^T
-          const uint32_t s = (kv_base + (uint32_t)jj) % FA_KV_STAGES;
-          const uint32_t dK = dK0 + s * (FA_KV_BYTES >> 4);
-#pragma unroll
-          for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tS, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
-          tc::umma_commit(&s_full[t]);
-          tc::umma_commit(&k_empty[s]);
-          if (twice) tc::umma_commit(&k_empty[s]);
-        };
-        tc::mbar_wait(&q_full, seg & 1u);
-        tc::mbar_wait(&k_full[kv_base % FA_KV_STAGES], (kv_base / FA_KV_STAGES) & 1u);
-        tc::tcgen05_fence_after();
-        issue_qk(0);
-        for (int jj = 0; jj < nb; ++jj) {
-          const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
-          if (jj + 1 < nb) {
-            // scores of the NEXT block: the buffer is free as soon as the group has block jj in registers
-            tc::mbar_wait(&k_full[(g + 1) % FA_KV_STAGES], ((g + 1) / FA_KV_STAGES) & 1u);
-            tc::mbar_wait(&s_empty[t], (bb + (uint32_t)jj) & 1u);
+    } else {
+      for (long long u = u_begin; u < u_end;) {
+        FA_SEGMENT_DECODE
+        if (warp == 1 || (warp == 2 && validB)) {
+          // ------------------------------------------------ MMA issuers: warp 1 drives tile A, warp 2 tile B (one elected lane each;
+          // operands stay in uniform registers).  The tiles share nothing but the K / V stages, so neither issuer ever waits for the
+          // other tile's softmax group: S_t(j+1) is issued the moment the group has S_t(j) in registers.
+          if (tc::elect_one()) {
+            const int t = warp - 1;
+            constexpr uint32_t idesc_qk = tc::make_idesc(FA_BM, FA_BN, 0, 0, 1);   // A = Q (K-major), B = K (K-major)
+            constexpr uint32_t idesc_pv = tc::make_idesc(FA_BM, FA_D, 0, 1, 1);    // A = P (TMEM, K-major), B = V (MN-major)
+            constexpr uint32_t hi_k = tc::desc_hi_sw128(1024);                     // K-major operands and MN-major V: SBO = 1024
+            const uint32_t dQ = tc::desc_lo_sw128(tc::smem_u32(sQ)) + (uint32_t)(t * (FA_Q_BYTES >> 4));
+            const uint32_t dK0 = tc::desc_lo_sw128(tc::smem_u32(sK));
+            // V descriptor: MN-major, 8-key groups 1024 B apart (SBO), one 64-wide N atom: LBO field = 1024 >> 4 as well
+            const uint32_t dV0 = ((tc::smem_u32(sV) >> 4) & 0x3FFF) | ((1024u >> 4) << 16);
+            const uint32_t tS = tmem + (uint32_t)t * FA_BN;
+            const uint32_t tO = tmem + FA_TMEM_O + (uint32_t)t * FA_D, tP = tmem + FA_TMEM_P + (uint32_t)t * (FA_BN / 2);
+            const uint32_t bb = blk_base[t];                                      // this tile's block counter at the segment start
+            const bool twice = !validB;                                           // tile A alone: both stage-release arrivals are mine
+            auto issue_qk = [&](int jj) {                                         // S_t = Q_t K_jj^T
+              const uint32_t s = (kv_base + (uint32_t)jj) % FA_KV_STAGES;
+              const uint32_t dK = dK0 + s * (FA_KV_BYTES >> 4);
+    #pragma unroll
+              for (int k = 0; k < FA_D / 16; ++k) tc::umma_f16_parts(tS, dQ + k * 2, hi_k, dK + k * 2, hi_k, idesc_qk, k ? 1u : 0u);
+              tc::umma_commit(&s_full[t]);
+              tc::umma_commit(&k_empty[s]);
+              if (twice) tc::umma_commit(&k_empty[s]);
+            };
+            tc::mbar_wait(&q_full, seg & 1u);
+            tc::mbar_wait(&k_full[kv_base % FA_KV_STAGES], (kv_base / FA_KV_STAGES) & 1u);
             tc::tcgen05_fence_after();
-            issue_qk(jj + 1);
-          }
-          tc::mbar_wait(&v_full[s], (g / FA_KV_STAGES) & 1u);
-          tc::mbar_wait(&p_full[t], (bb + (uint32_t)jj) & 1u);                 // P_t(jj) in TMEM, O_t rescaled if needed
-          tc::tcgen05_fence_after();
-          const uint32_t dV = dV0 + s * (FA_KV_BYTES >> 4);
-#pragma unroll
-          for (int k = 0; k < FA_BN / 16; ++k)        // A: P k-slice = 16 keys = 8 TMEM columns;  B: V rows [16k, 16k+16) x 64 dims
-            tc::umma_f16_ts(tO, tP + (uint32_t)(k * 8), dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (jj | k) ? 1u : 0u);
-          tc::umma_commit(&pv_done[t]);                                        // O_t includes block jj; P_t free
-          tc::umma_commit(&v_empty[s]);
-          if (twice) tc::umma_commit(&v_empty[s]);
-        }
-      }
-      __syncwarp();
-    } else if (warp >= 4) {
-      // ------------------------------------------------ softmax: tile t (8 warps), TWO threads per query row, 64 keys each
-      const int sw = warp - 4;                                                // 0..15
-      const int t = sw >> 3;
-      const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
-      const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
-      const int q = quarter * 32 + lane;                                      // TMEM lane == tile row
-      const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-      const int pair_bar = 2 + t * 4 + quarter;                               // named barrier of the two warps that share my rows
-      const bool tile_valid = t == 0 || validB;
-      const uint32_t tS = tmem + lane_off + (uint32_t)t * FA_BN + (uint32_t)hf * 64;
-      const uint32_t tO = tmem + lane_off + FA_TMEM_O + (uint32_t)t * FA_D + (uint32_t)hf * 32;   // my 32 of the 64 output dims
-      const uint32_t tP = tmem + lane_off + FA_TMEM_P + (uint32_t)t * (FA_BN / 2) + (uint32_t)hf * 32;
-      float m_run = -INFINITY, l_part = 0.f;                                  // l_part (my 64-key halves) is relative to m_run
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      uint32_t ov[32];
-      float l = 1.f;
-      const uint32_t bb = blk_base[t];
-
-      if (tile_valid) {
-        for (int jj = 0; jj < nb; ++jj) {
-          const uint32_t ph = (bb + (uint32_t)jj) & 1u;
-          FA_STAMP(0);
-          tc::mbar_wait(&s_full[t], ph);
-          FA_STAMP(1);
-          tc::tcgen05_fence_after();
-          uint32_t v[64];
-          tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
-          tc::tmem_ld_wait();
-          tc::tcgen05_fence_before();
-          FA_ARRIVE(&s_empty[t]);                                       // QK_t(jj + 1) may overwrite the score buffer now
-          const int kvalid = pr.nk - (kb0 + jj) * FA_BN - hf * 64;            // keys of my half that exist
-          if (kvalid < 64) {                                                  // only in the problem's last block
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i >= kvalid) v[i] = 0xff800000u;                            // -inf
-          }
-          float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 64; i += 2) mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-          xch[t][ph][hf][q] = mx;
-          FA_STAMP(2);
-          named_bar_sync(pair_bar, 64);                                       // the two warps that share this lane quarter
-          FA_STAMP(3);
-          mx = fmaxf(mx, xch[t][ph][hf ^ 1][q]);
-          const float m_blk = mx * p.scale_log2;
-          // lazy running maximum: move only when the block exceeds it by more than 2^TAU (both partner threads decide alike)
-          const bool need = jj > 0 && m_blk > m_run + FA_TAU;
-          const float m_new = (jj == 0 || need) ? fmaxf(m_blk, -1e30f) : m_run;   // finite even if the block holds no real key
-          if (jj > 0) {
-            tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
-            FA_STAMP(4);
-            if (__any_sync(0xffffffffu, need)) {
-              tc::tcgen05_fence_after();
-              const float alpha = need ? ex2_approx(m_run - m_new) : 1.f;     // O_t and the row sum are relative to m_run
-#pragma unroll 1
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t o16[16];
-                tmem_ld16(tO + hh * 16, o16);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
-                tmem_st16(tO + hh * 16, o16);
+            issue_qk(0);
+            for (int jj = 0; jj < nb; ++jj) {
+              const uint32_t g = kv_base + (uint32_t)jj, s = g % FA_KV_STAGES;
+              if (jj + 1 < nb) {
+                // scores of the NEXT block: the buffer is free as soon as the group has block jj in registers
+                tc::mbar_wait(&k_full[(g + 1) % FA_KV_STAGES], ((g + 1) / FA_KV_STAGES) & 1u);
+                tc::mbar_wait(&s_empty[t], (bb + (uint32_t)jj) & 1u);
+                tc::tcgen05_fence_after();
+                issue_qk(jj + 1);
               }
-              tmem_st_wait();
-              l_part *= alpha;
+              tc::mbar_wait(&v_full[s], (g / FA_KV_STAGES) & 1u);
+              tc::mbar_wait(&p_full[t], (bb + (uint32_t)jj) & 1u);                 // P_t(jj) in TMEM, O_t rescaled if needed
+              tc::tcgen05_fence_after();
+              const uint32_t dV = dV0 + s * (FA_KV_BYTES >> 4);
+    #pragma unroll
+              for (int k = 0; k < FA_BN / 16; ++k)        // A: P k-slice = 16 keys = 8 TMEM columns;  B: V rows [16k, 16k+16) x 64 dims
+                tc::umma_f16_ts(tO, tP + (uint32_t)(k * 8), dV + (uint32_t)((k * 16 * 128) >> 4), hi_k, idesc_pv, (jj | k) ? 1u : 0u);
+              tc::umma_commit(&pv_done[t]);                                        // O_t includes block jj; P_t free
+              tc::umma_commit(&v_empty[s]);
+              if (twice) tc::umma_commit(&v_empty[s]);
             }
           }
-          m_run = m_new;
-          // p = exp2(s * c - m); f32 row sum; bf16 pairs -> TMEM lane q, columns [32 hf, 32 hf + 32) of P_t, 16 columns at a time
-          float2 rs2 = make_float2(0.f, 0.f);
-          const float2 nm2 = make_float2(-m_new, -m_new);
-          uint32_t pk[16];
-          // experiment (off): the two tiles take turns on the SM's MUFU pipe, A(n), B(n), A(n+1), ...
-          if (FA_TURNS && validB) {
-            const uint32_t n = turn_base + (uint32_t)jj;
-            if (t == 1) tc::mbar_wait(&turn[0], n & 1u);                      // A finished its n-th exponential phase
-            else if (n > 0) tc::mbar_wait(&turn[1], (n - 1u) & 1u);           // B finished its (n-1)-th
-          }
-#pragma unroll
-          for (int tt = 0; tt < 8; ++tt) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = tt * 8 + e * 2;
-              const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
-              const bool poly = (((tt & 1) ? (POLY_MASK >> 4) : POLY_MASK) >> e) & 1;    // compile-time after unrolling
-              const float2 ab = (POLY_MASK & 0x100) ? x                                  // timing experiment: no exponential at all
-                                : poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
-              rs2 = __fadd2_rn(rs2, ab);
-              __nv_bfloat162 pr2 = __floats2bfloat162_rn(ab.x, ab.y);
-              pk[(tt & 3) * 4 + e] = *reinterpret_cast<uint32_t*>(&pr2);
-            }
-            if ((tt & 3) == 3) tmem_st16(tP + (tt >> 2) * 16, pk);
-          }
-          l_part += rs2.x + rs2.y;
-          if (FA_TURNS && validB) FA_ARRIVE(&turn[t]);                        // the pipe is the other tile's
-          FA_STAMP(5);
-          tmem_st_wait();
-          tc::tcgen05_fence_before();
-          FA_ARRIVE(&p_full[t]);
-          FA_STAMP(6);
+          __syncwarp();
         }
-        // ---- row sum of both halves, O_t (my 32 dims) into registers
-        lsum_s[t][hf][q] = l_part;
-        named_bar_sync(pair_bar, 64);
-        l = l_part + lsum_s[t][hf ^ 1][q];
-        tc::mbar_wait(&pv_done[t], (bb + (uint32_t)(nb - 1)) & 1u);
-        tc::tcgen05_fence_after();
-        tmem_ld32x(tO, ov);
-        tc::tmem_ld_wait();
-        tc::tcgen05_fence_before();
-      }
-      float m_fin = m_run;
-      bool store = true;
-      if (!whole) {
-        // ---- split item: publish my part (O, m, l); the part that arrives last merges all of them and writes the output
-        const int row = t * FA_BM + q;
-        const long long item_end = item_start + nblk;
-        const int c_first = fa_cta_of_unit(p, item_start), c_last = fa_cta_of_unit(p, item_end - 1);
-        float* mine = p.part + (size_t)(2 * cta + slot) * FA_PART_FLOATS;
-        if (tile_valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(mine + (size_t)row * FA_D + hf * 32 + i) =
-                make_float4(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]), __uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
-          if (hf == 0) { mine[2 * FA_BM * FA_D + row] = m_fin; mine[2 * FA_BM * FA_D + 2 * FA_BM + row] = l; }
-        }
-        __threadfence();
-        asm volatile("bar.sync 1, 512;" ::: "memory");                        // the sixteen softmax warps
-        if (threadIdx.x == 128) merge_flag_s = atomicAdd(p.counters + ioff + it, 1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        store = merge_flag_s == c_last - c_first;                             // uniform over the CTA: I am the last part
-        if (store && tile_valid) {
-          __threadfence();
-          for (int c2 = c_first; c2 <= c_last; ++c2) {
-            if (c2 == cta) continue;
-            const long long rs = fa_range_start(p, c2);
-            const int slot2 = (rs >= item_start) ? 0 : 1;                     // the item is CTA c2's first segment iff its range starts inside it
-            const float* oth = p.part + (size_t)(2 * c2 + slot2) * FA_PART_FLOATS;
-            const float mo = __ldcg(oth + 2 * FA_BM * FA_D + row), lo = __ldcg(oth + 2 * FA_BM * FA_D + 2 * FA_BM + row);
-            const float mm = fmaxf(m_fin, mo);
-            const float wa = ex2_approx(m_fin - mm), wb = ex2_approx(mo - mm);
-            l = l * wa + lo * wb;
-            m_fin = mm;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 o4 = __ldcg(reinterpret_cast<const float4*>(oth + (size_t)row * FA_D + hf * 32 + i));
-              ov[i] = __float_as_uint(__uint_as_float(ov[i]) * wa + o4.x * wb);
-              ov[i + 1] = __float_as_uint(__uint_as_float(ov[i + 1]) * wa + o4.y * wb);
-              ov[i + 2] = __float_as_uint(__uint_as_float(ov[i + 2]) * wa + o4.z * wb);
-              ov[i + 3] = __float_as_uint(__uint_as_float(ov[i + 3]) * wa + o4.w * wb);
-            }
-          }
-        }
-      }
-      if (store && tile_valid && q0 + t * FA_BM + q < pr.nq) {
-        const float inv = 1.f / l;
-        __nv_bfloat16* dst = p.O + (size_t)(pr.q_row0 + q0 + t * FA_BM + q) * p.ldo + h * FA_D + hf * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 pk4;
-          __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-          __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-          __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-          pk4.x = *reinterpret_cast<uint32_t*>(&a); pk4.y = *reinterpret_cast<uint32_t*>(&b2);
-          pk4.z = *reinterpret_cast<uint32_t*>(&c2); pk4.w = *reinterpret_cast<uint32_t*>(&d);
-          *reinterpret_cast<uint4*>(dst + i) = pk4;
-        }
+        FA_SEGMENT_ADVANCE
       }
     }
-    u = item_start + kb1;
-    ++seg; kv_base += (uint32_t)nb; blk_base[0] += (uint32_t)nb; if (validB) { blk_base[1] += (uint32_t)nb; turn_base += (uint32_t)nb; }
-    // ---- next segment: the softmax groups have O_t in registers (they waited for the last PV), Q / O / P may be overwritten
-    tc::tcgen05_fence_before();
-    __syncthreads();
-    tc::tcgen05_fence_after();
+  } else {
+#if FA_SOFTMAX_REGS
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA_SOFTMAX_REGS));
+#endif
+    for (long long u = u_begin; u < u_end;) {
+      FA_SEGMENT_DECODE
+        // ------------------------------------------------ softmax: tile t (8 warps), TWO threads per query row, 64 keys each
+        const int sw = warp - 4;                                                // 0..15
+        const int t = sw >> 3;
+        const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
+        const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
+        const int q = quarter * 32 + lane;                                      // TMEM lane == tile row
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const int pair_bar = 2 + t * 4 + quarter;                               // named barrier of the two warps that share my rows
+        const bool tile_valid = t == 0 || validB;
+        const uint32_t tS = tmem + lane_off + (uint32_t)t * FA_BN + (uint32_t)hf * 64;
+        const uint32_t tO = tmem + lane_off + FA_TMEM_O + (uint32_t)t * FA_D + (uint32_t)hf * 32;   // my 32 of the 64 output dims
+        const uint32_t tP = tmem + lane_off + FA_TMEM_P + (uint32_t)t * (FA_BN / 2) + (uint32_t)hf * 32;
+        float m_run = -INFINITY, l_part = 0.f;                                  // l_part (my 64-key halves) is relative to m_run
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        uint32_t ov[32];
+        float l = 1.f;
+        const uint32_t bb = blk_base[t];
+
+        if (tile_valid) {
+          for (int jj = 0; jj < nb; ++jj) {
+            const uint32_t ph = (bb + (uint32_t)jj) & 1u;
+            FA_STAMP(0);
+            tc::mbar_wait(&s_full[t], ph);
+            FA_STAMP(1);
+            tc::tcgen05_fence_after();
+            uint32_t v[64];
+            tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
+            tc::tmem_ld_wait();
+            tc::tcgen05_fence_before();
+            FA_ARRIVE(&s_empty[t]);                                       // QK_t(jj + 1) may overwrite the score buffer now
+            const int kvalid = pr.nk - (kb0 + jj) * FA_BN - hf * 64;            // keys of my half that exist
+            if (kvalid < 64) {                                                  // only in the problem's last block
+  #pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (i >= kvalid) v[i] = 0xff800000u;                            // -inf
+            }
+            float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  #pragma unroll
+            for (int i = 0; i < 64; i += 2) mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+            xch[t][ph][hf][q] = mx;
+            FA_STAMP(2);
+            named_bar_sync(pair_bar, 64);                                       // the two warps that share this lane quarter
+            FA_STAMP(3);
+            mx = fmaxf(mx, xch[t][ph][hf ^ 1][q]);
+            const float m_blk = mx * p.scale_log2;
+            // lazy running maximum: move only when the block exceeds it by more than 2^TAU (both partner threads decide alike)
+            const bool need = jj > 0 && m_blk > m_run + FA_TAU;
+            const float m_new = (jj == 0 || need) ? fmaxf(m_blk, -1e30f) : m_run;   // finite even if the block holds no real key
+            if (jj > 0) {
+              tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
+              FA_STAMP(4);
+              if (__any_sync(0xffffffffu, need)) {
+                tc::tcgen05_fence_after();
+                const float alpha = need ? ex2_approx(m_run - m_new) : 1.f;     // O_t and the row sum are relative to m_run
+  #pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t o16[16];
+                  tmem_ld16(tO + hh * 16, o16);
+                  tc::tmem_ld_wait();
+  #pragma unroll
+                  for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+                  tmem_st16(tO + hh * 16, o16);
+                }
+                tmem_st_wait();
+                l_part *= alpha;
+              }
+            }
+            m_run = m_new;
+            // p = exp2(s * c - m); f32 row sum; bf16 pairs -> TMEM lane q, columns [32 hf, 32 hf + 32) of P_t, 16 columns at a time
+            float2 rs2 = make_float2(0.f, 0.f);
+            const float2 nm2 = make_float2(-m_new, -m_new);
+            uint32_t pk[16];
+            // experiment (off): the two tiles take turns on the SM's MUFU pipe, A(n), B(n), A(n+1), ...
+            if (FA_TURNS && validB) {
+              const uint32_t n = turn_base + (uint32_t)jj;
+              if (t == 1) tc::mbar_wait(&turn[0], n & 1u);                      // A finished its n-th exponential phase
+              else if (n > 0) tc::mbar_wait(&turn[1], (n - 1u) & 1u);           // B finished its (n-1)-th
+            }
+  #pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = tt * 8 + e * 2;
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+                const bool poly = (((tt & 1) ? (POLY_MASK >> 4) : POLY_MASK) >> e) & 1;    // compile-time after unrolling
+                const float2 ab = (POLY_MASK & 0x100) ? x                                  // timing experiment: no exponential at all
+                                  : poly ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                rs2 = __fadd2_rn(rs2, ab);
+                __nv_bfloat162 pr2 = __floats2bfloat162_rn(ab.x, ab.y);
+                pk[(tt & 3) * 4 + e] = *reinterpret_cast<uint32_t*>(&pr2);
+              }
+              if ((tt & 3) == 3) tmem_st16(tP + (tt >> 2) * 16, pk);
+            }
+            l_part += rs2.x + rs2.y;
+            if (FA_TURNS && validB) FA_ARRIVE(&turn[t]);                        // the pipe is the other tile's
+            FA_STAMP(5);
+            tmem_st_wait();
+            tc::tcgen05_fence_before();
+            FA_ARRIVE(&p_full[t]);
+            FA_STAMP(6);
+          }
+          // ---- row sum of both halves, O_t (my 32 dims) into registers
+          lsum_s[t][hf][q] = l_part;
+          named_bar_sync(pair_bar, 64);
+          l = l_part + lsum_s[t][hf ^ 1][q];
+          tc::mbar_wait(&pv_done[t], (bb + (uint32_t)(nb - 1)) & 1u);
+          tc::tcgen05_fence_after();
+          tmem_ld32x(tO, ov);
+          tc::tmem_ld_wait();
+          tc::tcgen05_fence_before();
+        }
+        float m_fin = m_run;
+        bool store = true;
+        if (!whole) {
+          // ---- split item: publish my part (O, m, l); the part that arrives last merges all of them and writes the output
+          const int row = t * FA_BM + q;
+          const long long item_end = item_start + nblk;
+          const int c_first = fa_cta_of_unit(p, item_start), c_last = fa_cta_of_unit(p, item_end - 1);
+          float* mine = p.part + (size_t)(2 * cta + slot) * FA_PART_FLOATS;
+          if (tile_valid) {
+  #pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(mine + (size_t)row * FA_D + hf * 32 + i) =
+                  make_float4(__uint_as_float(ov[i]), __uint_as_float(ov[i + 1]), __uint_as_float(ov[i + 2]), __uint_as_float(ov[i + 3]));
+            if (hf == 0) { mine[2 * FA_BM * FA_D + row] = m_fin; mine[2 * FA_BM * FA_D + 2 * FA_BM + row] = l; }
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 512;" ::: "memory");                        // the sixteen softmax warps
+          if (threadIdx.x == 128) merge_flag_s = atomicAdd(p.counters + ioff + it, 1);
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          store = merge_flag_s == c_last - c_first;                             // uniform over the CTA: I am the last part
+          if (store && tile_valid) {
+            __threadfence();
+            for (int c2 = c_first; c2 <= c_last; ++c2) {
+              if (c2 == cta) continue;
+              const long long rs = fa_range_start(p, c2);
+              const int slot2 = (rs >= item_start) ? 0 : 1;                     // the item is CTA c2's first segment iff its range starts inside it
+              const float* oth = p.part + (size_t)(2 * c2 + slot2) * FA_PART_FLOATS;
+              const float mo = __ldcg(oth + 2 * FA_BM * FA_D + row), lo = __ldcg(oth + 2 * FA_BM * FA_D + 2 * FA_BM + row);
+              const float mm = fmaxf(m_fin, mo);
+              const float wa = ex2_approx(m_fin - mm), wb = ex2_approx(mo - mm);
+              l = l * wa + lo * wb;
+              m_fin = mm;
+  #pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 o4 = __ldcg(reinterpret_cast<const float4*>(oth + (size_t)row * FA_D + hf * 32 + i));
+                ov[i] = __float_as_uint(__uint_as_float(ov[i]) * wa + o4.x * wb);
+                ov[i + 1] = __float_as_uint(__uint_as_float(ov[i + 1]) * wa + o4.y * wb);
+                ov[i + 2] = __float_as_uint(__uint_as_float(ov[i + 2]) * wa + o4.z * wb);
+                ov[i + 3] = __float_as_uint(__uint_as_float(ov[i + 3]) * wa + o4.w * wb);
+              }
+            }
+          }
+        }
+        if (store && tile_valid && q0 + t * FA_BM + q < pr.nq) {
+          const float inv = 1.f / l;
+          __nv_bfloat16* dst = p.O + (size_t)(pr.q_row0 + q0 + t * FA_BM + q) * p.ldo + h * FA_D + hf * 32;
+  #pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk4;
+            __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            __nv_bfloat162 c2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+            __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            pk4.x = *reinterpret_cast<uint32_t*>(&a); pk4.y = *reinterpret_cast<uint32_t*>(&b2);
+            pk4.z = *reinterpret_cast<uint32_t*>(&c2); pk4.w = *reinterpret_cast<uint32_t*>(&d);
+            *reinterpret_cast<uint4*>(dst + i) = pk4;
+          }
+        }
+      FA_SEGMENT_ADVANCE
+    }
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -566,31 +599,25 @@ extern "C" __attribute__((visibility("default"))) int i4d_attention_bf16_tc(
   } else {
     p.n_ctas = items < sms ? items : sms;
   }
-  // share of exponentials on the FMA pipe (I4D_FA_POLY = 25 / 50 / 75 / 100, -1 = none at all; experiments)
+  // share of exponentials on the FMA pipe (I4D_FA_POLY = 12 / 25 / 37 / 50 / 75 / 100 percent, -1 = none at all; experiments)
+  using KernelFn = void (*)(const CUtensorMap, AttnParams);
+  static const struct { int pct; KernelFn fn; } table[] = {
+      {0, attn_tc_kernel<0x00>},  {12, attn_tc_kernel<0x80>}, {25, attn_tc_kernel<0x88>}, {37, attn_tc_kernel<0x8A>},
+      {50, attn_tc_kernel<0xAA>}, {75, attn_tc_kernel<0xEE>}, {100, attn_tc_kernel<0xFF>}, {-1, attn_tc_kernel<0x100>}};
   static int variant = -1;
   static bool attr_seen[64] = {};
   if (variant < 0) {
     const char* e = getenv("I4D_FA_POLY");
     const int v = e ? atoi(e) : FA_DEFAULT_POLY;
-    variant = v == 25 ? 1 : v == 50 ? 2 : v == 75 ? 3 : v == 100 ? 4 : v == -1 ? 5 : 0;
+    variant = 0;
+    for (int i = 0; i < (int)(sizeof(table) / sizeof(table[0])); ++i)
+      if (table[i].pct == v) variant = i;
   }
   if (i4d_first_use_on_device(attr_seen)) {
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0xFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(attn_tc_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    for (const auto& t : table)
+      I4D_CUDA_CALL(cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }
-  const int grid = p.n_ctas;
-  switch (variant) {
-    case 1: attn_tc_kernel<0x88><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 2: attn_tc_kernel<0xAA><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 3: attn_tc_kernel<0xEE><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 4: attn_tc_kernel<0xFF><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    case 5: attn_tc_kernel<0x100><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p); break;
-    default: attn_tc_kernel<0x00><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
-  }
+  table[variant].fn<<<p.n_ctas, FA_THREADS, FA_SMEM_BYTES, st>>>(tmX, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
