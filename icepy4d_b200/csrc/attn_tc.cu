@@ -63,10 +63,10 @@
 //                      intended, but the loads / row maxima of one tile now compete with the other's exponentials: 216 us
 #ifdef FA_WARP_ARRIVE
 #define FA_ARRIVALS 8
-#define FA_ARRIVE(bar) do { __syncwarp(); if (lane == 0) tc::mbar_arrive(bar); } while (0)
+#define FA_ARRIVE(addr) do { __syncwarp(); if (lane == 0) tc::mbar_arrive_a(addr); } while (0)
 #else
 #define FA_ARRIVALS 256
-#define FA_ARRIVE(bar) tc::mbar_arrive(bar)
+#define FA_ARRIVE(addr) tc::mbar_arrive_a(addr)
 #endif
 #ifndef FA_SOFTMAX_REGS
 #define FA_SOFTMAX_REGS 104             // 0 = no setmaxnreg (every thread keeps the 96 registers of the launch)
@@ -365,39 +365,46 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
 #if FA_SOFTMAX_REGS
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA_SOFTMAX_REGS));
 #endif
+    // ------------------------------------------------ softmax: tile t (8 warps), TWO threads per query row, 64 keys each.
+    // Thread constants are computed once and pinned in registers (the block loop is latency-bound: every address the compiler
+    // re-derives from %tid in front of a barrier or an exchange sits on the serial chain of the block).
+    const int sw = warp - 4;                                                // 0..15
+    const int t = sw >> 3;
+    const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
+    const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
+    const int q = quarter * 32 + lane;                                      // TMEM lane == tile row
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int pair_bar = (int)tc::keep_in_register((uint32_t)(2 + t * 4 + quarter));   // named barrier of the two warps that share my rows
+    const uint32_t tS = tc::keep_in_register(tmem + lane_off + (uint32_t)t * FA_BN + (uint32_t)hf * 64);
+    const uint32_t tO = tc::keep_in_register(tmem + lane_off + FA_TMEM_O + (uint32_t)t * FA_D + (uint32_t)hf * 32);   // my 32 of the 64 output dims
+    const uint32_t tP = tc::keep_in_register(tmem + lane_off + FA_TMEM_P + (uint32_t)t * (FA_BN / 2) + (uint32_t)hf * 32);
+    const uint32_t a_s_full = tc::keep_in_register(tc::smem_u32(&s_full[t])), a_s_empty = tc::keep_in_register(tc::smem_u32(&s_empty[t]));
+    const uint32_t a_p_full = tc::keep_in_register(tc::smem_u32(&p_full[t])), a_pv_done = tc::keep_in_register(tc::smem_u32(&pv_done[t]));
+    const uint32_t a_xch_mine = tc::keep_in_register(tc::smem_u32(&xch[t][0][hf][q]));       // block parity ph adds ph * sizeof(xch[t][0])
+    const uint32_t a_xch_part = tc::keep_in_register(tc::smem_u32(&xch[t][0][hf ^ 1][q]));
     for (long long u = u_begin; u < u_end;) {
       FA_SEGMENT_DECODE
-        // ------------------------------------------------ softmax: tile t (8 warps), TWO threads per query row, 64 keys each
-        const int sw = warp - 4;                                                // 0..15
-        const int t = sw >> 3;
-        const int hf = (sw >> 2) & 1;                                           // column half: keys [64 hf, 64 hf + 64) of the block
-        const int quarter = warp & 3;                                           // TMEM lane quarter this warp may access
-        const int q = quarter * 32 + lane;                                      // TMEM lane == tile row
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const int pair_bar = 2 + t * 4 + quarter;                               // named barrier of the two warps that share my rows
         const bool tile_valid = t == 0 || validB;
-        const uint32_t tS = tmem + lane_off + (uint32_t)t * FA_BN + (uint32_t)hf * 64;
-        const uint32_t tO = tmem + lane_off + FA_TMEM_O + (uint32_t)t * FA_D + (uint32_t)hf * 32;   // my 32 of the 64 output dims
-        const uint32_t tP = tmem + lane_off + FA_TMEM_P + (uint32_t)t * (FA_BN / 2) + (uint32_t)hf * 32;
         float m_run = -INFINITY, l_part = 0.f;                                  // l_part (my 64-key halves) is relative to m_run
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         uint32_t ov[32];
         float l = 1.f;
         const uint32_t bb = blk_base[t];
+        const int kv_left = (int)tc::keep_in_register((uint32_t)(pr.nk - kb0 * FA_BN - hf * 64));
 
         if (tile_valid) {
           for (int jj = 0; jj < nb; ++jj) {
             const uint32_t ph = (bb + (uint32_t)jj) & 1u;
             FA_STAMP(0);
-            tc::mbar_wait(&s_full[t], ph);
+            tc::mbar_wait_a(a_s_full, ph);
             FA_STAMP(1);
             tc::tcgen05_fence_after();
             uint32_t v[64];
             tmem_ld32x(tS, v); tmem_ld32x(tS + 32, v + 32);
             tc::tmem_ld_wait();
             tc::tcgen05_fence_before();
-            FA_ARRIVE(&s_empty[t]);                                       // QK_t(jj + 1) may overwrite the score buffer now
-            const int kvalid = pr.nk - (kb0 + jj) * FA_BN - hf * 64;            // keys of my half that exist
+            FA_ARRIVE(a_s_empty);                                       // QK_t(jj + 1) may overwrite the score buffer now
+            const int kvalid = kv_left - jj * FA_BN;                            // keys of my half that exist
             if (kvalid < 64) {                                                  // only in the problem's last block
   #pragma unroll
               for (int i = 0; i < 64; ++i)
@@ -407,17 +414,17 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
   #pragma unroll
             for (int i = 0; i < 64; i += 2) mxa[(i >> 1) & 3] = fmax3(mxa[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
             float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-            xch[t][ph][hf][q] = mx;
+            tc::sts_f32(a_xch_mine + ph * (uint32_t)sizeof(xch[0][0]), mx);
             FA_STAMP(2);
             named_bar_sync(pair_bar, 64);                                       // the two warps that share this lane quarter
             FA_STAMP(3);
-            mx = fmaxf(mx, xch[t][ph][hf ^ 1][q]);
+            mx = fmaxf(mx, tc::lds_f32(a_xch_part + ph * (uint32_t)sizeof(xch[0][0])));
             const float m_blk = mx * p.scale_log2;
             // lazy running maximum: move only when the block exceeds it by more than 2^TAU (both partner threads decide alike)
             const bool need = jj > 0 && m_blk > m_run + FA_TAU;
             const float m_new = (jj == 0 || need) ? fmaxf(m_blk, -1e30f) : m_run;   // finite even if the block holds no real key
             if (jj > 0) {
-              tc::mbar_wait(&pv_done[t], ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
+              tc::mbar_wait_a(a_pv_done, ph ^ 1u);                              // PV_t(jj-1) retired: O_t complete, P_t free
               FA_STAMP(4);
               if (__any_sync(0xffffffffu, need)) {
                 tc::tcgen05_fence_after();
@@ -462,18 +469,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
               if ((tt & 3) == 3) tmem_st16(tP + (tt >> 2) * 16, pk);
             }
             l_part += rs2.x + rs2.y;
-            if (FA_TURNS && validB) FA_ARRIVE(&turn[t]);                        // the pipe is the other tile's
+            if (FA_TURNS && validB) FA_ARRIVE(tc::smem_u32(&turn[t]));                        // the pipe is the other tile's
             FA_STAMP(5);
             tmem_st_wait();
             tc::tcgen05_fence_before();
-            FA_ARRIVE(&p_full[t]);
+            FA_ARRIVE(a_p_full);
             FA_STAMP(6);
           }
           // ---- row sum of both halves, O_t (my 32 dims) into registers
           lsum_s[t][hf][q] = l_part;
           named_bar_sync(pair_bar, 64);
           l = l_part + lsum_s[t][hf ^ 1][q];
-          tc::mbar_wait(&pv_done[t], (bb + (uint32_t)(nb - 1)) & 1u);
+          tc::mbar_wait_a(a_pv_done, (bb + (uint32_t)(nb - 1)) & 1u);
           tc::tcgen05_fence_after();
           tmem_ld32x(tO, ov);
           tc::tmem_ld_wait();
