@@ -30,3 +30,11 @@ if which in ("gemm", "all"):
             else:
                 ops_tc.gemm_tc(x[:, :K], W, b, out16=o, relu=True)
     torch.cuda.synchronize()
+if which in ("assign", "all"):
+    N2 = 16384
+    S2 = torch.randn(N2, N2, device="cuda") * 3
+    ws2 = ops.AssignWorkspace(N2, N2, S2.device)
+    z0, z1 = torch.randn(N2, device="cuda"), torch.randn(N2, device="cuda")
+    for _ in range(2):
+        ops.lg_assign(S2, z0, z1, 0.1, ws2)
+    torch.cuda.synchronize()
