@@ -248,7 +248,9 @@ def _event_time(fn, warm=3, reps=5):
 # ncu `--set full` captures of the final kernels (profiles/r2_ncu_*.txt): DRAM bytes per launch unit
 # (r2: 3.506 GB read + 33.1 MB written over a 20-iteration launch, L2 hit rate 51 % incl. the L2 prefetches)
 SINKHORN_TRAFFIC_PER_ITER = {"read": 175.3e6, "write": 1.65e6, "source": "profiles/r2_ncu_sinkhorn.txt"}
-DUALSOFTMAX_TRAFFIC = None
+# ncu dram__bytes_read + dram__bytes_write of the two one-read passes of i4d_lg_assign at 16384^2 (profiles/r2_ncu_rowcol.txt):
+# rowcol_lse_kernel 1.0743 GB + 12.5 MB, rowcol_argmax_kernel 1.0740 GB + 12.7 MB (the combine kernels move < 40 MB)
+DUALSOFTMAX_TRAFFIC = {(16384, 16384): 1.0743e9 + 12.48e6 + 1.0740e9 + 12.73e6}
 
 
 def _roofline_hbm(cfg_name: str, peaks):
@@ -293,7 +295,7 @@ def _roofline_hbm(cfg_name: str, peaks):
     alg = 2.0 * M * N * 4
     gbs = alg / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": DUALSOFTMAX_TRAFFIC, "kernel": f"i4d_lg_assign (dual softmax + mutual NN, {M}x{N} f32 similarity)",
+            "traffic": DUALSOFTMAX_TRAFFIC.get((M, N)), "kernel": f"i4d_lg_assign (dual softmax + mutual NN, {M}x{N} f32 similarity)",
             "ms_per_launch": ms, "peak_source": peaks["source"],
             "bytes_basis": "SURVEY.md §8d: 2 reads of the similarity matrix (row/column statistics, then row/column argmax)"}
 

@@ -127,7 +127,16 @@ class LightGlueB200:
         cs0 = ops.lg_posenc(kpts0.contiguous(), float(size0[0]), float(size0[1]), W.Wr)
         cs1 = ops.lg_posenc(kpts1.contiguous(), float(size1[0]), float(size1[1]), W.Wr)
         tc = self._tc
-        if tc is not None:
+        do_stop, do_prune = self.depth_confidence > 0, self.width_confidence > 0
+        sim = None
+        if tc is not None and not do_stop and not do_prune and collect is None:
+            # static schedule: all layers + the similarity matrix replayed from a CUDA graph (keyed on 256-keypoint buckets)
+            res = tc.graphed(desc0, desc1, cs0, cs1, W.layers[:nl], W.assign[nl - 1])
+            if res is not None:
+                x0, x1, sim = res
+        if sim is not None:
+            pass
+        elif tc is not None:
             # tensor-core path: both images stacked in one f32 residual stream X [m+n,256] (+ its bf16 shadow inside `tc`)
             X = torch.empty((m + n, 256), device=dev, dtype=torch.float32)
             X[:m] = desc0
@@ -142,12 +151,11 @@ class LightGlueB200:
             xm0[:, :256] = desc0
             xm1[:, :256] = desc1
             x0, x1 = xm0[:, :256], xm1[:, :256]
-        do_stop, do_prune = self.depth_confidence > 0, self.width_confidence > 0
         ind0, ind1 = torch.arange(m, device=dev), torch.arange(n, device=dev)
         prune0 = torch.ones(m, dtype=torch.int64, device=dev)
         prune1 = torch.ones(n, dtype=torch.int64, device=dev)
-        i = 0
-        for i in range(nl):
+        i = nl - 1 if sim is not None else 0
+        for i in (range(nl) if sim is None else ()):
             L = W.layers[i]
             if tc is not None:
                 tc.layer(X, cs, mc, nc, L)
@@ -211,7 +219,9 @@ class LightGlueB200:
             b = torch.full((x1.shape[0],), -1, device=dev, dtype=torch.int32)
             c, d = torch.zeros(x0.shape[0], device=dev), torch.zeros(x1.shape[0], device=dev)
         else:
-            if tc is not None:
+            if sim is not None:
+                pass                                                             # from the graph replay
+            elif tc is not None:
                 sim = tc.similarity(X, x0.shape[0], x1.shape[0], A)
             else:
                 md0, md1 = ops.gemm_f32(x0, A["wf"], A["bf"]), ops.gemm_f32(x1, A["wf"], A["bf"])

@@ -232,6 +232,8 @@ class LightGlueTensorCore:
         for A in w.assign:
             self.h[id(A["wf"])] = h(A["wf"])
         self._buf = {}
+        self._graphs = {}
+        self._static_buf = None
 
     def _w(self, t):
         return self.h[id(t)]
@@ -240,6 +242,7 @@ class LightGlueTensorCore:
         """Persistent activation buffers for nt = m + n stacked keypoints (re-allocated only when nt grows)."""
         b = self._buf
         if b.get("cap", 0) < nt:
+            self._graphs.clear()                                              # graphs hold pointers into the old buffers
             d = self.dev
             b = self._buf = {"cap": nt, "x16": torch.empty((nt, 512), device=d, dtype=BF16),
                              "qkv32": torch.empty((nt, 768), device=d), "qkv16": torch.empty((nt, 768), device=d, dtype=BF16),
@@ -257,31 +260,106 @@ class LightGlueTensorCore:
         layernorm_gelu_bf16(hid32, L[f"g_{tag}"], L[f"be_{tag}"], hid16)
         gemm_tc(hid16, self._w(L[f"w2_{tag}"]), L[f"b2_{tag}"], residual=X, out32=X, out16=x16[:, :256])
 
-    def layer(self, X: torch.Tensor, cs: torch.Tensor, m: int, n: int, L):
+    def layer(self, X: torch.Tensor, cs: torch.Tensor, m: int, n: int, L, counts: Optional[torch.Tensor] = None):
         """One LightGlue layer (self block on both images, cross block) on the stacked residual stream X [m+n,256] f32 (updated
-        in place), cs [m+n,64] rotary tables.  The bf16 shadow of X must be current (`refresh_shadow`)."""
+        in place), cs [m+n,64] rotary tables.  The bf16 shadow of X must be current (`refresh_shadow`).  counts (device int32 [4] =
+        real m, n, n, m) masks the padding keys when m / n are bucket sizes (CUDA-graph replay)."""
         nt = m + n
         b = self.buffers(nt)
         x16, qkv32, qkv16, att = b["x16"][:nt], b["qkv32"][:nt], b["qkv16"][:nt], b["att"][:nt]
         # ---- self block (lightglue.py:133-163): Wqkv -> rotary(q, k) -> attention -> out_proj -> FFN([x | message]) ----
         gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv32)
         rotary_cast_bf16(qkv32, cs, qkv16)
-        attention_tc(qkv16, [(0, m, 0, m), (m, n, m, n)], att, 0, 256, 512)
+        attention_tc(qkv16, [(0, m, 0, m), (m, n, m, n)], att, 0, 256, 512, key_counts=None if counts is None else counts[:2])
         gemm_tc(att, self._w(L["wo"]), L["bo"], out16=x16[:, 256:])
         self._ffn(X, nt, L, "s", b)
         # ---- cross block (lightglue.py:166-216): shared to_qk (q = k) and to_v, both directions in one attention launch ----
         p = qkv16[:, :512]                                                   # [qk | v]
         gemm_tc(x16[:, :256], self._w(L["wqkv_x"]), L["bqkv_x"], out16=p)
-        attention_tc(qkv16, [(0, m, m, n), (m, n, 0, m)], att, 0, 0, 256)
+        attention_tc(qkv16, [(0, m, m, n), (m, n, 0, m)], att, 0, 0, 256, key_counts=None if counts is None else counts[2:])
         gemm_tc(att, self._w(L["wo_x"]), L["bo_x"], out16=x16[:, 256:])
         self._ffn(X, nt, L, "x", b)
 
-    def similarity(self, X: torch.Tensor, m: int, n: int, A):
+    def similarity(self, X: torch.Tensor, m: int, n: int, A, out: Optional[torch.Tensor] = None):
         """sim = final_proj(x0) final_proj(x1)^T (lightglue.py:268-284; the 256^-1/4 scaling is folded into the weights)."""
         nt = m + n
         b = self.buffers(nt)
         md = b["md"][:nt]
         gemm_tc(b["x16"][:nt, :256], self._w(A["wf"]), A["bf"], out16=md)
-        sim = ops.padded_scores(m, n, X.device)
+        sim = ops.padded_scores(m, n, X.device) if out is None else out
         gemm_tc(md[:m], md[m:], out32=sim)
         return sim
+
+    # -- CUDA-graph replay of the STATIC schedule (no early stop, no pruning: 9 layers + similarity, ~170 launches per tile pair),
+    #    keyed on 256-keypoint shape buckets exactly like SuperGlueTensorCore._graphed: the layers run at the bucket size, the
+    #    attention kernel masks the padding keys from a device tensor with the real counts, the caller gets the [m, n] corner of the
+    #    bucket's similarity matrix and the final residual stream (for the matchability heads).
+    use_graphs = os.environ.get("I4D_NO_GRAPHS", "0") != "1"
+    MAX_GRAPHS = 16
+    GRAPH_MIN = 1024
+    GRAPH_BUCKET = 256
+
+    def _static(self, nt: int, n_sim: int):
+        st = self._static_buf
+        if st is None or st["nt"] < nt or st["sim"].numel() < n_sim:
+            self._graphs.clear()
+            nt = max(nt, 0 if st is None else st["nt"])
+            n_sim = max(n_sim, 0 if st is None else st["sim"].numel())
+            d = self.dev
+            st = self._static_buf = {"nt": nt, "X": torch.zeros((nt, 256), device=d), "cs": torch.zeros((nt, 64), device=d),
+                                     "sim": torch.empty(n_sim, device=d), "counts": torch.zeros(4, device=d, dtype=torch.int32)}
+        return st
+
+    def graphed(self, desc0: torch.Tensor, desc1: torch.Tensor, cs0: torch.Tensor, cs1: torch.Tensor, layers, A):
+        """-> (X0 [m,256], X1 [n,256] final residual streams, sim [m,n]) from a graph replay, or None (first call of a bucket,
+        graphs disabled): the caller then runs the eager schedule."""
+        m, n = desc0.shape[0], desc1.shape[0]
+        if not self.use_graphs or min(m, n) < self.GRAPH_MIN:
+            return None
+        B = self.GRAPH_BUCKET
+        p0, p1 = -(-m // B) * B, -(-n // B) * B
+        key = (p0, p1, len(layers), id(A), torch.cuda.current_stream().cuda_stream)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = "seen"           # first call of a bucket runs eagerly (it also warms every kernel up)
+            return None
+        try:
+            self.buffers(p0 + p1)                # may grow (and drop every graph) BEFORE anything is captured
+            st = self._static(p0 + p1, p0 * p1)
+            if key not in self._graphs:
+                self._graphs[key] = ent = "seen"
+            X, cs = st["X"][: p0 + p1], st["cs"][: p0 + p1]
+            sim = st["sim"][: p0 * p1].view(p0, p1)
+            if ent == "seen":
+                launches0 = N.LAUNCHES
+                X.zero_()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.refresh_shadow(X)
+                    for L in layers:
+                        self.layer(X, cs, p0, p1, L, counts=st["counts"])
+                    self.similarity(X, p0, p1, A, out=sim)
+                ent = self._graphs[key] = {"g": g, "launches": N.LAUNCHES - launches0}
+                N.LAUNCHES = launches0           # capture launched nothing
+            X[:m] = desc0
+            X[p0: p0 + n] = desc1
+            cs[:m] = cs0
+            cs[p0: p0 + n] = cs1
+            if m < p0:
+                X[m:p0].zero_()                  # padding rows restart from zero (the residual stream is updated in place)
+                cs[m:p0].zero_()
+            if n < p1:
+                X[p0 + n:].zero_()
+                cs[p0 + n:].zero_()
+            st["counts"].copy_(torch.tensor([m, n, n, m], dtype=torch.int32))
+            ent["g"].replay()
+            N.LAUNCHES += ent["launches"]
+            return X[:m], X[p0: p0 + n], sim[:m, :n]
+        except Exception as err:                 # noqa: BLE001 - eager execution is always available
+            import logging
+            logging.getLogger(__name__).warning(f"CUDA-graph capture of the LightGlue schedule failed ({err}); running eagerly")
+            type(self).use_graphs = False
+            self._graphs.clear()
+            return None

@@ -178,3 +178,37 @@ def test_superglue_graph_buckets_serve_uneven_keypoint_counts(tc):
     graphs = [k for k, v in net._graphs.items() if isinstance(v, dict)]
     assert len(graphs) >= 2, "bucketed graphs were not captured"
     assert all(k[0] % 256 == 0 and k[1] % 256 == 0 for k in graphs)
+
+
+def test_lightglue_static_schedule_graph_buckets(tc):
+    """The static LightGlue schedule (no early stop, no pruning) is replayed from a CUDA graph keyed on 256-keypoint buckets: for
+    uneven keypoint counts the replay must give the eager schedule's matches (same kernels; only the attention's stream-K split
+    and the padding rows differ)."""
+    from icepy4d_b200 import synthetic
+    from icepy4d_b200.matching.lightglue import LightGlueB200
+    lg = LightGlueB200(weights.make_lightglue_state(3), precision="bf16", depth_confidence=-1, width_confidence=-1)
+    assert lg._tc.use_graphs
+    gen = torch.Generator().manual_seed(11)
+    for n0, n1 in [(1500, 1301), (1410, 1290), (1536, 1280)]:               # the first two share the (1536, 1536) bucket
+        k0 = torch.rand(n0, 2, generator=gen) * torch.tensor([1328.0, 1498.0])
+        shift = torch.tensor([16.0, 24.0])
+        perm = torch.randperm(n0, generator=gen)[:n1]
+        k1 = (k0[perm] + shift) if n1 <= n0 else k0
+        d0 = torch.nn.functional.normalize(torch.randn(n0, 256, generator=gen), dim=1)
+        d1 = torch.nn.functional.normalize(d0[perm] + 0.15 * torch.randn(n1, 256, generator=gen), dim=1)
+        args = (k0.cuda(), d0.cuda(), (1329, 1499), k1.cuda(), d1.cuda(), (1329, 1499))
+        runs = [lg.match(*args) for _ in range(3)]                            # eager (bucket seen), capture + replay, replay
+        type(lg._tc).use_graphs = False
+        try:
+            ref = lg.match(*args)
+        finally:
+            type(lg._tc).use_graphs = True
+        r0 = ref["matches0"].cpu()
+        assert (r0 > -1).sum() > 0.5 * n1
+        for out in runs:
+            m0 = out["matches0"].cpu()
+            assert m0.shape == r0.shape
+            assert (m0 == r0).float().mean().item() > 0.995, (n0, n1)
+            assert torch.allclose(out["matching_scores0"].cpu(), ref["matching_scores0"].cpu(), atol=5e-2)
+    graphs = [k for k, v in lg._tc._graphs.items() if isinstance(v, dict)]
+    assert len(graphs) >= 2 and all(k[0] % 256 == 0 and k[1] % 256 == 0 for k in graphs), "bucketed graphs were not captured"
