@@ -109,7 +109,7 @@ def current_stream() -> int:
 LAUNCHES = 0
 _PER_CALL = {"i4d_sp_score_map": 1, "i4d_sp_conv1a_relu": 1, "i4d_sp_conv1ab_tc": 1, "i4d_maxpool2x2_nhwc": 1, "i4d_sp_nms_candidates": 1, "i4d_sp_select_topk": 10, "i4d_sp_sample_descriptors": 1,
              "i4d_gemm_f32": 1, "i4d_attention_f32": 1, "i4d_layernorm_gelu": 1, "i4d_lg_posenc": 1, "i4d_lg_rotary": 1,
-             "i4d_sg_kenc_input": 1, "i4d_set_sinkhorn_mode": 0, "i4d_row_lse": 1, "i4d_col_lse": 2, "i4d_lg_assign": 10, "i4d_undistort_points": 1,
+             "i4d_sg_kenc_input": 1, "i4d_set_sinkhorn_mode": 0, "i4d_row_lse": 1, "i4d_col_lse": 2, "i4d_lg_assign": 14, "i4d_undistort_points": 1,
              "i4d_triangulate_iterative_ls": 1, "i4d_triangulate_dlt": 1, "i4d_tile_to_gray_f32": 1, "i4d_pyr_down_u8": 1, "i4d_pyr_up_u8": 1, "i4d_essential_pose": 4, "i4d_interpolate_point_colors": 1}
 
 
