@@ -209,6 +209,7 @@ def test_lightglue_static_schedule_graph_buckets(tc):
             m0 = out["matches0"].cpu()
             assert m0.shape == r0.shape
             assert (m0 == r0).float().mean().item() > 0.995, (n0, n1)
-            assert torch.allclose(out["matching_scores0"].cpu(), ref["matching_scores0"].cpu(), atol=5e-2)
+            same = m0 == r0                                                   # a flipped borderline match changes its score to / from 0
+            assert torch.allclose(out["matching_scores0"].cpu()[same], ref["matching_scores0"].cpu()[same], atol=5e-2)
     graphs = [k for k, v in lg._tc._graphs.items() if isinstance(v, dict)]
     assert len(graphs) >= 2 and all(k[0] % 256 == 0 and k[1] % 256 == 0 for k in graphs), "bucketed graphs were not captured"
