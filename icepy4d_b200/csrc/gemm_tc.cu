@@ -92,42 +92,45 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (tc::elect_one()) {
-      uint32_t kc = 0;
+      uint32_t s = 0, sph = 1;                                       // stage + the phase of its "empty" barrier to wait for
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++kc) {
-          const int s = kc % GT_STAGES;
-          tc::mbar_wait(&empty_bar[s], ((kc / GT_STAGES) & 1) ^ 1);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait(&empty_bar[s], sph);
           uint8_t* sa = smem + s * GT_STAGE_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[s], GT_STAGE_BYTES);
           tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * GT_BK, m0);
           tc::tma_load_2d(sa + GT_BM * GT_BK * 2, &tmW, &full_bar[s], kb * GT_BK, n0);
+          if (++s == GT_STAGES) { s = 0; sph ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+    // ------------------------------------------------ MMA issuer.  The loop is pure latency between two MMA groups: stage / phase
+    // are carried as counters (no modulo), barrier addresses are kept in registers.
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(GT_BM, GT_BN, 0, 0, 1);
       constexpr uint32_t hi = tc::desc_hi_sw128(1024);
       const uint32_t d0 = tc::desc_lo_sw128(tc::smem_u32(smem));
-      uint32_t kc = 0, i = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-        const uint32_t b = i % GT_NACC;
-        tc::mbar_wait(&acc_empty[b], ((i / GT_NACC) & 1) ^ 1);      // the epilogue has drained this accumulator
+      const uint32_t a_full = tc::keep_in_register(tc::smem_u32(&full_bar[0])), a_empty = tc::keep_in_register(tc::smem_u32(&empty_bar[0]));
+      const uint32_t a_acc_full = tc::keep_in_register(tc::smem_u32(&acc_full[0])), a_acc_empty = tc::keep_in_register(tc::smem_u32(&acc_empty[0]));
+      uint32_t s = 0, sph = 0, b = 0, bph = 1;                       // smem stage + its phase, accumulator + the phase to wait for
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        tc::mbar_wait_a(a_acc_empty + b * 8, bph);                   // the epilogue has drained this accumulator
         tc::tcgen05_fence_after();
         const uint32_t acc = tmem_d + b * GT_BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++kc) {
-          const int s = kc % GT_STAGES;
-          tc::mbar_wait(&full_bar[s], (kc / GT_STAGES) & 1);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait_a(a_full + s * 8, sph);
           tc::tcgen05_fence_after();
-          const uint32_t da = d0 + (uint32_t)(s * (GT_STAGE_BYTES >> 4)), db = da + ((GT_BM * GT_BK * 2) >> 4);
+          const uint32_t da = d0 + s * (GT_STAGE_BYTES >> 4), db = da + ((GT_BM * GT_BK * 2) >> 4);
 #pragma unroll
           for (int k = 0; k < GT_BK / 16; ++k) tc::umma_f16_parts(acc, da + k * 2, hi, db + k * 2, hi, idesc, (kb | k) ? 1u : 0u);
-          tc::umma_commit(&empty_bar[s]);       // smem stage reusable once these MMAs retire
+          tc::umma_commit_a(a_empty + s * 8);     // smem stage reusable once these MMAs retire
+          if (++s == GT_STAGES) { s = 0; sph ^= 1u; }
         }
-        tc::umma_commit(&acc_full[b]);          // accumulator complete
+        tc::umma_commit_a(a_acc_full + b * 8);    // accumulator complete
+        if (++b == GT_NACC) { b = 0; bph ^= 1u; }
       }
     }
     __syncwarp();
