@@ -43,6 +43,8 @@ struct GemmTcParams {
   const float* bias;
   int has_r, has_c32, has_c16, relu;
   int dbg;   // experiments only (I4D_GEMM_DBG): 1 = no TMA stores, 2 = no proxy fence, 4 = no staging writes, 8 = no epilogue barrier
+  const float* rot_cs;   // optional rotary tables [M, 64] (cos[32] | sin[32] per row): output columns < rot_cols are rotated in pairs
+  int rot_cols;          // (multiple of 128; head_dim 64: column c belongs to pair (c % 64) / 2) — LightGlue's q / k, lightglue.py:49-57
 };
 
 __device__ __forceinline__ void gt_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -175,6 +177,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t b = i % GT_NACC, bb2 = i & 1;
       float* bs = sBias + bb2 * GT_BN;
       const float bias_next = bias_of(t + (int)gridDim.x);          // in flight during this tile
+      // rotary tables of my row: both of my chunks start at column 32 wg of a 64-wide head, i.e. they use the same 16 pairs; the
+      // loads are in flight while the accumulator is awaited
+      const bool rot = p.rot_cs != nullptr && n0 < p.rot_cols;
+      float4 rc[4], rs[4];
+      if (rot) {
+        const float4* cr = reinterpret_cast<const float4*>(p.rot_cs + (size_t)min(m0 + row, p.M - 1) * 64 + wg * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { rc[j] = __ldg(cr + j); rs[j] = __ldg(cr + 8 + j); }
+      }
       gt_epi_bar();                                                  // bias row of this tile visible (written a tile ago)
       tc::mbar_wait(&acc_full[b], (i / GT_NACC) & 1);
       tc::tcgen05_fence_after();
@@ -202,6 +213,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (rot) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                                // 4 pairs per float4 of cos / sin
+            const float cc[4] = {rc[j].x, rc[j].y, rc[j].z, rc[j].w}, ss[4] = {rs[j].x, rs[j].y, rs[j].z, rs[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x = f[8 * j + 2 * e], y = f[8 * j + 2 * e + 1];
+              f[8 * j + 2 * e] = x * cc[e] - y * ss[e];
+              f[8 * j + 2 * e + 1] = y * cc[e] + x * ss[e];
+            }
+          }
         }
         if (p.has_r) {
           tc::mbar_wait(&r_full[wg], S & 1);                         // R chunk g lives in buffer g & 1 = wg; its S-th use
@@ -326,9 +349,9 @@ int i4d_make_tmap_hwc_bf16(CUtensorMap* out, const void* base, uint64_t H, uint6
   return I4D_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
-    const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr, float* C32, int ldc32,
-    void* C16, int ldc16, int M, int N, int K, float alpha, int relu, void* stream) {
+static int gemm_tc_launch(const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr, float* C32,
+                          int ldc32, void* C16, int ldc16, int M, int N, int K, float alpha, int relu, const float* rot_cs,
+                          int rot_cols, void* stream) {
   I4D_CHECK_ARG(A && W && (C32 || C16), "null pointer");
   I4D_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad sizes");
   I4D_CHECK_ARG(K % GT_BK == 0, "K must be a multiple of 64 for the tensor-core GEMM");
@@ -349,12 +372,29 @@ extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("I4D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
-  GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu, dbg};
+  GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu, dbg, rot_cs, rot_cols};
   const int n_tiles = i4d_cdiv(N, GT_BN) * i4d_cdiv(M, GT_BM);
   const int grid = n_tiles < i4d_num_sms() ? n_tiles : i4d_num_sms();
   gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc(
+    const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr, float* C32, int ldc32,
+    void* C16, int ldc16, int M, int N, int K, float alpha, int relu, void* stream) {
+  return gemm_tc_launch(A, lda, W, ldw, bias, R, ldr, C32, ldc32, C16, ldc16, M, N, K, alpha, relu, nullptr, 0, stream);
+}
+
+// LightGlue's fused QKV projection with the rotary embedding applied to q and k in the epilogue (K12 of SURVEY.md's kernel list):
+// C16 = rotary(A W^T + bias) for the output columns < rot_cols, plain A W^T + bias for the rest (v).
+extern "C" __attribute__((visibility("default"))) int i4d_gemm_bf16_tc_rotary(
+    const void* A, int lda, const void* W, int ldw, const float* bias, const float* cs, int rot_cols, void* C16, int ldc16,
+    int M, int N, int K, void* stream) {
+  I4D_CHECK_ARG(cs && C16, "null pointer");
+  I4D_CHECK_ARG(rot_cols >= 0 && rot_cols % GT_BN == 0 && (reinterpret_cast<uintptr_t>(cs) & 15) == 0,
+                "rot_cols must be a multiple of 128 and cs 16-byte aligned");
+  return gemm_tc_launch(A, lda, W, ldw, bias, nullptr, 0, nullptr, 0, C16, ldc16, M, N, K, 1.f, 0, cs, rot_cols, stream);
 }
 
 // ---- f32 -> bf16 row-major conversion with leading dimensions (feeds the tensor-core path) ---------------------------

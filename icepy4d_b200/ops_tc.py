@@ -37,6 +37,17 @@ def gemm_tc(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return out32 if out32 is not None else out16
 
 
+def gemm_tc_rotary(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, cs: torch.Tensor, rot_cols: int, out16: torch.Tensor):
+    """out16 = rotary(A @ W^T + bias) on the first rot_cols output columns (q | k of LightGlue's fused QKV projection, heads of
+    64 columns), plain projection on the rest; cs [M,64] f32 from lg_posenc.  One kernel instead of GEMM -> f32 -> rotary pass."""
+    assert A.dtype == BF16 and W.dtype == BF16 and out16.dtype == BF16 and A.stride(1) == 1 and W.stride(1) == 1
+    assert cs.dtype == torch.float32 and cs.is_contiguous() and cs.shape == (A.shape[0], 64)
+    M, K = A.shape
+    N.call("i4d_gemm_bf16_tc_rotary", A, A.stride(0), W, W.stride(0), bias, cs, int(rot_cols), out16, out16.stride(0), M,
+           W.shape[0], K, _st())
+    return out16
+
+
 def attention_tc(X: torch.Tensor, problems: Sequence[Tuple[int, int, int, int]], out: torch.Tensor, q_col: int, k_col: int,
                  v_col: int, heads: int = 4, scale: float = 0.125, key_counts: Optional[torch.Tensor] = None):
     """X [rows, ld] bf16 holding Q/K/V column blocks; problems = [(q_row0, nq, k_row0, nk), ...]; out [rows, >=64*heads] bf16.
@@ -75,7 +86,7 @@ def layernorm_gelu_bf16(x32: torch.Tensor, gamma: torch.Tensor, beta: torch.Tens
     return out16
 
 
-N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1, "i4d_lg_rotary_cast_bf16": 1,
+N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_gemm_bf16_tc_rotary": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1, "i4d_lg_rotary_cast_bf16": 1,
                     "i4d_layernorm_gelu_bf16": 1})
 
 
@@ -268,8 +279,11 @@ class LightGlueTensorCore:
         b = self.buffers(nt)
         x16, qkv32, qkv16, att = b["x16"][:nt], b["qkv32"][:nt], b["qkv16"][:nt], b["att"][:nt]
         # ---- self block (lightglue.py:133-163): Wqkv -> rotary(q, k) -> attention -> out_proj -> FFN([x | message]) ----
-        gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv32)
-        rotary_cast_bf16(qkv32, cs, qkv16)
+        if self.fuse_rotary:
+            gemm_tc_rotary(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], cs, 512, qkv16)      # rotary(q, k) in the GEMM epilogue
+        else:
+            gemm_tc(x16[:, :256], self._w(L["wqkv"]), L["bqkv"], out32=qkv32)
+            rotary_cast_bf16(qkv32, cs, qkv16)
         attention_tc(qkv16, [(0, m, 0, m), (m, n, m, n)], att, 0, 256, 512, key_counts=None if counts is None else counts[:2])
         gemm_tc(att, self._w(L["wo"]), L["bo"], out16=x16[:, 256:])
         self._ffn(X, nt, L, "s", b)
@@ -295,6 +309,7 @@ class LightGlueTensorCore:
     #    attention kernel masks the padding keys from a device tensor with the real counts, the caller gets the [m, n] corner of the
     #    bucket's similarity matrix and the final residual stream (for the matchability heads).
     use_graphs = os.environ.get("I4D_NO_GRAPHS", "0") != "1"
+    fuse_rotary = os.environ.get("I4D_LG_NO_ROTARY_FUSION", "0") != "1"
     MAX_GRAPHS = 16
     GRAPH_MIN = 1024
     GRAPH_BUCKET = 256

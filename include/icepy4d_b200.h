@@ -116,6 +116,11 @@ int i4d_sg_kenc_input(const float* kpts, const float* scores, int n, float width
 int i4d_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, const float* R, int ldr,
                      float* C32, int ldc32, void* C16, int ldc16, int M, int N, int K, float alpha, int relu,
                      void* stream);
+/* The same GEMM with LightGlue's rotary embedding (lightglue.py:49-57, 155-159) applied in the epilogue: output columns
+ * < rot_cols (a multiple of 128; heads of 64 columns, pair p = (column % 64) / 2) are rotated by the row's angles,
+ * cs [M,64] = cos[32] | sin[32] from i4d_lg_posenc; the remaining columns (v) pass through.  bf16 output only. */
+int i4d_gemm_bf16_tc_rotary(const void* A, int lda, const void* W, int ldw, const float* bias, const float* cs, int rot_cols,
+                            void* C16, int ldc16, int M, int N, int K, void* stream);
 /* LightGlue glue of the tensor-core path (lightglue.py:49-57,144-159): fused element-wise passes between the tcgen05 kernels.
  *   i4d_lg_rotary_cast_bf16: qkv [n,768] f32 (heads contiguous: q | k | v, 4 x 64 each), cs [n,64] (cos[32] | sin[32] per rotary
  *     pair, from i4d_lg_posenc) -> out [n,768] bf16 with the rotary embedding applied to q and k.

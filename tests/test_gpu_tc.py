@@ -216,3 +216,25 @@ def test_lightglue_static_schedule_graph_buckets(tc):
             assert ds < 0.1, (n0, n1, ds)
     graphs = [k for k, v in lg._tc._graphs.items() if isinstance(v, dict)]
     assert len(graphs) >= 2 and all(k[0] % 256 == 0 and k[1] % 256 == 0 for k in graphs), "bucketed graphs were not captured"
+
+
+@pytest.mark.parametrize("n", [128, 1000, 4133])
+def test_gemm_tc_rotary_epilogue_equals_gemm_then_rotary_pass(tc, n):
+    """LightGlue's fused QKV projection: the rotary embedding of q and k in the GEMM epilogue must give what the two-kernel path
+    (GEMM -> f32 -> i4d_lg_rotary_cast_bf16) gives — same f32 arithmetic, one rounding to bf16."""
+    gen = torch.Generator().manual_seed(n)
+    A = (torch.randn(n, 256, generator=gen)).bfloat16().cuda()
+    W = (torch.randn(768, 256, generator=gen) * 0.1).bfloat16().cuda()
+    b = torch.randn(768, generator=gen).cuda()
+    ang = torch.rand(n, 32, generator=gen) * 6.28
+    cs = torch.cat([torch.cos(ang), torch.sin(ang)], 1).contiguous().cuda()
+    q32 = torch.empty(n, 768, device="cuda")
+    ref = torch.empty(n, 768, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc(A, W, b, out32=q32)
+    tc.rotary_cast_bf16(q32, cs, ref)
+    out = torch.empty(n, 768, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc_rotary(A, W, b, cs, 512, out)
+    d = (out.float() - ref.float()).abs()
+    assert torch.equal(out[:, 512:], ref[:, 512:])                           # v: untouched
+    assert d.max().item() <= 2.0 ** -7 * ref.float().abs().max().item()      # at most one bf16 ulp (fma contraction may differ)
+    assert (out != ref).float().mean().item() < 1e-2
