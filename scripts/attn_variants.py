@@ -22,4 +22,6 @@ for N in (8192, 16384):
     for _ in range(20): ops_tc.attention_tc(qkv, pr, att, 0, 256, 512)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"flags={' '.join(flags) or '-'} POLY={os.environ.get('I4D_FA_POLY','default')} N={N}: {ms*1e3:.1f} us  {2*4*(2*N*N*64*2)/ms/1e9:.0f} TFLOP/s", flush=True)
+    q = qkv[:512, :64].double(); k = qkv[:N, 256:320].double(); v = qkv[:N, 512:576].double()
+    err = (att[:512, :64].double() - torch.softmax(q @ k.t() * 0.125, -1) @ v).abs().max().item()
+    print(f"flags={' '.join(flags) or '-'} POLY={os.environ.get('I4D_FA_POLY','default')} N={N}: {ms*1e3:.1f} us  {2*4*(2*N*N*64*2)/ms/1e9:.0f} TFLOP/s  max abs err {err:.4f}", flush=True)
