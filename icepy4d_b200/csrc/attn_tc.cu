@@ -507,13 +507,23 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const __grid_con
           asm volatile("bar.sync 1, 512;" ::: "memory");
           store = merge_flag_s == c_last - c_first;                             // uniform over the CTA: I am the last part
           if (store && tile_valid) {
+            // The parts are folded in CTA order c_first .. c_last WHATEVER part arrived last (the merger re-reads its own part from
+            // global memory like everybody else's), so the result does not depend on the arrival order: bit-reproducible output.
             __threadfence();
             for (int c2 = c_first; c2 <= c_last; ++c2) {
-              if (c2 == cta) continue;
               const long long rs = fa_range_start(p, c2);
               const int slot2 = (rs >= item_start) ? 0 : 1;                     // the item is CTA c2's first segment iff its range starts inside it
               const float* oth = p.part + (size_t)(2 * c2 + slot2) * FA_PART_FLOATS;
               const float mo = __ldcg(oth + 2 * FA_BM * FA_D + row), lo = __ldcg(oth + 2 * FA_BM * FA_D + 2 * FA_BM + row);
+              if (c2 == c_first) {
+                m_fin = mo; l = lo;
+  #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 o4 = __ldcg(reinterpret_cast<const float4*>(oth + (size_t)row * FA_D + hf * 32 + i));
+                  ov[i] = __float_as_uint(o4.x); ov[i + 1] = __float_as_uint(o4.y); ov[i + 2] = __float_as_uint(o4.z); ov[i + 3] = __float_as_uint(o4.w);
+                }
+                continue;
+              }
               const float mm = fmaxf(m_fin, mo);
               const float wa = ex2_approx(m_fin - mm), wb = ex2_approx(mo - mm);
               l = l * wa + lo * wb;

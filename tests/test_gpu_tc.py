@@ -241,3 +241,18 @@ def test_gemm_tc_rotary_epilogue_equals_gemm_then_rotary_pass(tc, n):
     assert torch.equal(out[:, 512:], ref[:, 512:])                           # v: untouched
     assert d.max().item() <= 2.0 ** -7 * ref.float().abs().max().item()      # at most one bf16 ulp (fma contraction may differ)
     assert (out != ref).float().mean().item() < 1e-2
+
+
+def test_attention_tc_is_bit_reproducible(tc):
+    """Items cut by the stream-K range boundaries are merged by whichever part arrives last; the parts are folded in a fixed order,
+    so repeated launches give identical bits (2400 / 2300 keypoints: several split items)."""
+    gen = torch.Generator().manual_seed(77)
+    n0, n1 = 2400, 2300
+    X = (torch.randn(n0 + n1, 768, generator=gen) * 1.5).bfloat16().cuda()
+    outs = []
+    for _ in range(6):
+        out = torch.zeros(n0 + n1, 256, device="cuda", dtype=torch.bfloat16)
+        tc.attention_tc(X, [(0, n0, n0, n1), (n0, n1, 0, n0)], out, 0, 256, 512)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
