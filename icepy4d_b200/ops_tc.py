@@ -173,6 +173,7 @@ class SuperGlueTensorCore:
     def _static(self, nt: int, n_scores: int):
         st = self._static_buf
         if st is None or st["nt"] < nt or st["scores"].numel() < n_scores:
+            torch.cuda.current_stream().synchronize()
             self._graphs.clear()                                              # graphs hold pointers into the old buffers
             nt = max(nt, 0 if st is None else st["nt"])
             n_scores = max(n_scores, 0 if st is None else st["scores"].numel())
@@ -189,6 +190,7 @@ class SuperGlueTensorCore:
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= self.MAX_GRAPHS:
+                torch.cuda.current_stream().synchronize()                     # its replay may still be running
                 self._graphs.pop(next(iter(self._graphs)))                    # oldest bucket out
             self._graphs[key] = "seen"
             return None
@@ -253,6 +255,8 @@ class LightGlueTensorCore:
         """Persistent activation buffers for nt = m + n stacked keypoints (re-allocated only when nt grows)."""
         b = self._buf
         if b.get("cap", 0) < nt:
+            if self._graphs:
+                torch.cuda.current_stream().synchronize()
             self._graphs.clear()                                              # graphs hold pointers into the old buffers
             d = self.dev
             b = self._buf = {"cap": nt, "x16": torch.empty((nt, 512), device=d, dtype=BF16),
@@ -317,6 +321,7 @@ class LightGlueTensorCore:
     def _static(self, nt: int, n_sim: int):
         st = self._static_buf
         if st is None or st["nt"] < nt or st["sim"].numel() < n_sim:
+            torch.cuda.current_stream().synchronize()
             self._graphs.clear()
             nt = max(nt, 0 if st is None else st["nt"])
             n_sim = max(n_sim, 0 if st is None else st["sim"].numel())
@@ -337,6 +342,7 @@ class LightGlueTensorCore:
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= self.MAX_GRAPHS:
+                torch.cuda.current_stream().synchronize()                     # its replay may still be running
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = "seen"           # first call of a bucket runs eagerly (it also warms every kernel up)
             return None
