@@ -90,6 +90,23 @@ N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_gemm_bf16_tc_rotary": 1, "i4d_at
                     "i4d_layernorm_gelu_bf16": 1})
 
 
+
+class _CountsRing:
+    """Real keypoint counts of a bucketed graph replay, host -> device without a stream synchronisation: a ring of pinned int32[4]
+    staging buffers (a blocking copy from pageable memory would make the host wait for everything queued on the stream).  A slot is
+    reused 32 replays later; the host can never be that far ahead of the device (every tile pair reads its keypoint counts back)."""
+
+    def __init__(self, slots: int = 32):
+        self.bufs = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(slots)]
+        self.i = 0
+
+    def push(self, dst: torch.Tensor, a: int, b: int):
+        h = self.bufs[self.i]
+        self.i = (self.i + 1) % len(self.bufs)
+        h[0], h[1], h[2], h[3] = a, b, b, a
+        dst.copy_(h, non_blocking=True)
+
+
 class SuperGlueTensorCore:
     """GNN (18 layers) + final projection + score matrix of SuperGlue on the tensor-core path (superglue.py:131-149,276-280)."""
 
@@ -110,6 +127,7 @@ class SuperGlueTensorCore:
         self._buf = {}
         self._graphs = {}
         self._static_buf = None
+        self._counts_ring = _CountsRing()
 
     def _buffers(self, nt):
         if self._buf.get("nt") != nt:
@@ -214,8 +232,7 @@ class SuperGlueTensorCore:
                 x32[n0:p0].zero_()               # padding rows restart from zero every replay (the residual stream is in place)
             if n1 < p1:
                 x32[p0 + n1: p0 + p1].zero_()
-            # pageable source: the driver stages it before the call returns, so the host may run ahead of the stream
-            st["counts"].copy_(torch.tensor([n0, n1, n1, n0], dtype=torch.int32))
+            self._counts_ring.push(st["counts"], n0, n1)
             ent["g"].replay()
             N.LAUNCHES += ent["launches"]
             return scores[:n0, :n1]
@@ -247,6 +264,7 @@ class LightGlueTensorCore:
         self._buf = {}
         self._graphs = {}
         self._static_buf = None
+        self._counts_ring = _CountsRing()
 
     def _w(self, t):
         return self.h[id(t)]
@@ -374,7 +392,7 @@ class LightGlueTensorCore:
             if n < p1:
                 X[p0 + n:].zero_()
                 cs[p0 + n:].zero_()
-            st["counts"].copy_(torch.tensor([m, n, n, m], dtype=torch.int32))
+            self._counts_ring.push(st["counts"], m, n)
             ent["g"].replay()
             N.LAUNCHES += ent["launches"]
             return X[:m], X[p0: p0 + n], sim[:m, :n]
