@@ -692,6 +692,22 @@ struct SkCtx {
   uint32_t row_bytes;
 };
 // ring / barrier phase bookkeeping carried across stages, bands and iterations (one copy per thread, all identical)
+// Timeline instrumentation (-DSK_TRACE, scripts/sinkhorn_trace.py): CTA 0 stamps %clock64 at the synchronisation points of its
+// fast-mode stages (warps 0 and 9) and of the iteration boundary (thread 0).
+#ifdef SK_TRACE
+#define SK_TRACE_MAX 512
+__device__ unsigned long long sk_trace_buf[2][SK_TRACE_MAX][8];
+#define SK_STAMP(fq_, k) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 288) && (fq_) < 440) { unsigned long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); sk_trace_buf[threadIdx.x ? 1 : 0][(fq_)][k] = c_; } } while (0)
+#define SK_BSTAMP(it_, k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it_) < 64) { unsigned long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); sk_trace_buf[1][448 + (it_)][k] = c_; } } while (0)
+extern "C" __attribute__((visibility("default"))) int i4d_sinkhorn_trace_dump(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, sk_trace_buf, sizeof(sk_trace_buf));
+}
+#else
+#define SK_STAMP(fq_, k) do { } while (0)
+#define SK_BSTAMP(it_, k) do { } while (0)
+#endif
 struct SkRing {
   uint32_t seq;        // stages consumed so far (all iterations)
   uint32_t buf;        // seq % SK_STAGES
@@ -843,6 +859,7 @@ __device__ __forceinline__ void sk_col_accum(const SkCtx& c, int idx, uint32_t s
   const float mr = valid ? (c.c_nu - c.uold_s[idx * SK_ROWS + row]) : 0.f;
   const float ex = sk_ex2(c.extra_row - mr);                        // dustbin column term
   sk_mbar_wait(&c.bpart[pp], (rg.bp_par >> pp) & 1u);               // all warps: partials published, buffer emptied
+  SK_STAMP(fq + 1u, 4);
   rg.bp_par ^= 1u << pp;
   const float2 pr = *reinterpret_cast<const float2*>(&c.part_s[slot][row][(lane & 7) * 2]);
   float t = pr.x + pr.y;
@@ -891,7 +908,9 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
   float mrow[SK_ROWS], rsum[SK_ROWS];
 #pragma unroll
   for (int k = 0; k < SK_ROWS; ++k) mrow[k] = (FULL || k < nr) ? (c.c_nu - c.uold_s[idx * SK_ROWS + k]) : 0.f;   // previous u
+  SK_STAMP(rg.fq, 0);
   sk_wait_full(c, rg);
+  SK_STAMP(rg.fq, 1);
   const float2 l2e = make_float2(LOG2E, LOG2E);
 #pragma unroll
   for (int k = 0; k < SK_ROWS; ++k) {
@@ -914,6 +933,7 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
     }
     rsum[k] = s2.x + s2.y;
   }
+  SK_STAMP(rg.fq, 2);
   // transposed warp reduction of the two row sums: lanes 0-15 end up with row 0, lanes 16-31 with row 1
   const bool hi = (lane & 16) != 0;
   float keep = hi ? rsum[1] : rsum[0];
@@ -924,7 +944,9 @@ __device__ __forceinline__ void sk_stage_fast(const SkCtx& c, int idx, int idx_p
   if ((lane & 15) == 0) c.part_s[slot][lane >> 4][warp] = keep;
   __syncwarp();
   if (lane == 0) sk_mbar_arrive(&c.bpart[pp]);                       // release: this warp's partials, and its reads of the buffer
+  SK_STAMP(rg.fq, 3);
   if (HAVE_PREV) sk_col_accum<PREV_FULL>(c, idx_prev, rg.seq - 1, rg.fq - 1, rg, e_prev, cs, csN);
+  SK_STAMP(rg.fq, 5);
   rg.advance();
   ++rg.fq;
 }
@@ -1107,7 +1129,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
       float2 cs[SK_GROUPS][2];
       float csN;
+      SK_BSTAMP(fit, 0);
       sk_band_fast(ctx, rg, vl, cs, csN);
+      SK_BSTAMP(fit, 1);
       // ---- column sums -> fixed point -> the shared-memory buffer of the band's last stage (free: every warp has passed the wait
       //      for that stage's partials, i.e. every warp has taken its elements out of it) -> one bulk reduction into acc ----
       unsigned long long* acc = acc_base + (size_t)(fit % 3u) * acc_stride;
@@ -1131,6 +1155,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
         asm volatile("fence.proxy.async;" ::: "memory");             // my generic-proxy writes (shared and global) before the bulk engine's
         const float csN1 = __shfl_sync(0xffffffffu, csN, 16);
         __syncthreads();
+        SK_BSTAMP(fit, 2);
         if (tid == 0) {
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
                        ::"l"(acc), "r"((uint32_t)__cvta_generic_to_shared(stg0)), "r"((uint32_t)n4 * 16u) : "memory");
@@ -1143,7 +1168,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the reduction is performed before this CTA arrives
         }
       }
+      SK_BSTAMP(fit, 3);
       grid_barrier();
+      SK_BSTAMP(fit, 4);
       // ---- every CTA: new v of my columns from the reduced sums; recycle the buffer of two iterations ago ----
       {
         unsigned long long* old = acc_base + (size_t)((fit + 2u) % 3u) * acc_stride;
@@ -1177,6 +1204,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn_fused_kernel(const flo
       }
       { float* t = uold; uold = unew; unew = t; }
       v_regs = true;
+      SK_BSTAMP(fit, 5);
       ++fit;
       if (__syncthreads_or((bad || __ldcg(flag) != 0) ? 1 : 0)) {
         // the fast mode tripped (potential jump beyond the f32 exponent range): restart the whole solve in exact mode.  Every
