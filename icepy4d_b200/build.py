@@ -25,7 +25,7 @@ def _sources():
 
 
 def _deps_mtime():
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "icepy4d_b200.h"))
     return max(os.path.getmtime(h) for h in hdrs)
 
