@@ -246,8 +246,8 @@ def _event_time(fn, warm=3, reps=5):
 
 
 # ncu `--set full` captures of the final kernels (profiles/r2_ncu_*.txt): DRAM bytes per launch unit
-# (r2: 3.506 GB read + 33.1 MB written over a 20-iteration launch, L2 hit rate 51 % incl. the L2 prefetches)
-SINKHORN_TRAFFIC_PER_ITER = {"read": 175.3e6, "write": 1.65e6, "source": "profiles/r2_ncu_sinkhorn.txt"}
+# (r2, 256-thread instantiation: 3.421 GB read + 17.9 MB written over a 20-iteration launch, L2 hit rate 51 % incl. the L2 prefetches)
+SINKHORN_TRAFFIC_PER_ITER = {"read": 171.0e6, "write": 0.89e6, "source": "profiles/r2_ncu_sinkhorn.txt"}
 # ncu dram__bytes_read + dram__bytes_write of the two one-read passes of i4d_lg_assign at 16384^2 (profiles/r2_ncu_rowcol.txt):
 # rowcol_lse_kernel 1.0743 GB + 12.5 MB, rowcol_argmax_kernel 1.0740 GB + 12.7 MB (the combine kernels move < 40 MB)
 DUALSOFTMAX_TRAFFIC = {(16384, 16384): 1.0743e9 + 12.48e6 + 1.0740e9 + 12.73e6}
