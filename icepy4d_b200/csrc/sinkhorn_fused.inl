@@ -800,6 +800,11 @@ static int sinkhorn_fused_launch(float* S, int M, int N, int ld, float alpha, in
                              SK_STAGES * SK_ROWS * SK_MAXN * (int)sizeof(float)) != cudaSuccess) { cudaGetLastError(); return 1; }
   }
   int G = sms;
+  {   // I4D_SK_G: run on fewer CTAs (experiments: what a band pass costs when two problems share the GPU)
+    static int g_env = -1;
+    if (g_env < 0) { const char* e = getenv("I4D_SK_G"); g_env = e ? atoi(e) : 0; }
+    if (g_env > 0 && g_env < G) G = g_env;
+  }
   int rpc = (M + G - 1) / G;
   rpc = (rpc + SK_ROWS - 1) / SK_ROWS * SK_ROWS;
   if (rpc > SK_MAX_BAND) return 1;
