@@ -26,16 +26,32 @@
 #define GT_BM 128
 #define GT_BN 128
 #define GT_BK 64
-#define GT_STAGES 3
 #define GT_THREADS 320
 #define GT_STAGE_BYTES ((GT_BM + GT_BN) * GT_BK * 2)          // 32 KB
 #define GT_CHUNK_BYTES (GT_BM * 128)                            // 16 KB box: 128 rows x 128 B (32 f32 or 64 bf16 columns)
 #define GT_NACC 4                                               // TMEM accumulators (4 x 128 columns = all of TMEM): the MMA warp runs
                                                                 // up to four tiles ahead of the epilogue, which hides the hand-off latencies
-#define GT_NBOX 8                                               // staging pool shared by the R loads and the C32 / C16 stores
+// GT_STAGES (operand ring) and GT_NBOX (staging pool shared by the R loads and the C32 / C16 stores) are template parameters of the
+// kernel: <3, 8> serves every output combination; <5, 4> is for the bf16-only outputs without a residual (three of the four GEMMs of
+// a GNN layer), whose epilogue needs four boxes only.  The main loop of these short-K GEMMs is bound by the bytes the ring keeps in
+// flight against the L2 -> shared-memory latency (3 x 32 KB per SM and ~1 us: 98 GB/s per SM measured), not by the tensor pipe.
 #define GT_OFF_POOL (GT_STAGES * GT_STAGE_BYTES)
 #define GT_OFF_BIAS (GT_OFF_POOL + GT_NBOX * GT_CHUNK_BYTES)    // 2 x 128 f32
-#define GT_SMEM_BYTES (GT_OFF_BIAS + 2 * GT_BN * 4)             // the dynamic segment is 1024-byte aligned (extern __align__(1024))
+constexpr int gt_smem_bytes(int stages, int nbox) { return stages * GT_STAGE_BYTES + nbox * GT_CHUNK_BYTES + 2 * GT_BN * 4; }
+
+// Timeline instrumentation (scripts/gemm_trace.py builds a second library with -DGT_TRACE): CTA 0 stamps %clock64 at the
+// synchronisation points of the producer lane, the MMA lane and the first epilogue thread for its first GT_TRACE_MAX tiles.
+#ifdef GT_TRACE
+#define GT_TRACE_MAX 32
+__device__ unsigned long long gt_trace_buf[3][GT_TRACE_MAX][8];
+#define GT_STAMP(role, tile, k) do { if (blockIdx.x == 0 && (tile) < GT_TRACE_MAX) { unsigned long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)); gt_trace_buf[role][tile][k] = c_; } } while (0)
+extern "C" __attribute__((visibility("default"))) int i4d_gemm_trace_dump(unsigned long long* host) {
+  return cudaMemcpyFromSymbol(host, gt_trace_buf, sizeof(gt_trace_buf)) == cudaSuccess ? 0 : 1;
+}
+#else
+#define GT_STAMP(role, tile, k) do { } while (0)
+#endif
 
 struct GemmTcParams {
   int M, N, K;
@@ -59,6 +75,7 @@ __device__ __forceinline__ void gt_wait_read(int pending) {          // cp.async
   else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+template <int GT_STAGES, int GT_NBOX>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmR,
@@ -95,10 +112,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ------------------------------------------------ TMA producer
     if (tc::elect_one()) {
       uint32_t s = 0, sph = 1;                                       // stage + the phase of its "empty" barrier to wait for
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      [[maybe_unused]] int ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
         const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
         for (int kb = 0; kb < kblocks; ++kb) {
+          if (kb == 0) GT_STAMP(0, ti, 0);
           tc::mbar_wait(&empty_bar[s], sph);
+          if (kb == 0) GT_STAMP(0, ti, 1);
+          if (kb == kblocks - 1) GT_STAMP(0, ti, 2);
           uint8_t* sa = smem + s * GT_STAGE_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[s], GT_STAGE_BYTES);
           tc::tma_load_2d(sa, &tmA, &full_bar[s], kb * GT_BK, m0);
@@ -118,12 +139,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t a_full = tc::keep_in_register(tc::smem_u32(&full_bar[0])), a_empty = tc::keep_in_register(tc::smem_u32(&empty_bar[0]));
       const uint32_t a_acc_full = tc::keep_in_register(tc::smem_u32(&acc_full[0])), a_acc_empty = tc::keep_in_register(tc::smem_u32(&acc_empty[0]));
       uint32_t s = 0, sph = 0, b = 0, bph = 1;                       // smem stage + its phase, accumulator + the phase to wait for
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      [[maybe_unused]] int ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        GT_STAMP(1, ti, 0);
         tc::mbar_wait_a(a_acc_empty + b * 8, bph);                   // the epilogue has drained this accumulator
+        GT_STAMP(1, ti, 1);
         tc::tcgen05_fence_after();
         const uint32_t acc = tmem_d + b * GT_BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           tc::mbar_wait_a(a_full + s * 8, sph);
+          if (kb == 0) GT_STAMP(1, ti, 2);
+          if (kb == kblocks - 1) GT_STAMP(1, ti, 3);
           tc::tcgen05_fence_after();
           const uint32_t da = d0 + s * (GT_STAGE_BYTES >> 4), db = da + ((GT_BM * GT_BK * 2) >> 4);
 #pragma unroll
@@ -132,6 +158,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           if (++s == GT_STAGES) { s = 0; sph ^= 1u; }
         }
         tc::umma_commit_a(a_acc_full + b * 8);    // accumulator complete
+        GT_STAMP(1, ti, 4);
         if (++b == GT_NACC) { b = 0; bph ^= 1u; }
       }
     }
@@ -186,8 +213,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) { rc[j] = __ldg(cr + j); rs[j] = __ldg(cr + 8 + j); }
       }
+      if (e == 0) GT_STAMP(2, i, 0);
       gt_epi_bar();                                                  // bias row of this tile visible (written a tile ago)
+      if (e == 0) GT_STAMP(2, i, 1);
       tc::mbar_wait(&acc_full[b], (i / GT_NACC) & 1);
+      if (e == 0) GT_STAMP(2, i, 2);
       tc::tcgen05_fence_after();
       // both of my chunks leave TMEM together (two loads in flight), and the accumulator goes back to the MMA warp at once
       uint32_t vv[2][32];
@@ -197,6 +227,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+      if (e == 0) GT_STAMP(2, i, 3);
 #pragma unroll
       for (int st = 0; st < 2; ++st) {
         const int c = 2 * st + wg;                                   // my chunk of this step
@@ -260,9 +291,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         //   C32 (two stores per step): next step writes boxes (g0+2, g0+3) % n32, last used by stores g0+2-n32, g0+3-n32; this
         //        leader has issued stores <= g0-1, so at most n32 - 4 of them may still be pending.
         //   C16 (one store per step): next step writes box (S+1) % n16, last used by store S+1-n16: at most n16 - 2 pending.
+        if (e == 0) GT_STAMP(2, i, 4 + 2 * st);
         if (lead32 && p.has_c32) gt_wait_read(n32 - 4);
         if (lead16 && p.has_c16) gt_wait_read(n16 - 2);
         if (!(p.dbg & 8)) gt_epi_bar();
+        if (e == 0) GT_STAMP(2, i, 5 + 2 * st);
         if (lead32) {
           if (p.has_c32) {
             const uint32_t g0 = 2 * S;
@@ -368,14 +401,19 @@ static int gemm_tc_launch(const void* A, int lda, const void* W, int ldw, const 
   if (C16) { if (int rc = i4d_make_tmap_2d_bf16(&tmC16, C16, (uint64_t)M, (uint64_t)N, (uint64_t)ldc16, GT_BM, 64)) return rc; }
   static bool attr_seen[64] = {};
   if (i4d_first_use_on_device(attr_seen)) {
-    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(3, 8)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(5, 4)));
   }
-  static int dbg = -1;
+  static int dbg = -1, deep_ring = -1;
   if (dbg < 0) { const char* e = getenv("I4D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+  if (deep_ring < 0) { const char* e = getenv("I4D_GEMM_DEEP_RING"); deep_ring = e ? atoi(e) : 1; }   // 0: <3, 8> for everything (A/B runs)
   GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu, dbg, rot_cs, rot_cols};
   const int n_tiles = i4d_cdiv(N, GT_BN) * i4d_cdiv(M, GT_BM);
   const int grid = n_tiles < i4d_num_sms() ? n_tiles : i4d_num_sms();
-  gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  if (deep_ring && K >= 512 && C16 && !C32 && !R)       // K = 256: 15.3 us with <5, 4> against 14.9 (the shallower store ring); K = 512: 16.9 against 18.8
+    gemm_tc_kernel<5, 4><<<grid, GT_THREADS, gt_smem_bytes(5, 4), (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  else
+    gemm_tc_kernel<3, 8><<<grid, GT_THREADS, gt_smem_bytes(3, 8), (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
