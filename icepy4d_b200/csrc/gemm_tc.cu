@@ -2,8 +2,8 @@
 // bf16 operands (both K-major), f32 accumulation in TMEM, outputs f32 and/or bf16 from one epilogue.
 //
 // Persistent, warp-specialised: one CTA per SM walks 128 x 128 output tiles (n fastest, so neighbouring CTAs share A rows in L2).
-//   warp 0      TMA producer: A and W tiles of 128 x 64 bf16 (one 128-byte swizzle row per matrix row) through a 4-stage
-//               mbarrier ring; it runs ahead across tile boundaries
+//   warp 0      TMA producer: A and W tiles of 128 x 64 bf16 (one 128-byte swizzle row per matrix row) through a 3- to 5-stage
+//               mbarrier ring (template parameter); it runs ahead across tile boundaries
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma M128 N128 K16, four per stage, into one of FOUR TMEM accumulators,
 //               so the main loop of tile i+1 overlaps the epilogue of tile i
 //   warps 2..9  epilogue (two warpgroups, each takes every other 32-column chunk), thread = output row: tcgen05.ld 32 columns at a time -> alpha, bias (staged in shared memory), ReLU,
@@ -13,6 +13,9 @@
 //               stores are issued by two different threads so each has its own bulk-group FIFO): a box is rewritten only
 //               several stores later — waiting for the PREVIOUS store to release its box (a ~2500-clk round trip through the
 //               TMA unit) cost 80 % of the time of the first version of this epilogue.
+//               MERGED = true (bf16-only output, no residual): both 64-column halves of a tile are staged, then ONE proxy fence, ONE
+//               barrier and one bulk group of two stores per tile instead of a fence / barrier / store per half plus a barrier at
+//               the top of the tile (epilogue thread 0's timeline, scripts/gemm_trace.py: 3450 -> 2290 clk per tile).
 // The previous version (one tile per CTA, each thread storing its own row with 16-byte st.global) spent its time in setup
 // latency and 12-wavefront stores: 21-38 us per SuperGlue layer GEMM (profiles/).
 //
@@ -72,10 +75,11 @@ __device__ __forceinline__ void gt_wait_read(int pending) {          // cp.async
   if (pending >= 6) asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory");
   else if (pending >= 4) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
   else if (pending >= 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else if (pending >= 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
   else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <int GT_STAGES, int GT_NBOX>
+template <int GT_STAGES, int GT_NBOX, bool MERGED>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmR,
@@ -194,16 +198,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (lead32 && p.has_r) { issue_r(0); issue_r(1); }
     // bias of a tile is fetched one tile ahead (an exposed L2 round trip + barrier per tile was the longest link of the
     // epilogue's dependency chain) and parked in the double-buffered shared-memory row at the end of the previous tile
-    auto bias_of = [&](int tile) -> float {
-      if (tile >= n_tiles || e >= GT_BN || !p.bias) return 0.f;
-      return __ldg(p.bias + min((tile % tiles_n) * GT_BN + e, p.N - 1));
+    // tile coordinates advance by (gridDim.x / tiles_n, gridDim.x % tiles_n) with a carry: no integer division on the per-tile chain
+    // (the timeline showed ~900 clk per tile between the stamps around the two divisions of the old loop head)
+    const int dq = (int)gridDim.x / tiles_n, dr = (int)gridDim.x % tiles_n;
+    int tm = (int)blockIdx.x / tiles_n, tn = (int)blockIdx.x % tiles_n;
+    auto bias_at = [&](int tile_n, bool exists) -> float {
+      if (!exists || e >= GT_BN || !p.bias) return 0.f;
+      return __ldg(p.bias + min(tile_n * GT_BN + e, p.N - 1));
     };
-    if (e < GT_BN) sBias[e] = bias_of(blockIdx.x);
+    if (e < GT_BN) sBias[e] = bias_at(tn, (int)blockIdx.x < n_tiles);
+    if (MERGED) gt_epi_bar();                                        // bias row of the first tile visible
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const int m0 = (t / tiles_n) * GT_BM, n0 = (t % tiles_n) * GT_BN;
+      const int m0 = tm * GT_BM, n0 = tn * GT_BN;
+      int tn_next = tn + dr, tm_next = tm + dq;
+      if (tn_next >= tiles_n) { tn_next -= tiles_n; ++tm_next; }
       const uint32_t b = i % GT_NACC, bb2 = i & 1;
       float* bs = sBias + bb2 * GT_BN;
-      const float bias_next = bias_of(t + (int)gridDim.x);          // in flight during this tile
+      const float bias_next = bias_at(tn_next, t + (int)gridDim.x < n_tiles);   // in flight during this tile
       // rotary tables of my row: both of my chunks start at column 32 wg of a 64-wide head, i.e. they use the same 16 pairs; the
       // loads are in flight while the accumulator is awaited
       const bool rot = p.rot_cs != nullptr && n0 < p.rot_cols;
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         for (int j = 0; j < 4; ++j) { rc[j] = __ldg(cr + j); rs[j] = __ldg(cr + 8 + j); }
       }
       if (e == 0) GT_STAMP(2, i, 0);
-      gt_epi_bar();                                                  // bias row of this tile visible (written a tile ago)
+      if (!MERGED) gt_epi_bar();                                     // bias row of this tile visible (written a tile ago)
       if (e == 0) GT_STAMP(2, i, 1);
       tc::mbar_wait(&acc_full[b], (i / GT_NACC) & 1);
       if (e == 0) GT_STAMP(2, i, 2);
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             *reinterpret_cast<uint4*>(hb + ((((uint32_t)(wg * 4 + j)) ^ rsw) << 4)) = pk;
           }
         }
+        if (MERGED) continue;                                        // one fence / barrier / store group per TILE, below
         if (!(p.dbg & 2)) tc::fence_proxy_async_smem();              // my staged results -> visible to the TMA engine
         // ring discipline: before anybody writes the next step's boxes, the stores that last used them must have read them.
         //   C32 (two stores per step): next step writes boxes (g0+2, g0+3) % n32, last used by stores g0+2-n32, g0+3-n32; this
@@ -312,6 +324,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
       }
       if (e < GT_BN) sBias[(bb2 ^ 1) * GT_BN + e] = bias_next;         // its previous reader (tile i-1) finished a tile ago
+      if (MERGED) {
+        // bf16-only output without a residual: both 64-column halves of the tile are staged (boxes 2i, 2i + 1 of the ring), then ONE
+        // proxy fence, ONE barrier (which also publishes the next tile's bias row) and one bulk group of two stores per tile.
+        // Ring discipline: the next tile writes boxes (2i + 2, 2i + 3) % n16, last used by the group of tile i + 1 - n16 / 2; this
+        // leader has committed the groups of tiles <= i - 1, so at most n16 / 2 - 2 of them may still be reading.
+        tc::fence_proxy_async_smem();
+        if (e == 0) GT_STAMP(2, i, 4);
+        if (lead16) gt_wait_read(n16 / 2 - 2);
+        gt_epi_bar();
+        if (e == 0) GT_STAMP(2, i, 5);
+        if (lead16) {
+          gt_tma_store_2d(&tmC16, sC16 + ((2 * i) % (uint32_t)n16) * GT_CHUNK_BYTES, n0, m0);
+          gt_tma_store_2d(&tmC16, sC16 + ((2 * i + 1) % (uint32_t)n16) * GT_CHUNK_BYTES, n0 + 64, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tm = tm_next; tn = tn_next;
     }
     if (lead32 || lead16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -401,8 +430,11 @@ static int gemm_tc_launch(const void* A, int lda, const void* W, int ldw, const 
   if (C16) { if (int rc = i4d_make_tmap_2d_bf16(&tmC16, C16, (uint64_t)M, (uint64_t)N, (uint64_t)ldc16, GT_BM, 64)) return rc; }
   static bool attr_seen[64] = {};
   if (i4d_first_use_on_device(attr_seen)) {
-    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(3, 8)));
-    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(5, 4)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(3, 8)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<5, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(5, 4)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<3, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(3, 8)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<4, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(4, 6)));
+    I4D_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<5, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(5, 4)));
   }
   static int dbg = -1, deep_ring = -1;
   if (dbg < 0) { const char* e = getenv("I4D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
@@ -410,10 +442,20 @@ static int gemm_tc_launch(const void* A, int lda, const void* W, int ldw, const 
   GemmTcParams p{M, N, K, alpha, bias, R ? 1 : 0, C32 ? 1 : 0, C16 ? 1 : 0, relu, dbg, rot_cs, rot_cols};
   const int n_tiles = i4d_cdiv(N, GT_BN) * i4d_cdiv(M, GT_BM);
   const int grid = n_tiles < i4d_num_sms() ? n_tiles : i4d_num_sms();
-  if (deep_ring && K >= 512 && C16 && !C32 && !R)       // K = 256: 15.3 us with <5, 4> against 14.9 (the shallower store ring); K = 512: 16.9 against 18.8
-    gemm_tc_kernel<5, 4><<<grid, GT_THREADS, gt_smem_bytes(5, 4), (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
-  else
-    gemm_tc_kernel<3, 8><<<grid, GT_THREADS, gt_smem_bytes(3, 8), (cudaStream_t)stream>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  // bf16-only outputs without a residual (three of the four GEMMs of a GNN layer) take the merged epilogue protocol: <4, 6> for K < 512,
+  // <5, 4> from K = 512 on (16384 x 768: K = 256 12.1 / 12.3 us, K = 512 16.8 / 16.2 us; per-step protocol <3, 8>: 14.8 / 18.4 us).
+  // I4D_GEMM_VARIANT (experiments): 0 = <3, 8> per-step protocol for everything, 1 = <5, 4> per-step, 2 = <3, 8> merged, 3 = <4, 6> merged,
+  // 4 = <5, 4> merged
+  static int variant_env = -2;
+  if (variant_env == -2) { const char* e = getenv("I4D_GEMM_VARIANT"); variant_env = e ? atoi(e) : -1; }
+  const int variant = variant_env >= 0 ? variant_env : (!deep_ring ? 0 : (K >= 512 ? 4 : 3));
+  const bool simple_out = C16 && !C32 && !R;
+  const cudaStream_t cs = (cudaStream_t)stream;
+  if (simple_out && variant == 1) gemm_tc_kernel<5, 4, false><<<grid, GT_THREADS, gt_smem_bytes(5, 4), cs>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  else if (simple_out && variant == 2) gemm_tc_kernel<3, 8, true><<<grid, GT_THREADS, gt_smem_bytes(3, 8), cs>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  else if (simple_out && variant == 3) gemm_tc_kernel<4, 6, true><<<grid, GT_THREADS, gt_smem_bytes(4, 6), cs>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  else if (simple_out && variant == 4) gemm_tc_kernel<5, 4, true><<<grid, GT_THREADS, gt_smem_bytes(5, 4), cs>>>(tmA, tmW, tmR, tmC32, tmC16, p);
+  else gemm_tc_kernel<3, 8, false><<<grid, GT_THREADS, gt_smem_bytes(3, 8), cs>>>(tmA, tmW, tmR, tmC32, tmC16, p);
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }

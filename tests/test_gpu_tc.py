@@ -38,6 +38,11 @@ def test_gemm_tc(tc, M, N, K):
     tc.gemm_tc(big.cuda()[:, :K], W.cuda(), None, out32=out[:, :N])
     assert torch.allclose(out[:, :N].cpu().double(), A.double() @ W.double().t(), atol=2e-4 * K ** 0.5, rtol=1e-5)
     assert float(out[:, N:].abs().max()) == 0.0
+    # bf16-only output (the merged one-barrier-per-tile epilogue), no bias, into a column slice whose neighbours must stay untouched
+    wide = torch.zeros(M, N + 24, device="cuda", dtype=torch.bfloat16)
+    tc.gemm_tc(A.cuda(), W.cuda(), None, out16=wide[:, :N], alpha=0.25)
+    assert torch.allclose(wide[:, :N].cpu().double(), 0.25 * (A.double() @ W.double().t()), atol=0.05, rtol=1e-2)
+    assert float(wide[:, N:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M,N,K", [(4000, 768, 256), (16384, 256, 512), (3333, 520, 128)])
