@@ -501,3 +501,47 @@ extern "C" __attribute__((visibility("default"))) int i4d_f32_to_bf16(const floa
   I4D_CUDA_LAUNCH_CHECK();
   return I4D_OK;
 }
+
+// ---- f32 -> three bf16 column blocks for a split-precision product through the plain bf16 GEMM ------------------------
+// x = hi + lo + O(2^-17 |x|) with hi = bf16(x), lo = bf16(x - hi).  Concatenated along K,
+//   activations  A' = [hi | hi | lo]   (order 0)        weights  W' = [hi | lo | hi]   (order 1)
+// give  A' W'^T = A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T  accumulated in f32 by ONE tensor-core GEMM of depth 3K: the three-product
+// scheme of the SuperPoint convolutions (csrc/conv_tc.cu) for the layers that must keep ~f32 accuracy (SuperGlue's keypoint encoder,
+// thirdparty/SuperGlue/models/superglue.py:51-61,67-78, whose input carries the keypoint positions).
+__global__ void __launch_bounds__(256) f32_split3_bf16_kernel(const float* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
+                                                              int ldy, int rows, int cols, int order) {
+  const int cols4 = cols >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols4) return;
+  const int r = i / cols4, c = (i - r * cols4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + c);
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    hi[k] = __float2bfloat16_rn(x[k]);
+    lo[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+  }
+  uint2 ph, pl;
+  ph.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+  ph.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16);
+  pl.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
+  pl.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16);
+  __nv_bfloat16* y = Y + (size_t)r * ldy + c;
+  *reinterpret_cast<uint2*>(y) = ph;
+  *reinterpret_cast<uint2*>(y + cols) = order == 0 ? ph : pl;
+  *reinterpret_cast<uint2*>(y + 2 * cols) = order == 0 ? pl : ph;
+}
+
+extern "C" __attribute__((visibility("default"))) int i4d_f32_split3_bf16(const float* X, int ldx, void* Y, int ldy, int rows,
+                                                                         int cols, int order, void* stream) {
+  I4D_CHECK_ARG(X && Y && rows >= 0 && cols > 0, "bad arguments");
+  I4D_CHECK_ARG((cols & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 && ldy >= 3 * cols, "cols, ldx, ldy must be multiples of 4 and ldy >= 3 cols");
+  I4D_CHECK_ARG(order == 0 || order == 1, "order must be 0 (activations: hi|hi|lo) or 1 (weights: hi|lo|hi)");
+  if (rows == 0) return I4D_OK;
+  const long long n = (long long)rows * (cols / 4);
+  f32_split3_bf16_kernel<<<i4d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, rows,
+                                                                            cols, order);
+  I4D_CUDA_LAUNCH_CHECK();
+  return I4D_OK;
+}

@@ -124,8 +124,9 @@ class SuperGlueB200:
         if n0 == 0 or n1 == 0:  # superglue.py:255-262
             return (torch.full((n0,), -1, device=dev, dtype=torch.int32), torch.full((n1,), -1, device=dev, dtype=torch.int32),
                     torch.zeros(n0, device=dev), torch.zeros(n1, device=dev))
-        d0 = self.encode(kpts0, sc0, desc0, *shape0)
-        d1 = self.encode(kpts1, sc1, desc1, *shape1)
+        enc = self._tc.encode if self.precision == "bf16" and self._tc.split_kenc else self.encode
+        d0 = enc(kpts0, sc0, desc0, *shape0)
+        d1 = enc(kpts1, sc1, desc1, *shape1)
         if collect is not None:
             collect.append((d0.clone(), d1.clone()))
         if self.precision == "f32":

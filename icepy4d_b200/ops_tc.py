@@ -71,6 +71,15 @@ def to_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split3_bf16(x: torch.Tensor, out: torch.Tensor, weight: bool = False) -> torch.Tensor:
+    """x [n,c] f32 -> out [n,3c] bf16 = [hi | hi | lo] (activations) or [hi | lo | hi] (weights): operands of the three-product
+    split-precision GEMM (one gemm_tc call of depth 3c)."""
+    assert x.dtype == torch.float32 and out.dtype == BF16 and x.stride(1) == 1 and out.stride(1) == 1
+    assert out.shape == (x.shape[0], 3 * x.shape[1])
+    N.call("i4d_f32_split3_bf16", x, x.stride(0), out, out.stride(0), x.shape[0], x.shape[1], int(weight), _st())
+    return out
+
+
 def rotary_cast_bf16(qkv32: torch.Tensor, cs: torch.Tensor, out16: torch.Tensor) -> torch.Tensor:
     """qkv32 [n,768] f32, cs [n,64] -> out16 [n,768] bf16 with the rotary embedding applied to q and k (one pass)."""
     assert qkv32.dtype == torch.float32 and out16.dtype == BF16 and cs.dtype == torch.float32 and cs.is_contiguous()
@@ -86,7 +95,7 @@ def layernorm_gelu_bf16(x32: torch.Tensor, gamma: torch.Tensor, beta: torch.Tens
     return out16
 
 
-N._PER_CALL.update({"i4d_gemm_bf16_tc": 1, "i4d_gemm_bf16_tc_rotary": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1, "i4d_lg_rotary_cast_bf16": 1,
+N._PER_CALL.update({"i4d_f32_split3_bf16": 1, "i4d_gemm_bf16_tc": 1, "i4d_gemm_bf16_tc_rotary": 1, "i4d_attention_bf16_tc": 1, "i4d_f32_to_bf16": 1, "i4d_lg_rotary_cast_bf16": 1,
                     "i4d_layernorm_gelu_bf16": 1})
 
 
@@ -124,10 +133,33 @@ class SuperGlueTensorCore:
             self.layers.append({"wqkv": h(L["wqkv"]), "bqkv": L["bqkv"], "w1": h(w1f), "b1": b1f.contiguous(),
                                 "w2": h(L["w2"]), "b2": L["b2"]})
         self.wf, self.bf = h(w.wf), w.bf
+        # keypoint encoder (superglue.py:51-61,67-78): the two narrow layers (3 -> 32 -> 64) stay on the f32 SIMT GEMM, the three
+        # wide ones (64 -> 128 -> 256 -> 256, 97 % of its flops) run on the tensor cores as three-product split-precision GEMMs
+        # (weights pre-split [hi | lo | hi], activations split [hi | hi | lo] by one small kernel per layer): ~2^-16 relative error,
+        # far inside the bf16 rounding the GNN applies to the encoder's output anyway
+        self.kenc_f32 = list(w.kenc[:2])
+        self.kenc_tc = []
+        for wk, bk in w.kenc[2:]:
+            w3 = torch.empty((wk.shape[0], 3 * wk.shape[1]), device=self.dev, dtype=BF16)
+            split3_bf16(wk.contiguous(), w3, weight=True)
+            self.kenc_tc.append((w3, bk))
+        self.split_kenc = os.environ.get("I4D_SG_KENC_F32", "0") != "1"       # cross-check switch: all five layers on the f32 GEMM
         self._buf = {}
         self._graphs = {}
         self._static_buf = None
         self._counts_ring = _CountsRing()
+
+    def encode(self, kpts, scores, desc, height, width) -> torch.Tensor:
+        """desc + kenc([normalised kpts, score]) -> [n,256] f32 (superglue.py:67-78, 250-254)"""
+        x = ops.sg_kenc_input(kpts, scores, float(width), float(height))
+        for wk, bk in self.kenc_f32:
+            x = ops.gemm_f32(x, wk, bk, relu=True)
+        n = x.shape[0]
+        for i, (w3, bk) in enumerate(self.kenc_tc):
+            last = i == len(self.kenc_tc) - 1
+            a3 = split3_bf16(x, torch.empty((n, 3 * x.shape[1]), device=x.device, dtype=BF16))
+            x = gemm_tc(a3, w3, bk, residual=desc if last else None, out32=torch.empty((n, w3.shape[0]), device=x.device), relu=not last)
+        return x
 
     def _buffers(self, nt):
         if self._buf.get("nt") != nt:

@@ -143,6 +143,11 @@ int i4d_attention_bf16_tc(const void* X, int rows, int ld, int q_col, int k_col,
                           int ldo, void* workspace, size_t workspace_bytes, void* stream);
 /* row-major f32 -> bf16 with leading dimensions (cols % 4 == 0). */
 int i4d_f32_to_bf16(const float* X, int ldx, void* Y, int ldy, int rows, int cols, void* stream);
+/* row-major f32 [rows, cols] -> bf16 [rows, 3 cols]: hi = bf16(x), lo = bf16(x - hi) laid out as [hi | hi | lo] (order 0,
+ * activations) or [hi | lo | hi] (order 1, weights), so that ONE i4d_gemm_bf16_tc of depth 3 cols computes
+ * A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T in f32: the split-precision product for layers that must keep ~f32 accuracy on the tensor
+ * cores (SuperGlue's KeypointEncoder MLP, thirdparty/SuperGlue/models/superglue.py:51-61,67-78).  cols % 4 == 0. */
+int i4d_f32_split3_bf16(const float* X, int ldx, void* Y, int ldy, int rows, int cols, int order, void* stream);
 
 /* ---- assignment --------------------------------------------------------------------------------------- */
 size_t i4d_assignment_workspace_bytes(int M, int N);

@@ -261,3 +261,40 @@ def test_attention_tc_is_bit_reproducible(tc):
         outs.append(out)
     torch.cuda.synchronize()
     assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+@pytest.mark.parametrize("n", [1, 77, 2048, 8192])
+def test_superglue_keypoint_encoder_split_precision_gemms(tc, n):
+    """The wide layers of SuperGlue's KeypointEncoder (superglue.py:51-61,67-78) as three-product split-precision tensor-core GEMMs
+    ([hi|hi|lo] x [hi|lo|hi] through the bf16 GEMM, f32 accumulation) against the f32 SIMT path and an f64 evaluation of the same
+    folded weights: the split path must be as close to f64 as the f32 path is (both ~1e-6 relative), i.e. invisible next to the bf16
+    rounding (4e-3) the GNN applies to the encoder's output."""
+    from icepy4d_b200 import weights
+    from icepy4d_b200.matching.superglue import SuperGlueB200
+    sg = SuperGlueB200(weights.make_superglue_state(2), precision="bf16", sinkhorn_iterations=5)
+    gen = torch.Generator().manual_seed(n)
+    kpts = (torch.rand(n, 2, generator=gen) * torch.tensor([1999.0, 1332.0])).cuda()
+    sc = torch.rand(n, generator=gen).cuda()
+    desc = torch.nn.functional.normalize(torch.randn(n, 256, generator=gen), dim=1).cuda()
+    ref32 = sg.encode(kpts, sc, desc, 1333, 2000)                       # five f32 SIMT GEMMs
+    out = sg._tc.encode(kpts, sc, desc, 1333, 2000)
+    from icepy4d_b200 import ops
+    x = ops.sg_kenc_input(kpts, sc, 2000.0, 1333.0).double()
+    for i, (w, b) in enumerate(sg.w.kenc):
+        x = x @ w.double().t() + b.double()
+        if i < 4:
+            x = torch.relu(x)
+    ref64 = x + desc.double()
+    scale = ref64.abs().max().item()
+    e32 = (ref32.double() - ref64).abs().max().item() / scale
+    e3 = (out.double() - ref64).abs().max().item() / scale
+    assert e32 < 2e-5, e32
+    assert e3 < 2e-5, (e3, e32)
+    # the weight / activation layouts: [hi | lo | hi] and [hi | hi | lo], lo = bf16(x - hi)
+    w = torch.randn(64, 128, generator=gen).cuda()
+    for weight in (False, True):
+        s3 = tc.split3_bf16(w, torch.empty(64, 384, device="cuda", dtype=torch.bfloat16), weight=weight)
+        hi = w.bfloat16()
+        lo = (w - hi.float()).bfloat16()
+        exp = torch.cat([hi, lo, hi] if weight else [hi, hi, lo], 1)
+        assert torch.equal(s3, exp)
