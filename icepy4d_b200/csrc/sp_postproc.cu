@@ -59,11 +59,17 @@ __global__ void __launch_bounds__(128) sp_score_map_kernel(const float* __restri
 // a row (then of a column) from 8 + 2R inputs — 1.75 shared-memory reads per output at R = 3 instead of 7.  Row pass: lane ->
 // row (the row pitch Dp is odd, so the 32 lanes hit 32 different banks); column pass: lane -> column.  `src(i)` reads element i
 // of the [D][Dp] tile, `dst(y, x, m)` consumes the pooled value; positions outside the tile count as -inf.
-template <int R, typename Src, typename Dst>
+// K = position of this pool in the chain of five (1..5): the final mask is needed in the central NMS_T x NMS_T box only, pool k's
+// output therefore in [kR, D - kR)^2 (each later pool reaches R further).  The values inside that box are the ones a full-tile
+// pool would compute (its inputs lie in the previous pool's box), everything outside would never be read.  At R = 3 this is 11
+// rounds of 1024 tasks per tile instead of 20.
+template <int R, int K, typename Src, typename Dst>
 __device__ __forceinline__ void nms_pool(const Src& src, float* __restrict__ T1, const Dst& dst, int D, int Dp) {
-  const int NS = (D + 7) >> 3;
-  for (int task = threadIdx.x; task < D * NS; task += NMS_THREADS) {
-    const int st = task / D, y = task - st * D, x0 = st * 8;
+  const int lo = K * R, hi = D - K * R, w = hi - lo;                      // output box [lo, hi)^2
+  const int ry0 = lo - R, nrows = w + 2 * R;                              // rows of the row pass: [lo - R, hi + R), inside [0, D)
+  const int NS = (w + 7) >> 3;
+  for (int task = threadIdx.x; task < nrows * NS; task += NMS_THREADS) {
+    const int st = task / nrows, y = ry0 + (task - st * nrows), x0 = lo + st * 8;
     float v[8 + 2 * R];
 #pragma unroll
     for (int k = 0; k < 8 + 2 * R; ++k) {
@@ -75,12 +81,12 @@ __device__ __forceinline__ void nms_pool(const Src& src, float* __restrict__ T1,
       float m = v[i];
 #pragma unroll
       for (int k = 1; k <= 2 * R; ++k) m = fmaxf(m, v[i + k]);
-      if (x0 + i < D) T1[y * Dp + x0 + i] = m;
+      if (x0 + i < hi) T1[y * Dp + x0 + i] = m;
     }
   }
   __syncthreads();
-  for (int task = threadIdx.x; task < D * NS; task += NMS_THREADS) {
-    const int st = task / D, x = task - st * D, y0 = st * 8;
+  for (int task = threadIdx.x; task < w * NS; task += NMS_THREADS) {
+    const int st = task / w, x = lo + (task - st * w), y0 = lo + st * 8;
     float v[8 + 2 * R];
 #pragma unroll
     for (int k = 0; k < 8 + 2 * R; ++k) {
@@ -92,11 +98,13 @@ __device__ __forceinline__ void nms_pool(const Src& src, float* __restrict__ T1,
       float m = v[i];
 #pragma unroll
       for (int k = 1; k <= 2 * R; ++k) m = fmaxf(m, v[i + k]);
-      if (y0 + i < D) dst(y0 + i, x, m);
+      if (y0 + i < hi) dst(y0 + i, x, m);
     }
   }
   __syncthreads();
 }
+
+template <int V> struct nms_const { static constexpr int value = V; };
 
 template <int R>
 __global__ void __launch_bounds__(NMS_THREADS) sp_nms_kernel(const float* __restrict__ scores, int H, int W,
@@ -124,21 +132,23 @@ __global__ void __launch_bounds__(NMS_THREADS) sp_nms_kernel(const float* __rest
   NMS_FOR_TILE(y, x, D) S0[y * Dp + x] = inimg(y, x) ? __ldg(scores + (size_t)(ty0 + y) * W + (tx0 + x)) : -INFINITY;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  nms_pool<R>([&](int j) { return S0[j]; }, T1,
-              [&](int y, int x, float m) { M[y * Dp + x] = (inimg(y, x) && S0[y * Dp + x] == m) ? 1 : 0; }, D, Dp);
-  for (int it = 0; it < 2; ++it) {
-    nms_pool<R>([&](int j) { return M[j] ? 1.f : 0.f; }, T1,
+  nms_pool<R, 1>([&](int j) { return S0[j]; }, T1,
+                 [&](int y, int x, float m) { M[y * Dp + x] = (inimg(y, x) && S0[y * Dp + x] == m) ? 1 : 0; }, D, Dp);
+  auto suppress_and_add = [&](auto k_supp, auto k_max) {                  // one iteration of simple_nms (superpoint.py:56-62)
+    nms_pool<R, decltype(k_supp)::value>([&](int j) { return M[j] ? 1.f : 0.f; }, T1,
                 [&](int y, int x, float m) {
                   const bool supp = m > 0.f;
                   P[y * Dp + x] = supp ? 1 : 0;
                   X[y * Dp + x] = inimg(y, x) ? (supp ? 0.f : S0[y * Dp + x]) : -INFINITY;
                 }, D, Dp);
-    nms_pool<R>([&](int j) { return X[j]; }, T1,
+    nms_pool<R, decltype(k_max)::value>([&](int j) { return X[j]; }, T1,
                 [&](int y, int x, float m) {
                   const bool nm = inimg(y, x) && (X[y * Dp + x] == m);
                   if (nm && !P[y * Dp + x]) M[y * Dp + x] = 1;
                 }, D, Dp);
-  }
+  };
+  suppress_and_add(nms_const<2>{}, nms_const<3>{});
+  suppress_and_add(nms_const<4>{}, nms_const<5>{});
   // threshold + border + block-aggregated compaction (X is free now: reuse it as the per-CTA key list)
   // with R >= 1 the surviving maxima are at least R + 1 apart (<= 1024 per tile: 8 KB fits X); R = 0 keeps up to 4096 keys
   // in a dedicated area behind the masks
